@@ -1,0 +1,84 @@
+"""ctypes binding of lib/libr3d_b200.so (include/r3d_b200.h).
+
+This is the ONLY way the package reaches its kernels.  There is no CPU or PyTorch fallback: if the
+library is missing or a kernel fails, the call raises.  Error codes are mapped onto the exception
+types the reference raises at the same boundary (knn.cpp:15-17 -> RuntimeError; bad arguments ->
+ValueError).
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libr3d_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p, c_int, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/r3d_b200.h declares
+SIGNATURES = {
+    "r3d_abi_version": (c_int, []),
+    "r3d_error_string": (ctypes.c_char_p, [c_int]),
+    "r3d_last_cuda_error": (ctypes.c_char_p, []),
+    "r3d_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "r3d_knn": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int,
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "r3d_knn_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r3d_knn_set_variant": (c_int, [c_int]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library.  Raises (loudly) when it has not been built: run
+    ``python -m 3d_recognizer_b200.build`` / ``__graft_entry__.build()``."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.isfile(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built "
+                        "(python 3d_recognizer_b200/build.py). There is no CPU fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                if handle.r3d_abi_version() != 1:
+                    raise RuntimeError("libr3d_b200.so ABI version mismatch; rebuild")
+                _lib = handle
+    return _lib
+
+
+_EXC = {-1: ValueError, -2: RuntimeError, -3: ValueError, -4: ValueError, -5: ValueError, -6: RuntimeError,
+        -7: ValueError}
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    L = lib()
+    msg = L.r3d_error_string(rc).decode()
+    if rc == -6:
+        msg += ": " + L.r3d_last_cuda_error().decode()
+    raise _EXC.get(rc, RuntimeError)(f"{what}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) address of a contiguous tensor, or NULL for None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C-ABI tensors must be contiguous"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 hot path has no CPU fallback")

@@ -1,0 +1,395 @@
+// Exact brute-force K-nearest-neighbour search for sm_100a.
+//
+// Replaces the reference's native extension knn_tpk.knn (randlanet/utils/src/knn.cpp:43-61,
+// neighbors.h:281-322, nanoflann.hpp:1367) and the sqrt of KNN.forward (randlanet/utils/modules.py:149).
+//
+// Contract (include/r3d_b200.h): d2 = fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)), d = query - support
+// (nanoflann.hpp:488-497 built without FMA), neighbours ordered by (d2, index) ascending.
+//
+// Design
+//   * xyz_to_soa_kernel  packs (B,N,3) into three padded rows per cloud (x.., y.., z..), so a tile of
+//     support points is three contiguous, 16-byte aligned segments — the shape a 1-D TMA bulk copy
+//     (cp.async.bulk, SASS UBLKCP) wants.  Pad points carry +inf and can never be admitted.
+//   * knn_kernel: one thread owns Q queries and scans ALL support points in ascending index order.
+//     Support tiles (kTile points) are staged in shared memory by a double-buffered TMA bulk copy
+//     signalled through mbarriers; every lane reads the same support point (smem broadcast), so one
+//     LDS.128 feeds 4 points x Q queries.
+//   * The running K-best of every query lives in a per-thread column of shared memory
+//     ([k][q][thread], conflict free); only the admission threshold stays in a register.  Admission
+//     is strict '<' against the current K-th d2 and insertion is stable, which yields the (d2, index)
+//     order without comparing indices (the scan is ascending).
+//   * FP32-pipe budget.  The hot loop is issue bound, so it evaluates a CHEAP d2 with FMAs
+//     (3 sub + 1 mul + 2 fma) — packed two points per instruction with the Blackwell f32x2 ops in
+//     variant 2 — takes the min over 4 points (FMNMX3) and tests it against a threshold inflated by
+//     2^-20 relative (the FMA form differs from the contract form by < 3 ulp).  Only groups that pass
+//     (rare: K*ln(N/K) admissions per query) re-evaluate the contract d2 with separate roundings
+//     (__fmul_rn/__fadd_rn, never contracted) and run the exact admission test.  The prefilter is
+//     conservative, so results are bit-identical to variant 0, which evaluates the contract form
+//     for every pair.
+#include "common.cuh"
+
+#include <atomic>
+#include <math_constants.h>
+
+namespace r3d {
+
+constexpr int kKnnThreads = 256;
+constexpr int kTile = 2048;  // support points per smem stage (3 rows x 8 KB)
+
+static std::atomic<int> g_knn_variant{2};
+
+// ------------------------------------------------------------------------------------------- pack
+__global__ void xyz_to_soa_kernel(const float* __restrict__ xyz, long long batch_stride, float* __restrict__ soa,
+                                  int N, int Np) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
+    if (i < N) {
+        const float* p = xyz + (size_t)b * batch_stride + (size_t)i * 3;
+        x = p[0];
+        y = p[1];
+        z = p[2];
+    }
+    float* row = soa + (size_t)b * 3 * Np;
+    row[i] = x;
+    row[Np + i] = y;
+    row[2 * Np + i] = z;
+}
+
+// --------------------------------------------------------------------------------- packed helpers
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// the contract distance: three separate roundings, never contracted into FMAs
+__device__ __forceinline__ float d2_contract(float qx, float qy, float qz, float sx, float sy, float sz) {
+    const float dx = __fsub_rn(qx, sx), dy = __fsub_rn(qy, sy), dz = __fsub_rn(qz, sz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+// cheap form for the prefilter (differs from the contract form by < 3 ulp; all terms >= 0)
+__device__ __forceinline__ float d2_cheap(float qx, float qy, float qz, float sx, float sy, float sz) {
+    const float dx = qx - sx, dy = qy - sy, dz = qz - sz;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+__device__ __forceinline__ float inflate(float thr) {
+    // > 3 ulp relative plus an absolute term that covers the subnormal range
+    return fmaf(thr, 0x1p-20f, thr) + 1e-40f;
+}
+
+// stable insertion into an ascending column of shared memory; returns the new K-th d2
+__device__ __noinline__ float list_insert(float* ld, int* li, int K, int stride, float d, int id) {
+    int pos = K - 1;
+    while (pos > 0) {
+        const float pd = ld[(pos - 1) * stride];
+        if (!(pd > d)) break;
+        ld[pos * stride] = pd;
+        li[pos * stride] = li[(pos - 1) * stride];
+        --pos;
+    }
+    ld[pos * stride] = d;
+    li[pos * stride] = id;
+    return ld[(K - 1) * stride];
+}
+
+// ------------------------------------------------------------------------------------- the kernel
+// VARIANT 0: contract d2 for every pair.  1: FMA prefilter, scalar.  2: FMA prefilter, packed f32x2.
+// K1: K == 1, best candidate kept in registers (decoder / post-process 1-NN, modules.py:358).
+template <int VARIANT, int Q, bool K1>
+__global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ sup_soa, int Nsp,
+                                                          const float* __restrict__ query, long long q_stride,
+                                                          int Ns, int Nq, int K,
+                                                          int64_t* __restrict__ idx64, int32_t* __restrict__ idx32,
+                                                          float* __restrict__ dist, float* __restrict__ dist_sq) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);                         // [2][3][kTile]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * 3 * kTile * sizeof(float));
+    float* list_d = reinterpret_cast<float*>(smem_raw + 2 * 3 * kTile * sizeof(float) + 16);
+    int* list_i = reinterpret_cast<int*>(list_d + (size_t)(K1 ? 0 : K) * Q * kKnnThreads);
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const float* sup = sup_soa + (size_t)b * 3 * Nsp;
+    const int num_tiles = (Ns + kTile - 1) / kTile;
+    constexpr int stride = Q * kKnnThreads;
+
+    auto issue = [&](int t) {
+        const int s = t & 1;
+        const int n = min(kTile, Ns - t * kTile);
+        const uint32_t bytes = (uint32_t)((n + 3) & ~3) * sizeof(float);
+        mbar_expect_tx(&bars[s], 3 * bytes);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            tma_bulk_g2s(tile + (s * 3 + c) * kTile, sup + (size_t)c * Nsp + (size_t)t * kTile, bytes, &bars[s]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (num_tiles > 1) issue(1);
+    }
+
+    // ---- per-thread query state
+    float qx[Q], qy[Q], qz[Q], thr[Q], thr_hi[Q];
+    int best_i[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        int qi = blockIdx.x * stride + q * kKnnThreads + tid;
+        qi = min(qi, Nq - 1);
+        const float* p = query + (size_t)b * q_stride + (size_t)qi * 3;
+        qx[q] = p[0];
+        qy[q] = p[1];
+        qz[q] = p[2];
+        thr[q] = CUDART_INF_F;
+        thr_hi[q] = CUDART_INF_F;
+        best_i[q] = -1;
+        if (!K1) {
+            for (int k = 0; k < K; ++k) {
+                list_d[k * stride + q * kKnnThreads + tid] = CUDART_INF_F;
+                list_i[k * stride + q * kKnnThreads + tid] = -1;
+            }
+        }
+    }
+
+    for (int t = 0; t < num_tiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&bars[s], (t >> 1) & 1);
+        const float* xs = tile + (s * 3 + 0) * kTile;
+        const float* ys = tile + (s * 3 + 1) * kTile;
+        const float* zs = tile + (s * 3 + 2) * kTile;
+        const int n = min(kTile, Ns - t * kTile);
+        const int n4 = (n + 3) & ~3;
+        const int base = t * kTile;
+
+#pragma unroll 2
+        for (int j = 0; j < n4; j += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xs + j);
+            const float4 y4 = *reinterpret_cast<const float4*>(ys + j);
+            const float4 z4 = *reinterpret_cast<const float4*>(zs + j);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                float m;
+                if (VARIANT == 2) {
+                    const uint64_t qxx = pk2(qx[q], qx[q]), qyy = pk2(qy[q], qy[q]), qzz = pk2(qz[q], qz[q]);
+                    const uint64_t dx01 = sub2(qxx, pk2(x4.x, x4.y)), dx23 = sub2(qxx, pk2(x4.z, x4.w));
+                    const uint64_t dy01 = sub2(qyy, pk2(y4.x, y4.y)), dy23 = sub2(qyy, pk2(y4.z, y4.w));
+                    const uint64_t dz01 = sub2(qzz, pk2(z4.x, z4.y)), dz23 = sub2(qzz, pk2(z4.z, z4.w));
+                    const uint64_t a01 = fma2(dz01, dz01, fma2(dy01, dy01, mul2(dx01, dx01)));
+                    const uint64_t a23 = fma2(dz23, dz23, fma2(dy23, dy23, mul2(dx23, dx23)));
+                    float a0, a1, a2, a3;
+                    upk2(a01, a0, a1);
+                    upk2(a23, a2, a3);
+                    m = min3(fminf(a0, a1), a2, a3);
+                } else if (VARIANT == 1) {
+                    const float a0 = d2_cheap(qx[q], qy[q], qz[q], x4.x, y4.x, z4.x);
+                    const float a1 = d2_cheap(qx[q], qy[q], qz[q], x4.y, y4.y, z4.y);
+                    const float a2 = d2_cheap(qx[q], qy[q], qz[q], x4.z, y4.z, z4.z);
+                    const float a3 = d2_cheap(qx[q], qy[q], qz[q], x4.w, y4.w, z4.w);
+                    m = min3(fminf(a0, a1), a2, a3);
+                } else {
+                    const float a0 = d2_contract(qx[q], qy[q], qz[q], x4.x, y4.x, z4.x);
+                    const float a1 = d2_contract(qx[q], qy[q], qz[q], x4.y, y4.y, z4.y);
+                    const float a2 = d2_contract(qx[q], qy[q], qz[q], x4.z, y4.z, z4.z);
+                    const float a3 = d2_contract(qx[q], qy[q], qz[q], x4.w, y4.w, z4.w);
+                    m = min3(fminf(a0, a1), a2, a3);
+                }
+                if (m < thr_hi[q]) {
+                    // rare path: exact admission, ascending index order inside the group
+                    for (int u = 0; u < 4; ++u) {
+                        const float d = d2_contract(qx[q], qy[q], qz[q], xs[j + u], ys[j + u], zs[j + u]);
+                        if (d < thr[q]) {
+                            if (K1) {
+                                thr[q] = d;
+                                best_i[q] = base + j + u;
+                            } else {
+                                thr[q] = list_insert(list_d + q * kKnnThreads + tid, list_i + q * kKnnThreads + tid, K,
+                                                     stride, d, base + j + u);
+                            }
+                            thr_hi[q] = (VARIANT == 0) ? thr[q] : inflate(thr[q]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && t + 2 < num_tiles) issue(t + 2);
+    }
+
+    // ---- write-out
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int qi = blockIdx.x * stride + q * kKnnThreads + tid;
+        if (qi >= Nq) continue;
+        const size_t o = ((size_t)b * Nq + qi) * K;
+        for (int k = 0; k < K; ++k) {
+            const float d = K1 ? thr[q] : list_d[k * stride + q * kKnnThreads + tid];
+            const int id = K1 ? best_i[q] : list_i[k * stride + q * kKnnThreads + tid];
+            if (idx64) idx64[o + k] = id;
+            if (idx32) idx32[o + k] = id;
+            if (dist) dist[o + k] = __fsqrt_rn(d);
+            if (dist_sq) dist_sq[o + k] = d;
+        }
+    }
+}
+
+static size_t knn_smem_bytes(int K, int Q, bool k1) {
+    return 2 * 3 * kTile * sizeof(float) + 16 + (k1 ? 0 : (size_t)K * Q * kKnnThreads * 8);
+}
+
+template <int VARIANT, int Q, bool K1>
+static int launch_knn(const float* sup_soa, int Nsp, const float* query, long long q_stride, int B, int Ns, int Nq,
+                      int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq, cudaStream_t st) {
+    auto kern = knn_kernel<VARIANT, Q, K1>;
+    const size_t smem = knn_smem_bytes(K, Q, K1);
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(Nq, Q * kKnnThreads), B);
+    kern<<<grid, kKnnThreads, smem, st>>>(sup_soa, Nsp, query, q_stride, Ns, Nq, K, idx64, idx32, dist, dist_sq);
+    R3D_LAUNCH_CHECK("knn_kernel");
+    return R3D_OK;
+}
+
+template <int VARIANT>
+static int dispatch_q(int Q, bool k1, const float* sup_soa, int Nsp, const float* query, long long q_stride, int B,
+                      int Ns, int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
+                      cudaStream_t st) {
+#define R3D_KNN_CASE(QQ)                                                                                      \
+    if (Q == QQ)                                                                                              \
+        return k1 ? launch_knn<VARIANT, QQ, true>(sup_soa, Nsp, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist,  \
+                                                  dist_sq, st)                                                \
+                  : launch_knn<VARIANT, QQ, false>(sup_soa, Nsp, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist, \
+                                                   dist_sq, st);
+    R3D_KNN_CASE(1)
+    R3D_KNN_CASE(2)
+    R3D_KNN_CASE(4)
+#undef R3D_KNN_CASE
+    return R3D_EINVAL;
+}
+
+static int pick_q(int B, int Nq, int K) {
+    // shared-memory cap: K*Q*256*8 B of lists + 48 KB of tiles must fit 227 KB
+    int qmax = (K <= 16) ? 4 : (K <= 32) ? 2 : 1;
+    // do not starve the 148 SMs when there are few queries
+    const long long total = (long long)B * Nq;
+    int q = qmax;
+    while (q > 1 && total < (long long)kNumSMs * kKnnThreads * q) q >>= 1;
+    return q;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K) {
+    (void)Nq;
+    (void)K;
+    if (B <= 0 || Ns <= 0) return 256;
+    const size_t Nsp = (size_t)((Ns + 3) & ~3);
+    return align_up((size_t)B * 3 * Nsp * sizeof(float), 256) + 256;
+}
+
+extern "C" int r3d_knn_set_variant(int variant) {
+    if (variant < 0 || variant > 2) return g_knn_variant.load();
+    return g_knn_variant.exchange(variant);
+}
+
+extern "C" int r3d_knn(const float* support, long long support_batch_stride, const float* query,
+                       long long query_batch_stride, int B, int Ns, int Nq, int K, int64_t* idx64, int32_t* idx32,
+                       float* dist, float* dist_sq, void* workspace, size_t workspace_bytes, r3d_stream_t stream) {
+    if (B < 0 || Ns < 0 || Nq < 0 || K <= 0) return R3D_EINVAL;
+    if (K > R3D_KNN_KMAX) return R3D_EKMAX;
+    if (Ns < K) return R3D_ENOT_ENOUGH;  // knn.cpp:15-17
+    if (B == 0 || Nq == 0) return R3D_OK;
+    if (!support || !query || !workspace) return R3D_EINVAL;
+    if (!is_aligned(workspace, 256) || !is_aligned(support, 4) || !is_aligned(query, 4)) return R3D_EALIGN;
+    if (workspace_bytes < r3d_knn_workspace_bytes(B, Ns, Nq, K)) return R3D_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (support_batch_stride == 0) support_batch_stride = (long long)Ns * 3;
+    if (query_batch_stride == 0) query_batch_stride = (long long)Nq * 3;
+    if (support_batch_stride < (long long)Ns * 3 || query_batch_stride < (long long)Nq * 3) return R3D_EINVAL;
+
+    const int Nsp = (Ns + 3) & ~3;
+    float* soa = static_cast<float*>(workspace);
+    {
+        dim3 grid(ceil_div(Nsp, 256), B);
+        xyz_to_soa_kernel<<<grid, 256, 0, st>>>(support, support_batch_stride, soa, Ns, Nsp);
+        R3D_LAUNCH_CHECK("xyz_to_soa_kernel");
+    }
+    const bool k1 = (K == 1);
+    const int Q = k1 ? ((long long)B * Nq >= (long long)kNumSMs * kKnnThreads * 4 ? 4 : pick_q(B, Nq, 16))
+                     : pick_q(B, Nq, K);
+    switch (g_knn_variant.load()) {
+        case 0: return dispatch_q<0>(Q, k1, soa, Nsp, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
+                                       dist_sq, st);
+        case 1: return dispatch_q<1>(Q, k1, soa, Nsp, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
+                                       dist_sq, st);
+        default: return dispatch_q<2>(Q, k1, soa, Nsp, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
+                                       dist_sq, st);
+    }
+}
+
+extern "C" int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq, int K, int64_t* idx64,
+                            float* dist_sq) {
+    if (B < 0 || Ns < 0 || Nq < 0 || K <= 0) return R3D_EINVAL;
+    if (K > R3D_KNN_KMAX) return R3D_EKMAX;
+    if (Ns < K) return R3D_ENOT_ENOUGH;
+    if (B == 0 || Nq == 0) return R3D_OK;
+    if (!support || !query || !idx64 || !dist_sq) return R3D_EINVAL;
+    const size_t sb = (size_t)B * Ns * 3 * sizeof(float), qb = (size_t)B * Nq * 3 * sizeof(float);
+    const size_t ib = (size_t)B * Nq * K * sizeof(int64_t), db = (size_t)B * Nq * K * sizeof(float);
+    const size_t wb = r3d_knn_workspace_bytes(B, Ns, Nq, K);
+    const bool self = (support == query && Ns == Nq);
+    unsigned char* dev = nullptr;
+    const size_t o_s = 0, o_q = align_up(sb, 256), o_i = o_q + (self ? 0 : align_up(qb, 256)),
+                 o_d = o_i + align_up(ib, 256), o_w = o_d + align_up(db, 256);
+    R3D_CUDA_TRY(cudaMalloc(&dev, o_w + wb));
+    cudaStream_t st = nullptr;
+    int rc = R3D_OK;
+    cudaError_t e = cudaMemcpyAsync(dev + o_s, support, sb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !self) e = cudaMemcpyAsync(dev + o_q, query, qb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = r3d_knn(reinterpret_cast<float*>(dev + o_s), 0, reinterpret_cast<float*>(dev + (self ? o_s : o_q)), 0, B,
+                     Ns, Nq, K, reinterpret_cast<int64_t*>(dev + o_i), nullptr, nullptr,
+                     reinterpret_cast<float*>(dev + o_d), dev + o_w, wb, st);
+        if (rc == R3D_OK) {
+            e = cudaMemcpyAsync(idx64, dev + o_i, ib, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dist_sq, dev + o_d, db, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        set_cuda_error(e, "r3d_knn_host");
+        return R3D_ECUDA;
+    }
+    return rc;
+}

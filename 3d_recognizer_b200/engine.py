@@ -1,0 +1,158 @@
+"""Execution engine behind ``modules.RandLANet.forward`` (reference: randlanet/utils/modules.py:542-611).
+
+All tensors are POINT-MAJOR: features (B, N, C), neighbourhoods (B, N, K, C).  A point's channels are
+contiguous, so a neighbour gather is one contiguous C-float read and "random down-sampling"
+(modules.py:586-589: the first N/4^l points of the permuted cloud) is a prefix view per cloud.
+
+Two execution paths share this file:
+
+* ``forward_kernels``  — inference (no autograd): hand-written sm_100a kernels through the C ABI for
+  every stage (KNN, fused LocSE + attentive pooling per LFA block, pointwise MLPs, 1-NN up-sampling).
+* ``forward_autograd`` — training / whenever gradients are required: the exact CUDA KNN plus
+  differentiable tensor ops for the rest (being replaced stage by stage by autograd.Functions over
+  backward kernels).
+
+Neither path runs on the CPU; ``ops`` raises if a tensor is not on a CUDA device.
+"""
+from typing import List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def conv_weight_2d(smlp) -> torch.Tensor:
+    """(C_out, C_in) view of a SharedMLP's 1x1 conv weight.  Conv2d stores (C_out,C_in,1,1);
+    ConvTranspose2d stores (C_in,C_out,1,1) (checkpoint schema)."""
+    w = smlp.conv.weight
+    if isinstance(smlp.conv, torch.nn.ConvTranspose2d):
+        return w.view(w.shape[0], w.shape[1]).t()
+    return w.view(w.shape[0], w.shape[1])
+
+
+def _activation(y: torch.Tensor, act) -> torch.Tensor:
+    if act is None:
+        return y
+    if isinstance(act, torch.nn.ReLU):
+        return F.relu(y)
+    if isinstance(act, torch.nn.LeakyReLU):
+        return F.leaky_relu(y, act.negative_slope)
+    return act(y)
+
+
+def batch_norm_lastdim(bn: torch.nn.BatchNorm2d, y: torch.Tensor) -> torch.Tensor:
+    """BatchNorm2d semantics (modules.py:86-90) for a channel-last tensor: statistics over every
+    leading position (B*N or B*N*K), biased variance for normalisation, running stats updated with
+    momentum 0.99 and the unbiased variance in training mode."""
+    c = y.shape[-1]
+    out = F.batch_norm(y.reshape(-1, c), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                       bn.training, bn.momentum, bn.eps)
+    if bn.training and bn.track_running_stats:
+        bn.num_batches_tracked.add_(1)
+    return out.view_as(y)
+
+
+def shared_mlp(smlp, x: torch.Tensor) -> torch.Tensor:
+    """SharedMLP on a channel-last tensor (..., C_in) -> (..., C_out)."""
+    y = F.linear(x, conv_weight_2d(smlp), smlp.conv.bias)
+    if smlp.batch_norm is not None:
+        y = batch_norm_lastdim(smlp.batch_norm, y)
+    return _activation(y, smlp.activation)
+
+
+def gather_points(feat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """feat (B,Ns,C), idx (B,Nq,K) -> (B,Nq,K,C): rows of ``feat`` at the neighbour indices."""
+    B, Ns, C = feat.shape
+    _, Nq, K = idx.shape
+    flat = (idx.long() + (torch.arange(B, device=idx.device) * Ns).view(B, 1, 1)).reshape(-1)
+    return feat.reshape(B * Ns, C).index_select(0, flat).view(B, Nq, K, C)
+
+
+def relative_position_encoding(xyz: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor) -> torch.Tensor:
+    """(B,N,K,10) = [p_i, p_j, p_i - p_j, |p_i - p_j|] (modules.py:170-186)."""
+    pj = gather_points(xyz, idx)
+    pi = xyz.unsqueeze(2).expand_as(pj)
+    return torch.cat((pi, pj, pi - pj, dist.unsqueeze(-1)), dim=-1)
+
+
+def attentive_pooling(pool, x: torch.Tensor) -> torch.Tensor:
+    """x (B,N,K,d) -> (B,N,n_out): softmax over K of Linear(x), weighted sum, SharedMLP
+    (modules.py:246-253)."""
+    scores = F.softmax(F.linear(x, pool.score_fn[0].weight), dim=2)
+    return shared_mlp(pool.mlp, (scores * x).sum(dim=2))
+
+
+def lfa_block(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    """LocalFeatureAggregation (modules.py:298-325): xyz (B,N,3), feat (B,N,n_in) -> (B,N,2d)."""
+    nn_ = ops.knn(xyz, xyz, lfa._n_neighbors, idx64=True, dist=True)
+    idx, dist = nn_["idx64"], nn_["dist"]
+    f = shared_mlp(lfa.mlp1, feat)
+    r1 = shared_mlp(lfa.mlp_rpe1, relative_position_encoding(xyz, idx, dist))
+    p1 = attentive_pooling(lfa.pool1, torch.cat((r1, gather_points(f, idx)), dim=-1))
+    r2 = shared_mlp(lfa.mlp_rpe2, r1)                     # fed by r1, not by the raw encoding (modules.py:321)
+    p2 = attentive_pooling(lfa.pool2, torch.cat((r2, gather_points(p1, idx)), dim=-1))
+    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
+
+
+def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch.Tensor) -> torch.Tensor:
+    """UpSampler (modules.py:343-456) on point-major features: feat (B,N1,F) -> (B,N2,F)."""
+    if approach == "nni":
+        idx = ops.knn(xyz, xyz_up, 1, idx64=True, dist=False)["idx64"]
+        return gather_points(feat, idx).squeeze(2)
+    # "nna" reaches the inverse-distance branch too (default argument, modules.py:372 / :435)
+    power = 2.0 if approach == "isdw" else 1.0
+    nn_ = ops.knn(xyz, xyz_up, 8, idx64=True, dist=True)
+    eps = 1e-7
+    w = (1.0 + eps) / (nn_["dist"] ** power + eps)
+    w = w / w.sum(dim=-1, keepdim=True)
+    return (w.unsqueeze(-1) * gather_points(feat, nn_["idx64"])).sum(dim=2)
+
+
+# ------------------------------------------------------------------------------------ full forward
+def forward_autograd(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
+    s = net.settings
+    dec, L = s.decimation, len(s.layer_sizes)
+    B, N, _ = inp.shape
+    perm = torch.from_numpy(np.ascontiguousarray(permutation)).to(inp.device, non_blocking=True)
+
+    inp = inp.float()
+    feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
+    feat = F.leaky_relu(batch_norm_lastdim(net.bn_start[0], feat), net.bn_start[1].negative_slope)
+    xyz = inp[..., :3].index_select(1, perm).contiguous()
+    feat = feat.index_select(1, perm)
+
+    skips: List[torch.Tensor] = []
+    n_l = N
+    cur = feat
+    for lfa in net.encoder:
+        out = lfa_block(lfa, xyz[:, :n_l], cur)
+        skips.append(out)
+        n_l //= dec
+        cur = out[:, :n_l]
+    cur = shared_mlp(net.mlp, cur)
+    for stage in net.decoder:
+        n_up = skips[-1].shape[1]          # N // dec^(l-1): the encoder level this stage returns to
+        up = upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up])
+        cur = shared_mlp(stage, torch.cat((up, skips.pop()), dim=-1))
+        n_l = n_up
+    inv = torch.argsort(perm)
+    cur = cur.index_select(1, inv)
+    cur = shared_mlp(net.fc_end[0], cur)
+    cur = shared_mlp(net.fc_end[1], cur)
+    cur = F.dropout(cur, net.fc_end[2].p, net.fc_end[2].training)
+    return shared_mlp(net.fc_end[3], cur).transpose(1, 2)
+
+
+def _require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("3d_recognizer_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+
+
+def forward(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
+    if inp.device != net.device:
+        inp = inp.to(net.device)
+    _require_cuda(inp)
+    return forward_autograd(net, inp, permutation)

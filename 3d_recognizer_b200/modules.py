@@ -1,0 +1,225 @@
+"""Drop-in for the reference's ``randlanet.utils.modules`` on the RandLA-Net hot path.
+
+Same class names, constructor signatures, ``forward`` contracts, exceptions and — because the
+parameter holders are real ``Conv2d`` / ``ConvTranspose2d`` / ``BatchNorm2d`` / ``Linear`` modules
+registered in the same order — the same ``state_dict`` (reference: randlanet/utils/modules.py;
+schema in SURVEY.md §5).  What differs is everything underneath:
+
+* every neighbour search goes to the exact CUDA KNN (``r3d_knn``), whatever ``settings.knn`` says
+  (the reference's back-ends are a CPU FAISS IVF index and an inexact matmul form; the native
+  nanoflann extension it was meant to use is orphaned — SURVEY.md F5-F8);
+* ``RandLANet.forward`` does not compose these modules: it hands the whole cloud batch to
+  ``engine.forward`` which runs hand-written sm_100a kernels over point-major (B, N, C) tensors.
+
+The small modules keep a working ``forward`` with the reference's tensor layouts so that code which
+pokes at them individually still runs; they need a CUDA device like everything else here.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import engine, ops
+
+
+@dataclass
+class RandLANetSettings:
+    """Model settings; fields, defaults and validation of the reference (modules.py:10-57)."""
+    n_classes: int
+    n_points: int = 10000
+    n_features: int = 0
+    n_neighbors: int = 32
+    decimation: int = 4
+    layer_sizes: List[int] = field(default_factory=lambda: [16, 64, 128, 256])
+    #: accepted for compatibility ("kdtree" | "approximate" | "naive"); every value runs the exact CUDA KNN
+    knn: str = "approximate"
+    #: post-processing up-sampler: "none" | "nni" | "nna" | "idw" | "isdw"
+    upsampling: str = "nni"
+
+    def __post_init__(self):
+        assert self.knn in ["kdtree", "approximate", "naive"], (
+            f'knn value "{self.knn}" not understood, should be "kdtree", "approximate" or "naive"')
+        assert self.upsampling in ["none", "nni", "nna", "idw", "isdw"], (
+            f'upsampling value "{self.upsampling}" not understood, '
+            'should be "none", "nni", "nna", "idw", or "isdw"')
+
+    def update(self, **kwargs):
+        for key, value in kwargs.items():
+            if hasattr(self, key):
+                setattr(self, key, value)
+
+
+class SharedMLP(torch.nn.Module):
+    """Per-point MLP layer: 1x1 (transposed) convolution + BatchNorm2d(eps=1e-6, momentum=0.99) +
+    optional activation (modules.py:60-104).  Holds the parameters; the engine reads them."""
+
+    def __init__(self, n_in: int, n_out: int, transpose: bool = False, bn: bool = True,
+                 activation: Optional[torch.nn.Module] = None):
+        super().__init__()
+        conv = torch.nn.ConvTranspose2d if transpose else torch.nn.Conv2d
+        self.conv = conv(n_in, n_out, kernel_size=1, stride=1, padding_mode="zeros")
+        self.batch_norm = torch.nn.BatchNorm2d(n_out, eps=1e-6, momentum=0.99) if bn else None
+        self.activation = activation
+        self.transpose = transpose
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        """(B, n_in, N, K) -> (B, n_out, N, K)."""
+        x = input.permute(0, 2, 3, 1)
+        y = engine.shared_mlp(self, x)
+        return y.permute(0, 3, 1, 2)
+
+
+_KNN_APPROACHES = ("kdtree", "approximate", "naive")
+
+
+class KNN(torch.nn.Module):
+    """K nearest neighbours (modules.py:107-150): indices int64 (B,N,K) and distances (NOT squared)."""
+
+    def __init__(self, device: torch.device):
+        super().__init__()
+        self._device = device
+
+    def forward(self, xyz: torch.Tensor, xyz_query: torch.Tensor, n_neighbors: int,
+                approach: str = "approximate") -> Tuple[torch.Tensor, torch.Tensor]:
+        if approach not in _KNN_APPROACHES:
+            raise ValueError(f"KNN approach {approach} not understood!")
+        dev = self._device
+        out = ops.knn(xyz.to(dev), xyz if xyz_query is xyz else xyz_query.to(dev), n_neighbors)
+        return out["idx64"], out["dist"]
+
+
+class RelativePositionEncoding(torch.nn.Module):
+    """cat[p_i, p_j, p_i - p_j, |p_i - p_j|] -> (B,10,N,K) (modules.py:153-186)."""
+
+    def forward(self, xyz: torch.Tensor, neighbors: torch.Tensor, distances: torch.Tensor):
+        return engine.relative_position_encoding(xyz, neighbors, distances).permute(0, 3, 1, 2)
+
+
+class PointFeatureAugmentation(torch.nn.Module):
+    """Neighbour-feature gather concatenated behind the position encoding (modules.py:189-221)."""
+
+    def forward(self, relative_position_encoding: torch.Tensor, features: torch.Tensor,
+                neighbors: torch.Tensor) -> torch.Tensor:
+        nf = engine.gather_points(features.squeeze(-1).transpose(1, 2), neighbors)   # (B,N,K,C)
+        return torch.cat((relative_position_encoding, nf.permute(0, 3, 1, 2)), dim=-3)
+
+
+class AttentivePooling(torch.nn.Module):
+    """softmax_K(Linear(x)) * x summed over K, then a SharedMLP (modules.py:224-253)."""
+
+    def __init__(self, n_in: int, n_out: int):
+        super().__init__()
+        self.score_fn = torch.nn.Sequential(torch.nn.Linear(n_in, n_in, bias=False), torch.nn.Softmax(dim=-2))
+        self.mlp = SharedMLP(n_in, n_out, activation=torch.nn.ReLU())
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        """(B, n_in, N, K) -> (B, n_out, N, 1)."""
+        y = engine.attentive_pooling(self, input.permute(0, 2, 3, 1))
+        return y.transpose(1, 2).unsqueeze(-1)
+
+
+class LocalFeatureAggregation(torch.nn.Module):
+    """Dilated residual block (modules.py:256-325)."""
+
+    def __init__(self, n_in: int, n_out: int, n_neighbors: int, device: torch.device):
+        super().__init__()
+        self._n_neighbors = n_neighbors
+        self._device = device
+        self.mlp1 = SharedMLP(n_in, n_out // 2, activation=torch.nn.LeakyReLU(0.2))
+        self.mlp2 = SharedMLP(n_out, 2 * n_out)
+        self.shortcut = SharedMLP(n_in, 2 * n_out)
+        self.knn = KNN(device)
+        self.rpe = RelativePositionEncoding()
+        self.pfa = PointFeatureAugmentation()
+        self.mlp_rpe1 = SharedMLP(10, n_out // 2, activation=torch.nn.ReLU())
+        self.mlp_rpe2 = SharedMLP(n_out // 2, n_out // 2, activation=torch.nn.ReLU())
+        self.pool1 = AttentivePooling(n_out, n_out // 2)
+        self.pool2 = AttentivePooling(n_out, n_out)
+        self.lrelu = torch.nn.LeakyReLU()
+
+    def forward(self, xyz: torch.Tensor, input: torch.Tensor, knn_approach: str):
+        """xyz (B,N,3), input (B,n_in,N,1) -> (B, 2*n_out, N, 1)."""
+        if knn_approach not in _KNN_APPROACHES:
+            raise ValueError(f"KNN approach {knn_approach} not understood!")
+        y = engine.lfa_block(self, xyz.to(self._device), input.squeeze(-1).transpose(1, 2))
+        return y.transpose(1, 2).unsqueeze(-1)
+
+
+class UpSampler(torch.nn.Module):
+    """Feature up-sampling from a coarse to a fine point set (modules.py:328-456)."""
+
+    def __init__(self, upsampling_approach: str, device: torch.device):
+        super().__init__()
+        self._upsampling_approach = upsampling_approach
+        self._device = device
+        self.knn = KNN(device)
+
+    def forward(self, features: torch.Tensor, xyz: torch.Tensor, xyz_upsampled: torch.Tensor) -> torch.Tensor:
+        """features (B,F,N1,1), xyz (B,N1,3), xyz_upsampled (B,N2,3) -> (B,F,N2,1)."""
+        ap = self._upsampling_approach
+        if ap == "none":
+            return features
+        if ap not in ("nni", "nna", "idw", "isdw"):
+            raise ValueError(f"Upsampling approach {ap} not understood!")
+        dev = self._device
+        y = engine.upsample(ap, features.to(dev).squeeze(-1).transpose(1, 2), xyz.to(dev), xyz_upsampled.to(dev))
+        return y.transpose(1, 2).unsqueeze(-1)
+
+
+class RandLANet(torch.nn.Module):
+    """RandLA-Net (modules.py:459-611): forward((B,N,3+F)) -> logits (B,C,N)."""
+
+    def __init__(self, settings: RandLANetSettings, device: Optional[torch.device] = None):
+        super().__init__()
+        self._settings = settings
+        k = settings.n_neighbors
+        if device is None:
+            device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self._device = device
+        sizes = settings.layer_sizes
+        L = len(sizes)
+        # (1) K points must survive down to the last encoder level; (2) >= 2 points at the bottleneck
+        self._min_n_points = max(k * settings.decimation ** (L - 1), 2 * settings.decimation ** L)
+
+        self.fc_start = torch.nn.Linear(settings.n_features + 3, 8)
+        self.bn_start = torch.nn.Sequential(torch.nn.BatchNorm2d(8, eps=1e-6, momentum=0.99),
+                                            torch.nn.LeakyReLU(0.2))
+        self.encoder = torch.nn.ModuleList()
+        width = 8
+        for d in sizes:
+            self.encoder.append(LocalFeatureAggregation(width, d, k, device))
+            width = 2 * d
+        self.mlp = SharedMLP(width, width, activation=torch.nn.ReLU())
+        self.upsampling = UpSampler("nni", device)
+        self.decoder = torch.nn.ModuleList()
+        width *= 2      # skip connection concatenated in front of each decoder stage
+        for d in sizes[::-1][1:]:
+            self.decoder.append(SharedMLP(width, 2 * d, transpose=True, activation=torch.nn.ReLU()))
+            width = 4 * d
+        self.decoder.append(SharedMLP(width, 8, transpose=True, activation=torch.nn.ReLU()))
+        self.fc_end = torch.nn.Sequential(
+            SharedMLP(8, 64, activation=torch.nn.ReLU()),
+            SharedMLP(64, 32, activation=torch.nn.ReLU()),
+            torch.nn.Dropout(),
+            SharedMLP(32, settings.n_classes, bn=False),
+        )
+        self.to(self._device)
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def settings(self) -> RandLANetSettings:
+        return self._settings
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        B, N, dim = input.size()
+        assert dim == 3 + self._settings.n_features, "Input should have shape (B, N, 3 + F)!"
+        assert N >= self._min_n_points, f"Input point cloud should have at least {self._min_n_points} points!"
+        # the one host-side draw that defines "random down-sampling" for the whole batch: same RNG,
+        # same call, same point in the forward as the reference (modules.py:571)
+        permutation = np.random.permutation(N)
+        return engine.forward(self, input, permutation)

@@ -1,0 +1,84 @@
+/*
+ * r3d_b200.h — C ABI of the B200-native RandLA-Net hot path (3d_recognizer drop-in).
+ *
+ * One shared library, lib/libr3d_b200.so, built from 3d_recognizer_b200/csrc/ for sm_100a.
+ * Plain pointers and sizes only; no torch / pybind types.  The reference's FFI for this path
+ * is the pybind11 module `knn_tpk` (randlanet/utils/src/bindings.cpp:5-7); everything else on the
+ * path is Python calling torch ops (randlanet/utils/modules.py), so the remaining entry points
+ * mirror the reference's operator boundaries one to one (file:line cited per function).
+ *
+ * Conventions (all functions):
+ *   - return 0 on success or a negative R3D_E* code; r3d_error_string() names it.  The Python
+ *     host (3d_recognizer_b200/_cabi.py) maps codes to the reference's exception types.
+ *   - "*_host" entry points take HOST buffers, own their device memory and synchronise: they are
+ *     the drop-in for a CPU-tensor FFI call such as knn_tpk.knn.
+ *   - every other entry point takes DEVICE pointers on the current device, never allocates,
+ *     frees or synchronises, and launches on `stream` (a cudaStream_t passed as void*).  The
+ *     caller allocates outputs and the workspace (size from the matching *_workspace_bytes).
+ *   - tensors are dense row-major with the layouts written beside each argument; float = fp32.
+ *   - no global mutable state: safe from several host threads and from a spawned process
+ *     (reference: train.py:108-115 trains in a spawned child, main.py:71-89 predicts on the Tk thread).
+ */
+#ifndef R3D_B200_H
+#define R3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_ABI_VERSION 1
+
+#define R3D_OK 0
+#define R3D_EINVAL (-1)        /* null pointer / negative size / bad enum          -> ValueError   */
+#define R3D_ENOT_ENOUGH (-2)   /* Ns < K  (knn.cpp:15-17 TORCH_CHECK)               -> RuntimeError */
+#define R3D_EKMAX (-3)         /* K larger than the compiled maximum (R3D_KNN_KMAX) -> ValueError   */
+#define R3D_EALIGN (-4)        /* pointer not aligned as documented                 -> ValueError   */
+#define R3D_EWORKSPACE (-5)    /* workspace too small                               -> ValueError   */
+#define R3D_ECUDA (-6)         /* CUDA runtime error (see r3d_last_cuda_error)      -> RuntimeError */
+#define R3D_EUNSUPPORTED (-7)  /* shape outside what the kernels are built for      -> ValueError   */
+
+#define R3D_KNN_KMAX 64
+
+typedef void* r3d_stream_t; /* cudaStream_t */
+
+int r3d_abi_version(void);
+const char* r3d_error_string(int code);
+/* text of the last CUDA error seen by THIS thread inside the library ("" if none) */
+const char* r3d_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------ KNN
+ * Replaces knn_tpk.knn(support, querry, k) (bindings.cpp:5-7 -> knn.cpp:43-61 -> neighbors.h:281-322
+ * -> nanoflann.hpp:1367) and folds KNN.forward's sqrt (modules.py:149).
+ * Exact search.  d2 = fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) with d = query - support
+ * (nanoflann.hpp:488-497 compiled without FMA); neighbours ordered by (d2, index) ascending, i.e.
+ * exact ties go to the LOWER support index, also at the K-th boundary.  Coordinates must be finite.
+ *
+ *   support (B,Ns,3)  query (B,Nq,3)           fp32; query may alias support (self search).
+ *       *_batch_stride: floats between consecutive clouds (0 = dense, i.e. N*3).  A stride larger
+ *       than N*3 addresses the first N points of longer clouds — the "random down-sampling = prefix
+ *       of the permuted cloud" views of RandLANet.forward (modules.py:586-589, :596-597) — without a copy.
+ *   idx64   (B,Nq,K)  int64   nullable        (the reference's index dtype)
+ *   idx32   (B,Nq,K)  int32   nullable        (what the fused kernels below consume)
+ *   dist    (B,Nq,K)  fp32    nullable        sqrt(d2)   — what KNN.forward returns
+ *   dist_sq (B,Nq,K)  fp32    nullable        d2         — what knn_tpk.knn returns
+ * workspace: r3d_knn_workspace_bytes(), 256-byte aligned.
+ */
+size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K);
+int r3d_knn(const float* support, long long support_batch_stride, const float* query,
+            long long query_batch_stride, int B, int Ns, int Nq, int K,
+            int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
+            void* workspace, size_t workspace_bytes, r3d_stream_t stream);
+/* host-buffer drop-in for knn_tpk.knn: (idx int64, d2 fp32), both (B,Nq,K), caller-allocated. */
+int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq, int K,
+                 int64_t* idx64, float* dist_sq);
+/* tuning hook for benchmarks/tests: 0 exact scalar, 1 FMA-prefilter scalar, 2 FMA-prefilter
+ * packed f32x2 (default).  All variants return identical results.  Returns the previous value. */
+int r3d_knn_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3D_B200_H */

@@ -1,0 +1,129 @@
+"""CPU tests of the host-side logic (no GPU): checkpoint schema, settings validation, and the
+engine's tensor plumbing (point-major layouts, permutation, prefix down-sampling, decoder wiring)
+checked against the golden vectors produced by the REFERENCE modules (oracle/make_golden.py).
+
+The product has no CPU path: to exercise the host logic here the CUDA KNN entry point is replaced,
+in this test only, by the oracle KNN, and the CUDA-device guard is lifted."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import network as onet
+from oracle.knn import knn_exact
+
+E2E = {
+    "k16_n1024": (dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=16, knn="naive"), 2, 1024, 11),
+    "k32_n2500": (dict(n_classes=2, n_points=2500, n_features=0, n_neighbors=32, knn="naive"), 1, 2500, 12),
+    "k16_f2_c3_n1100": (dict(n_classes=3, n_points=1100, n_features=2, n_neighbors=16, knn="approximate"), 2, 1100, 13),
+}
+
+
+def make_input(B, N, F, seed):
+    rng = np.random.RandomState(seed)
+    x = rng.rand(B, N, 3 + F).astype(np.float32)
+    x[..., :3] = x[..., :3] * np.array([0.78, 0.61, 0.55], np.float32) + np.array([-0.44, -0.31, 0.05], np.float32)
+    return x
+
+
+@pytest.fixture()
+def cpu_product(monkeypatch, r3d):
+    ops = importlib.import_module("3d_recognizer_b200.ops")
+    engine = importlib.import_module("3d_recognizer_b200.engine")
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+
+    def knn_stub(support, query, k, idx64=True, idx32=False, dist=True, dist_sq=False):
+        i, d2 = knn_exact(support.detach().numpy(), query.detach().numpy(), k)
+        out = {}
+        if idx64:
+            out["idx64"] = torch.from_numpy(i)
+        if idx32:
+            out["idx32"] = torch.from_numpy(i.astype(np.int32))
+        if dist:
+            out["dist"] = torch.sqrt(torch.from_numpy(d2))
+        if dist_sq:
+            out["dist_sq"] = torch.from_numpy(d2)
+        return out
+
+    monkeypatch.setattr(ops, "knn", knn_stub)
+    monkeypatch.setattr(engine, "_require_cuda", lambda t: None)
+    return modules
+
+
+def test_settings_validation(r3d):
+    m = importlib.import_module("3d_recognizer_b200.modules")
+    s = m.RandLANetSettings(n_classes=2)
+    assert (s.n_points, s.n_neighbors, s.decimation, s.layer_sizes, s.knn, s.upsampling) == \
+        (10000, 32, 4, [16, 64, 128, 256], "approximate", "nni")
+    with pytest.raises(AssertionError):
+        m.RandLANetSettings(n_classes=2, knn="ball")
+    with pytest.raises(AssertionError):
+        m.RandLANetSettings(n_classes=2, upsampling="cubic")
+    s.update(n_points=5, bogus=1)
+    assert s.n_points == 5 and not hasattr(s, "bogus")
+
+
+@pytest.mark.parametrize("name", list(E2E))
+def test_state_dict_schema_matches_reference(r3d, name):
+    m = importlib.import_module("3d_recognizer_b200.modules")
+    st = E2E[name][0]
+    net = m.RandLANet(m.RandLANetSettings(**st), torch.device("cpu"))
+    sd = net.state_dict()
+    schema = onet.state_dict_schema(st)        # verified == the reference's state_dict in make_golden.py
+    assert list(sd.keys()) == list(schema.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == schema[k][0] and v.dtype == schema[k][1], k
+    if st["n_features"] == 0 and st["n_classes"] == 2:
+        assert sum(p.numel() for p in net.parameters()) == 1322666
+        assert len(sd) == 262 and len(list(net.parameters())) == 154
+
+
+def test_forward_asserts(cpu_product):
+    m = cpu_product
+    net = m.RandLANet(m.RandLANetSettings(n_classes=2, n_neighbors=16), torch.device("cpu"))
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 1024, 4))
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 1023, 3))          # min = max(16*64, 2*256) = 1024
+
+
+@pytest.mark.parametrize("name", list(E2E))
+def test_engine_host_logic_vs_reference_golden(cpu_product, name):
+    m = cpu_product
+    g = np.load(os.path.join(GOLDEN, "e2e_golden.npz"))
+    st, B, N, seed = E2E[name]
+    net = m.RandLANet(m.RandLANetSettings(**st), torch.device("cpu"))
+    net.load_state_dict(onet.synth_state_dict(st, seed))
+    x = torch.from_numpy(make_input(B, N, st["n_features"], seed))
+    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, st["n_classes"], (B, N)))
+
+    net.eval()
+    np.random.seed(seed)
+    with torch.no_grad():
+        logits = net(x)
+    ref = torch.from_numpy(g[f"{name}/eval_logits"])
+    assert logits.shape == ref.shape
+    assert (logits - ref).abs().max() / ref.abs().max() < 1e-4
+
+    net.train()
+    net.fc_end[2].p = 0.0
+    np.random.seed(seed)
+    logits = net(x)
+    ref = torch.from_numpy(g[f"{name}/train_logits"])
+    assert (logits - ref).abs().max() / ref.abs().max() < 1e-4
+    loss = onet.dice_loss(logits, labels)
+    assert abs(loss.item() - float(g[f"{name}/train_loss"])) < 1e-5
+    net.zero_grad()
+    loss.backward()
+    got = {k: onet.grad_fixture_view(p.grad) for k, p in net.named_parameters()}
+    refg = {k: torch.from_numpy(g[f"{name}/grad/{k}"]) for k in got}
+    worst, wname = onet.grad_parity(got, refg)
+    assert worst < 1e-4, (worst, wname)
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert np.allclose(v.numpy(), g[f"{name}/after/{k}"], rtol=1e-4, atol=1e-5), k
+        if "num_batches_tracked" in k:
+            assert int(v) == 8
