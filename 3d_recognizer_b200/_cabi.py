@@ -24,12 +24,40 @@ SIGNATURES = {
     "r3d_abi_version": (c_int, []),
     "r3d_error_string": (ctypes.c_char_p, [c_int]),
     "r3d_last_cuda_error": (ctypes.c_char_p, []),
+    "r3d_launch_count": (ctypes.c_ulonglong, []),
     "r3d_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "r3d_knn": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_knn_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r3d_knn_set_variant": (c_int, [c_int]),
+    "r3d_fp32_probe_floats": (c_size_t, []),
+    "r3d_fp32_probe": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(ctypes.c_double), c_void_p]),
 }
+
+
+# ---- per-kernel device timing (bench.py's roofline): when KERNEL_TIMERS is a dict, every ops wrapper
+# brackets its C-ABI call with CUDA events on the launching stream and files them under a kernel name.
+KERNEL_TIMERS = None
+
+
+class kernel_timer:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name, **work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if KERNEL_TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMERS is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            KERNEL_TIMERS.setdefault(self.name, []).append((self.e0, e1, self.work))
+        return False
 
 
 def lib() -> ctypes.CDLL:

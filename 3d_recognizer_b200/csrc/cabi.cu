@@ -1,11 +1,15 @@
 // C-ABI plumbing shared by all entry points: version, error strings, per-thread CUDA error text.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
 namespace r3d {
 static thread_local char tls_cuda_error[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_cuda_error(cudaError_t e, const char* where) {
     std::snprintf(tls_cuda_error, sizeof(tls_cuda_error), "%s: %s (%s)", where, cudaGetErrorString(e),
@@ -15,6 +19,8 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }  // namespace r3d
 
 extern "C" int r3d_abi_version(void) { return R3D_ABI_VERSION; }
+
+extern "C" unsigned long long r3d_launch_count(void) { return r3d::g_launches.load(); }
 
 extern "C" const char* r3d_last_cuda_error(void) { return r3d::tls_cuda_error; }
 

@@ -7,6 +7,7 @@
 namespace r3d {
 
 void set_cuda_error(cudaError_t e, const char* where);
+void count_launch();  // every kernel launch of the library is counted (r3d_launch_count)
 
 #define R3D_CUDA_TRY(expr)                                  \
     do {                                                    \
@@ -19,6 +20,7 @@ void set_cuda_error(cudaError_t e, const char* where);
 
 #define R3D_LAUNCH_CHECK(what)                              \
     do {                                                    \
+        ::r3d::count_launch();                              \
         cudaError_t _e = cudaGetLastError();                \
         if (_e != cudaSuccess) {                            \
             ::r3d::set_cuda_error(_e, what);                \

@@ -1,0 +1,281 @@
+// Per-point ("shared") MLP layers for sm_100a: y = act(scale * (W [xa ; xb]) + shift).
+//
+// Replaces every SharedMLP / Linear on single points of the reference
+// (randlanet/utils/modules.py:60-104 SharedMLP; call sites :314 mlp1, :325 mlp2 + shortcut, :253 pool
+// MLPs, :565-566 fc_start + bn_start, :591 bottleneck, :594-605 decoder, :610 fc_end) together with the
+// tensor shuffling the reference does around them:
+//   * row gather on source A  — the decoder's 1-NN up-sampling gather (modules.py:359-363), the
+//     permutation at the start (:572-573) and the inverse permutation at the end (:608);
+//   * concatenation of a second source B — the decoder skip concat (modules.py:600-602) and, with the
+//     BN scales folded into the weights, the residual sum mlp2(p2) + shortcut(input) (:325).
+// Eval-mode BatchNorm (eps 1e-6) is an affine map, folded by the host into (scale, shift) or directly
+// into W; train-mode layers run with scale = NULL/identity and write the pre-BN tensor.
+//
+// Layout: point-major.  Source rows are contiguous C floats; clouds are `*_bstride` floats apart so
+// that a prefix view [:, :n] of a longer cloud needs no copy.  Weights come transposed, wT (Cin, Cout).
+//
+// Two kernels:
+//   pw_gemm_kernel<TM,TN>  register-tiled FP32 GEMM (8x8 per thread, operands staged in shared memory
+//                          transposed so both are read with LDS.128) for Cout >= 16;
+//   pw_small_kernel        one thread per row for Cout <= 16 (fc_start 3->8, last decoder stage,
+//                          class logits): HBM-bound streaming.
+#include "common.cuh"
+
+namespace r3d {
+
+struct PwArgs {
+    const float* xa;
+    long long xa_bstride;
+    int ca;
+    const int32_t* gidx;       // nullable; row n of cloud b reads xa row gidx[b*gidx_bstride + n]
+    long long gidx_bstride;    // 0 => the same index vector for every cloud
+    const float* xb;           // nullable second source
+    long long xb_bstride;
+    int cb;
+    const float* wT;           // (ca+cb, cout)
+    const float* scale;        // nullable (cout)
+    const float* shift;        // nullable (cout)
+    int act;                   // 0 none, 1 relu, 2 leaky relu
+    float slope;
+    float* y;
+    long long y_bstride;
+    int y_ld;                  // floats between consecutive output rows (>= cout): lets a layer write a channel slice
+    int cout;
+    int B;
+    int n;                     // rows per cloud
+    int transpose_out;         // 1: write y as (B, cout, n) — the reference's logits layout (modules.py:611)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+
+__device__ __forceinline__ const float* src_row(const PwArgs& a, int b, int n, bool second) {
+    if (second) return a.xb + (size_t)b * a.xb_bstride + (size_t)n * a.cb;
+    int r = n;
+    if (a.gidx) r = a.gidx[(size_t)b * a.gidx_bstride + n];
+    return a.xa + (size_t)b * a.xa_bstride + (size_t)r * a.ca;
+}
+
+// ------------------------------------------------------------------------------------ GEMM kernel
+constexpr int kPwKC = 16;  // input channels per staged chunk
+
+template <int TM, int TN>
+__global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) {
+    constexpr int NT = (TM / 8) * (TN / 8);
+    constexpr int TMP = TM + 4;
+    __shared__ __align__(16) float As[kPwKC][TMP];
+    __shared__ __align__(16) float Ws[kPwKC][TN];
+
+    const int tid = threadIdx.x;
+    const int tr = tid / (TN / 8);   // row group
+    const int tc = tid % (TN / 8);   // col group: cols tc*4 + {0..3} and TN/2 + tc*4 + {0..3}
+    const long long M = (long long)a.B * a.n;
+    const long long m0 = (long long)blockIdx.x * TM;
+    const int n0 = blockIdx.y * TN;
+    const int cin = a.ca + a.cb;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // each thread stages A elements (row r, 4 consecutive channels): index i -> c4 = i % 4, r = i / 4
+    constexpr int A_ITEMS = TM * (kPwKC / 4);
+    constexpr int W_ITEMS = kPwKC * TN / 4;
+
+    for (int c0 = 0; c0 < cin; c0 += kPwKC) {
+        // ---- stage A chunk (transposed into [c][row])
+        for (int i = tid; i < A_ITEMS; i += NT) {
+            const int c4 = i % (kPwKC / 4), r = i / (kPwKC / 4);
+            const long long m = m0 + r;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < M) {
+                const int b = (int)(m / a.n), n = (int)(m % a.n);
+                const int c = c0 + c4 * 4;
+                // a 4-channel group never straddles the A/B boundary when ca % 4 == 0 (checked by the host);
+                // otherwise fall back to scalar selection
+                if ((a.ca & 3) == 0 && (a.cb & 3) == 0) {
+                    if (c < cin) {
+                        const bool second = c >= a.ca;
+                        const float* row = src_row(a, b, n, second);
+                        const float4 t = *reinterpret_cast<const float4*>(row + (second ? c - a.ca : c));
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int cc = c + u;
+                        if (cc < cin) {
+                            const bool second = cc >= a.ca;
+                            v[u] = src_row(a, b, n, second)[second ? cc - a.ca : cc];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) As[c4 * 4 + u][r] = v[u];
+        }
+        // ---- stage W chunk
+        for (int i = tid; i < W_ITEMS; i += NT) {
+            const int kk = i / (TN / 4), j4 = i % (TN / 4);
+            const int c = c0 + kk, col = n0 + j4 * 4;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < cin) {
+                const float* wr = a.wT + (size_t)c * a.cout;
+                if ((a.cout & 3) == 0 && col + 3 < a.cout) {
+                    t = *reinterpret_cast<const float4*>(wr + col);
+                } else {
+                    if (col + 0 < a.cout) t.x = wr[col + 0];
+                    if (col + 1 < a.cout) t.y = wr[col + 1];
+                    if (col + 2 < a.cout) t.z = wr[col + 2];
+                    if (col + 3 < a.cout) t.w = wr[col + 3];
+                }
+            }
+            *reinterpret_cast<float4*>(&Ws[kk][j4 * 4]) = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kPwKC; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tr * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][tr * 8 + 4]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][tc * 4]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][TN / 2 + tc * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int col = n0 + h * (TN / 2) + tc * 4;
+        float sc[4], sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = col + j < a.cout;
+            sc[j] = (a.scale && ok) ? a.scale[col + j] : 1.f;
+            sh[j] = (a.shift && ok) ? a.shift[col + j] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long m = m0 + tr * 8 + i;
+            if (m >= M) continue;
+            const int b = (int)(m / a.n), n = (int)(m % a.n);
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = apply_act(fmaf(acc[i][h * 4 + j], sc[j], sh[j]), a.act, a.slope);
+            if (a.transpose_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < a.cout) a.y[(size_t)b * a.y_bstride + (size_t)(col + j) * a.n + n] = o[j];
+            } else {
+                float* yr = a.y + (size_t)b * a.y_bstride + (size_t)n * a.y_ld;
+                if (col + 3 < a.cout && (a.y_ld & 3) == 0 && (a.y_bstride & 3) == 0) {
+                    *reinterpret_cast<float4*>(yr + col) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < a.cout) yr[col + j] = o[j];
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- small kernel
+// Cout <= 16: one thread per output row; weights (cin x cout) live in shared memory.
+constexpr int kPwSmallMaxCout = 16;
+constexpr int kPwSmallMaxW = 4096;  // floats of weights staged in smem (cin*cout <= 4096)
+
+__global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
+    __shared__ float Ws[kPwSmallMaxW];
+    const int cin = a.ca + a.cb;
+    for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x) Ws[i] = a.wT[i];
+    __syncthreads();
+    const long long M = (long long)a.B * a.n;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int b = (int)(m / a.n), n = (int)(m % a.n);
+    float acc[kPwSmallMaxCout];
+#pragma unroll
+    for (int j = 0; j < kPwSmallMaxCout; ++j) acc[j] = 0.f;
+    const float* ra = src_row(a, b, n, false);
+    for (int c = 0; c < a.ca; ++c) {
+        const float x = ra[c];
+#pragma unroll
+        for (int j = 0; j < kPwSmallMaxCout; ++j)
+            if (j < a.cout) acc[j] = fmaf(x, Ws[c * a.cout + j], acc[j]);
+    }
+    if (a.cb > 0) {
+        const float* rb = src_row(a, b, n, true);
+        for (int c = 0; c < a.cb; ++c) {
+            const float x = rb[c];
+#pragma unroll
+            for (int j = 0; j < kPwSmallMaxCout; ++j)
+                if (j < a.cout) acc[j] = fmaf(x, Ws[(a.ca + c) * a.cout + j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kPwSmallMaxCout; ++j) {
+        if (j >= a.cout) break;
+        const float sc = a.scale ? a.scale[j] : 1.f, sh = a.shift ? a.shift[j] : 0.f;
+        const float o = apply_act(fmaf(acc[j], sc, sh), a.act, a.slope);
+        if (a.transpose_out)
+            a.y[(size_t)b * a.y_bstride + (size_t)j * a.n + n] = o;
+        else
+            a.y[(size_t)b * a.y_bstride + (size_t)n * a.y_ld + j] = o;
+    }
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
+                             long long gidx_bstride, const float* xb, long long xb_bstride, int cb, const float* wT,
+                             const float* scale, const float* shift, int act, float slope, float* y,
+                             long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
+                             r3d_stream_t stream) {
+    if (B < 0 || n < 0 || ca <= 0 || cb < 0 || cout <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (B == 0 || n == 0) return R3D_OK;
+    if (!xa || !wT || !y || (cb > 0 && !xb)) return R3D_EINVAL;
+    if (y_ld == 0) y_ld = cout;
+    if (y_ld < cout) return R3D_EINVAL;
+    if (xa_bstride == 0) xa_bstride = (long long)n * ca;
+    if (xb_bstride == 0) xb_bstride = (long long)n * cb;
+    if (y_bstride == 0) y_bstride = transpose_out ? (long long)cout * n : (long long)n * y_ld;
+    if (!is_aligned(xa, 16) || (xb && !is_aligned(xb, 16)) || !is_aligned(wT, 16) || !is_aligned(y, 16))
+        return R3D_EALIGN;
+    // vector loads need every source row 16-byte aligned
+    if ((ca % 4 == 0 && cb % 4 == 0) && ((xa_bstride % 4) || (cb > 0 && (xb_bstride % 4)))) return R3D_EALIGN;
+    PwArgs a{xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
+             y, y_bstride, y_ld, cout, B, n, transpose_out};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long M = (long long)B * n;
+    if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
+        pw_small_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(a);
+        R3D_LAUNCH_CHECK("pw_small_kernel");
+        return R3D_OK;
+    }
+    if (cout <= 32) {
+        dim3 grid((unsigned)((M + 255) / 256), (cout + 31) / 32);
+        pw_gemm_kernel<256, 32><<<grid, 128, 0, st>>>(a);
+    } else if (cout <= 64 || M < 64 * 148) {
+        dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
+        pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)((M + 63) / 64), (cout + 127) / 128);
+        pw_gemm_kernel<64, 128><<<grid, 128, 0, st>>>(a);
+    }
+    R3D_LAUNCH_CHECK("pw_gemm_kernel");
+    return R3D_OK;
+}

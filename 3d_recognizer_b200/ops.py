@@ -58,10 +58,12 @@ def knn(support: torch.Tensor, query: torch.Tensor, k: int, *, idx64: bool = Tru
             out["dist_sq"] = torch.empty((B, Nq, k), dtype=torch.float32, device=dev)
         wbytes = L.r3d_knn_workspace_bytes(B, Ns, Nq, k)
         ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
-        rc = L.r3d_knn(ctypes.c_void_p(support.data_ptr()), s_stride, ctypes.c_void_p(query.data_ptr()), q_stride,
-                       B, Ns, Nq, k,
-                       _cabi.ptr(out.get("idx64")), _cabi.ptr(out.get("idx32")), _cabi.ptr(out.get("dist")),
-                       _cabi.ptr(out.get("dist_sq")), _cabi.ptr(ws), wbytes, _cabi.stream_ptr(dev))
+        with _cabi.kernel_timer("knn_k1" if k == 1 else "knn", flops=8.0 * B * Ns * Nq,
+                                bytes=4.0 * B * (3 * Ns + 3 * Nq + Nq * k * (len(out) + ("idx64" in out)))):
+            rc = L.r3d_knn(ctypes.c_void_p(support.data_ptr()), s_stride, ctypes.c_void_p(query.data_ptr()),
+                           q_stride, B, Ns, Nq, k,
+                           _cabi.ptr(out.get("idx64")), _cabi.ptr(out.get("idx32")), _cabi.ptr(out.get("dist")),
+                           _cabi.ptr(out.get("dist_sq")), _cabi.ptr(ws), wbytes, _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_knn")
     return out
 

@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of this repo.
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0.  A "step" is one pass of the RandLA-Net hot path over one batch of synthetic
+clouds.  Workloads (BASELINE.json `configs`):
+
+  train2500   (default; configs[1]) training step — forward + dice loss + backward + Adam — on a
+              fingertip-style batch of 8 clouds x 2 500 points (train.py:50-56 cloud size), K=16,
+              4 encoder levels [16,64,128,256], per GPU (weak scaling; NCCL gradient all-reduce at N>1)
+  train40960  (configs[3]) the same step on 40 960-point clouds, global batch 64 split over the GPUs
+  infer16k | infer64k | infer256k   (configs[2]) eval forward, global batch 32 split over the GPUs
+  knn1m_k16 | knn1m_k32             (configs[4]) 1 M x 1 M exact KNN micro-benchmark (1 GPU)
+
+`value`  : points/sec (queries/sec for knn*) with the batch already resident in HBM.
+`e2e`    : the same through the public API (Model.train_step / Model.predict / ops.knn_host) with HOST
+           buffers: pinned host -> device copy of the batch and a device -> host read of the result
+           inside the timed region, every step.
+`--impl reference` times the reference's own CPU implementation of the same step on the host cores
+(the oracle port of randlanet/utils/modules.py driven by the exact KNN; nanoflann from oracle/_ref for
+the KNN micro-benchmark when it was built) on a bounded sample of the workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, n_points, K, global_batch or None (=> per-GPU batch below), per_gpu_batch)
+    "train2500": dict(kind="train", n=2500, k=16, per_gpu_batch=8, scaling="weak"),
+    "train40960": dict(kind="train", n=40960, k=16, global_batch=64, scaling="strong"),
+    "infer16k": dict(kind="infer", n=16384, k=16, global_batch=32, scaling="strong"),
+    "infer64k": dict(kind="infer", n=65536, k=16, global_batch=32, scaling="strong"),
+    "infer256k": dict(kind="infer", n=262144, k=16, global_batch=32, scaling="strong"),
+    "knn1m_k16": dict(kind="knn", n=1 << 20, k=16, per_gpu_batch=1, scaling="weak"),
+    "knn1m_k32": dict(kind="knn", n=1 << 20, k=32, per_gpu_batch=1, scaling="weak"),
+}
+SETTINGS = dict(n_classes=2, n_features=0, decimation=4, layer_sizes=[16, 64, 128, 256], knn="naive",
+                upsampling="nni")
+L2_FLUSH_BYTES = 256 << 20        # > the 126 MB L2
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def dist_setup(n_gpus):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, world) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def timed_steps(step_fn, steps, warmup, world, flush):
+    """W untimed warm-up steps, then exactly K steps, each bracketed by CUDA events on the current
+    stream with an L2 flush in between (outside the events); barrier + synchronize on both sides.
+    Returns (sum of the K step times in ms — max over ranks, wall seconds of the whole region)."""
+    for i in range(warmup):
+        step_fn(i)
+    barrier(world)
+    evs = []
+    t0 = time.perf_counter()
+    for i in range(steps):
+        flush.add_(1.0)                       # writes 256 MB: evicts the previous step from L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_fn(warmup + i)
+        e1.record()
+        evs.append((e0, e1))
+    barrier(world)
+    wall = time.perf_counter() - t0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    return max_over_ranks(total_ms, world), wall
+
+
+def measure_fp32_peak(cabi):
+    """Live FP32-pipe peak (TFLOP/s) from the library's probe kernel: best of 3, scalar FFMA and FFMA2."""
+    import ctypes
+    L = cabi.lib()
+    out = torch.empty(L.r3d_fp32_probe_floats(), dtype=torch.float32, device="cuda")
+    res = {}
+    for mode, name in ((0, "ffma"), (1, "ffma2")):
+        flops = ctypes.c_double(0)
+        best = None
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cabi.check(L.r3d_fp32_probe(mode, 4000, cabi.ptr(out), ctypes.byref(flops), cabi.stream_ptr(out.device)),
+                       "r3d_fp32_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if it > 0:
+                best = ms if best is None else min(best, ms)
+        res[name] = flops.value / best * 1e-9
+    return res
+
+
+def kernel_table(timers):
+    """name -> dict(launches, ms_total, ms_avg, flops, bytes) from the C-ABI wrappers' event pairs."""
+    tab = {}
+    for name, lst in timers.items():
+        ms = [a.elapsed_time(b) for a, b, _ in lst]
+        tab[name] = dict(launches=len(lst), ms_total=sum(ms), ms_avg=sum(ms) / len(ms),
+                         flops=sum(w.get("flops", 0.0) for _, _, w in lst) / len(lst),
+                         bytes=sum(w.get("bytes", 0.0) for _, _, w in lst) / len(lst))
+    return tab
+
+
+def roofline_of(tab, peaks, fp32_peak):
+    """Roofline entry of the dominant kernel (largest share of the timed region)."""
+    if not tab:
+        return None
+    name = max(tab, key=lambda n: tab[n]["ms_total"])
+    k = tab[name]
+    t_s = k["ms_avg"] * 1e-3
+    t_hbm = k["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    t_fp32 = k["flops"] / (fp32_peak["ffma"] * 1e12)
+    if t_fp32 >= t_hbm:
+        ach = k["flops"] / t_s * 1e-12
+        return dict(kernel=name, bound="fp32", achieved=ach, peak=fp32_peak["ffma"], unit="TFLOP/s",
+                    frac=ach / fp32_peak["ffma"], traffic=None, launches=k["launches"], ms_avg=k["ms_avg"],
+                    peak_source="FFMA probe kernel measured in this run (r3d_fp32_probe); FFMA2 packed: %.1f"
+                                % fp32_peak["ffma2"],
+                    algorithmic_flops_per_launch=k["flops"], algorithmic_bytes_per_launch=k["bytes"])
+    ach = k["bytes"] / t_s * 1e-9
+    return dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                traffic=None, launches=k["launches"], ms_avg=k["ms_avg"], peak_source=peaks["source"],
+                algorithmic_flops_per_launch=k["flops"], algorithmic_bytes_per_launch=k["bytes"])
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_train_or_infer(kind, n, k, batch, budget_s, max_steps, seed=0):
+    """The reference's CPU implementation of one step (oracle port of modules.py + exact KNN, torch
+    intra-op threads = all host cores).  Returns (points/sec, steps run, batch used, cores)."""
+    from oracle import network as onet
+    syn = importlib.import_module("3d_recognizer_b200.synthetic")
+    losses = importlib.import_module("3d_recognizer_b200.losses")
+    st = dict(SETTINGS, n_points=n, n_neighbors=k)
+    sd = onet.synth_state_dict(st, seed)
+    params = []
+    if kind == "train":
+        for name, t in sd.items():
+            if t.is_floating_point() and "running" not in name:
+                t.requires_grad_(True)
+                params.append(t)
+        opt = torch.optim.Adam(params, lr=1e-2)
+    x, lab = syn.fingertip_batch(seed, batch, n, n_raw=max(150_000, 2 * n))
+    x, lab = torch.from_numpy(x), torch.from_numpy(lab)
+    crit = losses.get_loss("dice")
+    times = []
+    t_start = time.perf_counter()
+    for i in range(max_steps + 1):                    # first step is warm-up
+        t0 = time.perf_counter()
+        if kind == "train":
+            logits = onet.forward(sd, st, x, training=True)
+            loss = crit(logits, lab)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                onet.forward(sd, st, x, training=False)
+        dt = time.perf_counter() - t0
+        if i > 0:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    return batch * n / statistics.mean(times), len(times), batch, torch.get_num_threads()
+
+
+def cpu_knn(n, k, budget_s):
+    """KNN queries/sec on the host: the reference's nanoflann extension (oracle/_ref, single threaded by
+    construction, knn.cpp:53) when it was built, else the oracle brute force on all cores; on a bounded
+    sample of the queries against the full 1 M support."""
+    from oracle import knn as oknn
+    syn = importlib.import_module("3d_recognizer_b200.synthetic")
+    s = syn.uniform_clouds(0, 1, n)
+    nq = 100_000 if oknn.have_ref() else 2_000
+    q = syn.uniform_clouds(1, 1, nq)
+    t0 = time.perf_counter()
+    if oknn.have_ref():
+        oknn.ref_knn_tpk(s, q, k)
+        kind, cores = "reference", 1
+    else:
+        oknn.knn_exact(s, q, k)
+        kind, cores = "port", os.cpu_count()
+    dt = time.perf_counter() - t0
+    return nq / dt, kind, cores, f"{nq} queries against the full {n}-point support (tree build included)"
+
+
+def run_reference(args, wl, name):
+    """--impl reference: rank 0 only, host cores only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.set_num_threads(os.cpu_count())
+    if wl["kind"] == "knn":
+        v, kind, cores, sample = cpu_knn(wl["n"], wl["k"], 30)
+        unit, metric = "queries/s", "knn_queries_per_sec"
+        ms = 1e3 * wl["n"] / v
+        cfg = dict(workload=name, n_points=wl["n"], k=wl["k"])
+    else:
+        gb = wl.get("global_batch") or wl["per_gpu_batch"] * world
+        b = min(gb, 8 if wl["n"] <= 4096 else 1)
+        v, nsteps, b, cores = cpu_train_or_infer(wl["kind"], wl["n"], wl["k"], b, 25 * max(1, args.steps) / 5,
+                                                 max(1, args.steps))
+        kind = "port"
+        sample = f"{nsteps} step(s) of batch {b} x {wl['n']} points after 1 warm-up"
+        unit = "points/s"
+        metric = "train_step_points_per_sec" if wl["kind"] == "train" else "forward_points_per_sec"
+        ms = 1e3 * b * wl["n"] / v
+        cfg = dict(workload=name, n_points=wl["n"], k=wl["k"], global_batch=gb, layer_sizes=SETTINGS["layer_sizes"])
+    line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling=wl["scaling"], vs_baseline=None,
+                dtype="f32", data="synthetic", config=cfg,
+                cpu_baseline=dict(value=v, unit=unit, cores=cores, kind=kind, sample=sample),
+                e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="train2500", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    name = args.workload
+    wl = WORKLOADS[name]
+    if args.impl == "reference":
+        return run_reference(args, wl, name)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); use --impl reference for the CPU arm")
+    rank, local, world = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    cabi = importlib.import_module("3d_recognizer_b200._cabi")
+    ops = importlib.import_module("3d_recognizer_b200.ops")
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+    model_mod = importlib.import_module("3d_recognizer_b200.model")
+    parallel = importlib.import_module("3d_recognizer_b200.parallel")
+    syn = importlib.import_module("3d_recognizer_b200.synthetic")
+    L = cabi.lib()
+    peaks = load_peaks()
+    flush = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+
+    n, k = wl["n"], wl["k"]
+    if "global_batch" in wl:
+        lo, hi = parallel.shard_range(wl["global_batch"], rank, world)
+        batch, gbatch = hi - lo, wl["global_batch"]
+    else:
+        batch, gbatch = wl["per_gpu_batch"], wl["per_gpu_batch"] * world
+    fp32_peak = measure_fp32_peak(cabi)
+    extras = {}
+
+    if wl["kind"] == "knn":
+        metric, unit = "knn_queries_per_sec", "queries/s"
+        s_h = torch.from_numpy(syn.uniform_clouds(2 * rank, batch, n)).pin_memory()
+        q_h = torch.from_numpy(syn.uniform_clouds(2 * rank + 1, batch, n)).pin_memory()
+        s_d, q_d = s_h.to(dev), q_h.to(dev)
+        units_per_step = batch * n
+
+        def dev_step(i):
+            ops.knn(s_d, q_d, k, idx64=True, dist=False, dist_sq=True)
+
+        def e2e_step(i):
+            ops.knn_host(s_h.numpy(), q_h.numpy(), k)
+
+        h2d, d2h = 2 * batch * n * 12, batch * n * k * 12
+    else:
+        st = modules.RandLANetSettings(**dict(SETTINGS, n_points=n, n_neighbors=k))
+        torch.manual_seed(0)
+        model = model_mod.Model(st, device=dev)
+        parallel.broadcast_parameters(model.module)
+        pool = 4
+        data = [syn.fingertip_batch(1000 * rank + j, batch, n, n_raw=max(150_000, 2 * n)) for j in range(pool)]
+        x_h = [torch.from_numpy(x).pin_memory() for x, _ in data]
+        y_h = [torch.from_numpy(y).pin_memory() for _, y in data]
+        x_d = [x.to(dev) for x in x_h]
+        y_d = [y.to(dev) for y in y_h]
+        units_per_step = batch * n
+        unit = "points/s"
+        if wl["kind"] == "train":
+            metric = "train_step_points_per_sec"
+            opt = model.make_optimizer(1e-2)
+            flat = parallel.FlatGradients(model.module) if world > 1 else None
+            sink = torch.zeros((), device=dev)
+
+            def dev_step(i):
+                sink.copy_(model.train_step(x_d[i % pool], y_d[i % pool], opt, "dice", flat))
+
+            def e2e_step(i):
+                loss = model.train_step(x_h[i % pool], y_h[i % pool], opt, "dice", flat)
+                loss.item()                                            # D2H read of the step's result
+
+            h2d, d2h = batch * n * (12 + 8), 4
+        else:
+            metric = "forward_points_per_sec"
+            model.module.eval()
+            res_h = torch.empty((batch, 2, n), dtype=torch.float32).pin_memory()
+
+            def dev_step(i):
+                with torch.no_grad():
+                    model.module(x_d[i % pool])
+
+            def e2e_step(i):
+                with torch.no_grad():
+                    logits = model.module(x_h[i % pool].to(dev, non_blocking=True))
+                    res_h.copy_(logits, non_blocking=True)
+                torch.cuda.synchronize()
+
+            h2d, d2h = batch * n * 12, batch * n * 2 * 4
+
+    # ---- device-resident timed region (value) with per-kernel timers and launch counting
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    cabi.KERNEL_TIMERS = {}
+    launches0 = L.r3d_launch_count()
+    with ClockSampler(local) as clk:
+        total_ms, wall = timed_steps(dev_step, args.steps, 1, world, flush)
+    launches = L.r3d_launch_count() - launches0
+    launches -= launches // (args.steps + 1)                  # the one extra untimed step inside timed_steps
+    tab = kernel_table(cabi.KERNEL_TIMERS)
+    cabi.KERNEL_TIMERS = None
+    ms_per_step = total_ms / args.steps
+    value = sum_over_ranks(units_per_step, world) / (ms_per_step * 1e-3)
+    clocks = clk.summary()
+
+    # ---- end-to-end through the public API with host buffers
+    e2e_ms, _ = timed_steps(e2e_step, args.steps, 2, world, flush)
+    e2e_value = sum_over_ranks(units_per_step, world) / (e2e_ms / args.steps * 1e-3)
+
+    # the timers saw warm-up launches of timed_steps too: scale totals to the K timed steps
+    for kname in tab:
+        tab[kname]["ms_per_step"] = tab[kname]["ms_total"] / (args.steps + 1)
+        tab[kname]["share_of_step"] = tab[kname]["ms_per_step"] / ms_per_step
+    roof = roofline_of(tab, peaks, fp32_peak)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        if wl["kind"] == "knn":
+            v, kind, cores, sample = cpu_knn(n, k, 30)
+            cpu_base = dict(value=v, unit=unit, cores=cores, kind=kind, sample=sample)
+        else:
+            b = min(batch, 8 if n <= 4096 else 1)
+            v, nsteps, b, cores = cpu_train_or_infer(wl["kind"], n, k, b, 15, 8)
+            cpu_base = dict(value=v, unit=unit, cores=cores, kind="port",
+                            sample=f"{nsteps} step(s) of batch {b} x {n} points after 1 warm-up, oracle port of "
+                                   "randlanet/utils/modules.py + exact KNN, torch threads = all host cores")
+
+    if rank == 0:
+        line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling=wl["scaling"], vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=name, n_points=n, k=k, global_batch=gbatch, per_gpu_batch=batch,
+                                layer_sizes=SETTINGS["layer_sizes"], l2="flushed between steps (256 MB write)",
+                                parallelism=f"dp{world}" + (" + NCCL grad all-reduce" if wl["kind"] == "train" and world > 1 else "")),
+                    e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base,
+                    kernels={kn: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in kv.items()}
+                             for kn, kv in tab.items()},
+                    fp32_peak_tflops=fp32_peak, wall_s_timed_region=wall, extras=extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

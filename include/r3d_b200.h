@@ -48,6 +48,8 @@ int r3d_abi_version(void);
 const char* r3d_error_string(int code);
 /* text of the last CUDA error seen by THIS thread inside the library ("" if none) */
 const char* r3d_last_cuda_error(void);
+/* number of kernels this library has launched in this process so far (bench.py's gpu_launches) */
+unsigned long long r3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------ KNN
  * Replaces knn_tpk.knn(support, querry, k) (bindings.cpp:5-7 -> knn.cpp:43-61 -> neighbors.h:281-322
@@ -77,6 +79,13 @@ int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq
 /* tuning hook for benchmarks/tests: 0 exact scalar, 1 FMA-prefilter scalar, 2 FMA-prefilter
  * packed f32x2 (default).  All variants return identical results.  Returns the previous value. */
 int r3d_knn_set_variant(int variant);
+
+/* ------------------------------------------------------------------------------ FP32 peak probe
+ * Roofline denominator of the CUDA-core kernels, measured live by bench.py (MEASURED_PEAKS.json has
+ * HBM and bf16 tensor peaks only).  mode 0 = scalar FFMA, 1 = packed FFMA2 (f32x2).  `out` is a device
+ * buffer of r3d_fp32_probe_floats() floats; *flops (host, nullable) receives the launch's flop count. */
+size_t r3d_fp32_probe_floats(void);
+int r3d_fp32_probe(int mode, int iters, float* out, double* flops, r3d_stream_t stream);
 
 #ifdef __cplusplus
 }
