@@ -30,6 +30,12 @@ SIGNATURES = {
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_knn_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r3d_knn_set_variant": (c_int, [c_int]),
+    "r3d_lfa_pool": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_pointwise": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
+                              ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
+                              c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_fp32_probe_floats": (c_size_t, []),
     "r3d_fp32_probe": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(ctypes.c_double), c_void_p]),
 }
@@ -101,6 +107,11 @@ def ptr(t):
         return None
     assert t.is_contiguous(), "C-ABI tensors must be contiguous"
     return ctypes.c_void_p(t.data_ptr())
+
+
+def raw(t):
+    """Address of a tensor whose strides are passed separately (row-contiguous views)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
 def stream_ptr(device) -> ctypes.c_void_p:

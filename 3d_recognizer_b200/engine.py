@@ -151,8 +151,133 @@ def _require_cuda(t: torch.Tensor) -> None:
         raise RuntimeError("3d_recognizer_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
 
 
+# ------------------------------------------------------------------- inference path: C-ABI kernels only
+def _fold(smlp):
+    """Eval-mode SharedMLP -> (wT (Cin,Cout), scale (Cout), shift (Cout)): y = scale*(W x) + shift with the
+    conv bias and the BatchNorm running statistics (eps 1e-6, modules.py:87) folded in."""
+    w = conv_weight_2d(smlp).detach()
+    bias = smlp.conv.bias.detach()
+    bn = smlp.batch_norm
+    if bn is None:
+        return w.t().contiguous(), torch.ones_like(bias), bias.clone()
+    scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() + (bias - bn.running_mean) * scale
+    return w.t().contiguous(), scale.contiguous(), shift.contiguous()
+
+
+def _act_of(smlp):
+    a = smlp.activation
+    if a is None:
+        return None, 0.0
+    if isinstance(a, torch.nn.ReLU):
+        return "relu", 0.0
+    if isinstance(a, torch.nn.LeakyReLU):
+        return "lrelu", float(a.negative_slope)
+    raise ValueError(f"unsupported activation {a}")
+
+
+def _state_version(net) -> tuple:
+    return tuple(t._version for t in net.state_dict(keep_vars=True).values())
+
+
+def folded_parameters(net) -> dict:
+    """Kernel-ready eval-mode parameters, cached on the module and rebuilt when any parameter or buffer
+    changed (tensor version counters)."""
+    ver = _state_version(net)
+    cache = getattr(net, "_r3d_folded", None)
+    if cache is not None and cache["version"] == ver:
+        return cache
+    with torch.no_grad():
+        c = {"version": ver}
+        bn0 = net.bn_start[0]
+        s0 = bn0.weight * torch.rsqrt(bn0.running_var + bn0.eps)
+        c["start"] = (net.fc_start.weight.t().contiguous(), s0.contiguous(),
+                      (bn0.bias + (net.fc_start.bias - bn0.running_mean) * s0).contiguous())
+        enc = []
+        for lfa in net.encoder:
+            e = {}
+            e["mlp1"] = _fold(lfa.mlp1)
+            w1T, a1, b1 = _fold(lfa.mlp_rpe1)
+            e["rpe1"] = (w1T.t().contiguous(), a1, b1)                      # (h,10) [out][in]
+            e["rpe2"] = _fold(lfa.mlp_rpe2)                                 # wT (h,h) [in][out]
+            e["score1"] = lfa.pool1.score_fn[0].weight.detach().t().contiguous()
+            e["score2"] = lfa.pool2.score_fn[0].weight.detach().t().contiguous()
+            e["pool1"] = _fold(lfa.pool1.mlp)
+            e["pool2"] = _fold(lfa.pool2.mlp)
+            # residual sum mlp2(p2) + shortcut(x) as ONE layer over [p2 ; x]: BN scales folded into W
+            w2T, s2, t2 = _fold(lfa.mlp2)
+            wsT, ss, ts = _fold(lfa.shortcut)
+            e["res"] = (torch.cat((w2T * s2, wsT * ss), dim=0).contiguous(), None, (t2 + ts).contiguous())
+            enc.append(e)
+        c["encoder"] = enc
+        c["mlp"] = _fold(net.mlp)
+        c["decoder"] = [_fold(m) for m in net.decoder]
+        c["end0"] = _fold(net.fc_end[0])
+        c["end1"] = _fold(net.fc_end[1])
+        c["end3"] = _fold(net.fc_end[3])
+    net._r3d_folded = c
+    return c
+
+
+def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
+    """Eval-mode forward on the sm_100a kernels only: per LFA block one KNN, two fused LocSE+pooling
+    launches and four per-point layers; per decoder stage one 1-NN and one gather+concat+MLP launch."""
+    s = net.settings
+    dec, k = s.decimation, s.n_neighbors
+    B, N, _ = inp.shape
+    P = folded_parameters(net)
+    dev = inp.device
+    perm64 = torch.from_numpy(np.ascontiguousarray(permutation)).to(dev, non_blocking=True)
+    perm = perm64.to(torch.int32)
+    inp = inp.float().contiguous()
+
+    # fc_start + bn_start + LeakyReLU(0.2) fused with the point permutation (modules.py:565-573)
+    w, sc, sh = P["start"]
+    cur = ops.pointwise(inp, w, sc, sh, "lrelu", 0.2, gidx=perm)
+    xyz = inp[..., :3].index_select(1, perm64).contiguous()
+
+    skips: List[torch.Tensor] = []
+    n_l = N
+    for lfa, e in zip(net.encoder, P["encoder"]):
+        x = cur[:, :n_l]
+        xyz_l = xyz[:, :n_l]
+        idx = ops.knn(xyz_l, xyz_l, k, idx64=False, idx32=True, dist=False)["idx32"]
+        w, sc, sh = e["mlp1"]
+        f = ops.pointwise(x, w, sc, sh, "lrelu", 0.2)
+        w1, a1, b1 = e["rpe1"]
+        w2T, a2, b2 = e["rpe2"]
+        pooled = ops.lfa_pool(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1"])
+        w, sc, sh = e["pool1"]
+        p1 = ops.pointwise(pooled, w, sc, sh, "relu")
+        pooled = ops.lfa_pool(2, xyz_l, idx, p1, w1, a1, b1, w2T, a2, b2, e["score2"])
+        w, sc, sh = e["pool2"]
+        p2 = ops.pointwise(pooled, w, sc, sh, "relu")
+        w, sc, sh = e["res"]
+        cur = ops.pointwise(p2, w, sc, sh, "lrelu", 0.01, xb=x)
+        skips.append(cur)
+        n_l //= dec
+    w, sc, sh = P["mlp"]
+    cur = ops.pointwise(cur[:, :n_l], w, sc, sh, "relu")
+    for w, sc, sh in P["decoder"]:
+        skip = skips.pop()
+        n_up = skip.shape[1]
+        nn1 = ops.knn(xyz[:, :n_l], xyz[:, :n_up], 1, idx64=False, idx32=True, dist=False)["idx32"]
+        cur = ops.pointwise(cur, w, sc, sh, "relu", gidx=nn1.view(B, n_up), xb=skip)
+        n_l = n_up
+    inv = torch.empty_like(perm)
+    inv[perm64] = torch.arange(N, dtype=torch.int32, device=dev)
+    w, sc, sh = P["end0"]
+    cur = ops.pointwise(cur, w, sc, sh, "relu", gidx=inv)              # inverse permutation (modules.py:608)
+    w, sc, sh = P["end1"]
+    cur = ops.pointwise(cur, w, sc, sh, "relu")
+    w, sc, sh = P["end3"]                                              # Dropout is the identity in eval mode
+    return ops.pointwise(cur, w, sc, sh, None, transpose_out=True)
+
+
 def forward(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
     if inp.device != net.device:
         inp = inp.to(net.device)
     _require_cuda(inp)
+    if not net.training and not torch.is_grad_enabled():
+        return forward_kernels(net, inp, permutation)
     return forward_autograd(net, inp, permutation)

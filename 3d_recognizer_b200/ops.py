@@ -83,3 +83,79 @@ def knn_host(support: np.ndarray, query: np.ndarray, k: int) -> Tuple[np.ndarray
                                   k, ctypes.c_void_p(idx.ctypes.data), ctypes.c_void_p(d2.ctypes.data))
     _cabi.check(rc, "r3d_knn_host")
     return idx, d2
+
+
+def _rows_view(x: torch.Tensor):
+    """(tensor, batch stride in floats) for a (B,n,C) fp32 tensor with contiguous rows; prefix views
+    x[:, :n] of a dense tensor pass through without a copy."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, n, C = x.shape
+    if B == 0 or n == 0:
+        return x.contiguous(), 0
+    ok = x.stride(2) == 1 and x.stride(1) == C and (B == 1 or x.stride(0) >= n * C)
+    if not ok:
+        x = x.contiguous()
+    return x, (x.stride(0) if B > 1 else n * C)
+
+
+def lfa_pool(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Tensor, w_rpe1, a_rpe1, b_rpe1,
+             w_rpe2T, a_rpe2, b_rpe2, w_scoreT) -> torch.Tensor:
+    """Fused LocSE + attentive pooling of one LFA half (C ABI ``r3d_lfa_pool``; modules.py:316-323).
+    xyz (B,N,3), idx32 (B,N,K) int32, feat (B,N,h) -> pooled (B,N,d), d = 2h."""
+    _cabi.require_cuda(xyz, "xyz")
+    xyz, xs = _cloud_view(xyz)
+    feat, fs = _rows_view(feat.detach())
+    B, N, K = idx32.shape
+    h = feat.shape[2]
+    d = 2 * h
+    dev = xyz.device
+    pooled = torch.empty((B, N, d), dtype=torch.float32, device=dev)
+    # algorithmic work per point (SURVEY.md §8a): flops 2K(10h + d^2 + d) [+ 2K h^2 in stage 2]
+    flops = float(B) * N * (2 * K * (10 * h + d * d + d + (h * h if stage == 2 else 0)))
+    nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_pool(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
+                                      _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T),
+                                      _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_scoreT), _cabi.ptr(pooled),
+                                      B, N, K, d, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_pool")
+    return pooled
+
+
+_ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2}
+
+
+def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=None, slope: float = 0.0,
+              gidx: Optional[torch.Tensor] = None, xb: Optional[torch.Tensor] = None, n_rows: Optional[int] = None,
+              transpose_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-point layer y = act(scale * (W [xa[g] ; xb]) + shift) (C ABI ``r3d_pointwise``).
+    xa (B,na,ca) [gathered through gidx int32 (n,) shared or (B,n) per cloud], xb (B,n,cb) optional,
+    wT (ca+cb, cout).  Returns (B,n,cout), or (B,cout,n) with ``transpose_out``."""
+    _cabi.require_cuda(xa, "xa")
+    xa, xas = _rows_view(xa.detach())
+    B, na, ca = xa.shape
+    n = n_rows if n_rows is not None else (gidx.shape[-1] if gidx is not None else na)
+    cb, xbs = 0, 0
+    if xb is not None:
+        xb, xbs = _rows_view(xb.detach())
+        cb = xb.shape[2]
+        assert xb.shape[1] >= n
+    cout = wT.shape[1]
+    assert wT.shape[0] == ca + cb and wT.is_contiguous()
+    dev = xa.device
+    if out is None:
+        out = torch.empty((B, cout, n) if transpose_out else (B, n, cout), dtype=torch.float32, device=dev)
+    gs = 0
+    if gidx is not None:
+        assert gidx.dtype == torch.int32 and gidx.is_contiguous()
+        gs = 0 if gidx.dim() == 1 else gidx.stride(0)
+    flops = 2.0 * B * n * (ca + cb) * cout
+    nbytes = 4.0 * B * n * (ca + cb + cout)
+    with torch.cuda.device(dev), _cabi.kernel_timer("pointwise", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_pointwise(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
+                                       _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act], float(slope),
+                                       _cabi.ptr(out), 0, 0, cout, B, n, 1 if transpose_out else 0,
+                                       _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_pointwise")
+    return out

@@ -80,6 +80,47 @@ int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq
  * packed f32x2 (default).  All variants return identical results.  Returns the previous value. */
 int r3d_knn_set_variant(int variant);
 
+/* ------------------------------------------------------- fused LocSE + attentive pooling (one LFA half)
+ * Replaces, for one half of LocalFeatureAggregation.forward (modules.py:316-319 = stage 1, :321-323 =
+ * stage 2), the op sequence RelativePositionEncoding (modules.py:170-186) -> mlp_rpe1 (:317)
+ * [-> mlp_rpe2 (:321), stage 2] -> PointFeatureAugmentation gather + concat (:209-221) ->
+ * AttentivePooling score Linear + softmax over K + weighted sum (:246-252).  The pooling MLP (:253) is
+ * a per-point layer: r3d_pointwise.  Nothing of shape (B,C,N,K) is written to memory.
+ *
+ *   xyz      (B,N,3)   fp32, clouds xyz_bstride floats apart (0 = dense)
+ *   idx      (B,N,K)   int32 neighbour indices (r3d_knn idx32)
+ *   feat     (B,N,h)   fp32 rows gathered at the neighbours (h = d/2): mlp1 output (stage 1) or the
+ *                      pool-1 output (stage 2); clouds feat_bstride floats apart (0 = dense)
+ *   w_rpe1   (h,10)    mlp_rpe1 conv weight, [out][in]
+ *   a_rpe1,b_rpe1 (h)  per-channel affine applied after it: r1 = relu(a*(W rpe)+b)  (BatchNorm + conv
+ *                      bias folded by the host: running stats in eval mode, batch stats in train mode)
+ *   w_rpe2T  (h,h)     mlp_rpe2 weight TRANSPOSED, [in][out]; a_rpe2,b_rpe2 (h)     (stage 2 only)
+ *   w_scoreT (d,d)     score Linear weight TRANSPOSED, [in][out]
+ *   pooled   (B,N,d)   out: sum_k softmax_k(s)[k,c] * x[k,c],  x = [r ; feat[idx]]
+ * Supported: d in {16,32,64,128,256}, K in {16,32}; other shapes -> R3D_EUNSUPPORTED.
+ * feat, pooled, w_rpe2T, w_scoreT 16-byte aligned. */
+int r3d_lfa_pool(int stage, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                 long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                 const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,
+                 float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
+
+/* ----------------------------------------------------------------------------- per-point MLP layer
+ * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
+ * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,
+ * :591, :594-605, :610) fused with the tensor shuffling around them: the row gather g() is the decoder's
+ * 1-NN up-sampling (modules.py:359-363) or the (inverse) point permutation (:572-573, :608); the second
+ * source is the decoder skip concat (:600-602) or, with folded BN scales, the residual sum of :325.
+ *   xa (B,*,ca) rows of ca floats, clouds xa_bstride apart; gidx int32 nullable, cloud b uses
+ *      gidx[b*gidx_bstride + n] (gidx_bstride 0 = one index vector shared by all clouds)
+ *   xb (B,n,cb) nullable; wT (ca+cb, cout) = weight transposed; scale, shift (cout) nullable
+ *   act 0 none, 1 relu, 2 leaky relu(slope)
+ *   y  (B,n,y_ld >= cout) rows, clouds y_bstride apart; transpose_out=1 writes (B,cout,n) instead
+ *      (the logits layout, modules.py:611).  0 strides mean dense. */
+int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* gidx, long long gidx_bstride,
+                  const float* xb, long long xb_bstride, int cb, const float* wT, const float* scale,
+                  const float* shift, int act, float slope, float* y, long long y_bstride, int y_ld, int cout,
+                  int B, int n, int transpose_out, r3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------ FP32 peak probe
  * Roofline denominator of the CUDA-core kernels, measured live by bench.py (MEASURED_PEAKS.json has
  * HBM and bf16 tensor peaks only).  mode 0 = scalar FFMA, 1 = packed FFMA2 (f32x2).  `out` is a device

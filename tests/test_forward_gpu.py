@@ -1,0 +1,167 @@
+"""GPU parity of the fused inference kernels (C ABI r3d_lfa_pool / r3d_pointwise) and of the whole
+eval-mode forward / Model.predict against the oracle and the golden vectors written by the REFERENCE
+modules (oracle/make_golden.py).  Bar: logits within 1e-4 relative in fp32 (north_star)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+from oracle import network as onet
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+E2E = {
+    "k16_n1024": (dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=16, knn="naive"), 2, 1024, 11),
+    "k32_n2500": (dict(n_classes=2, n_points=2500, n_features=0, n_neighbors=32, knn="naive"), 1, 2500, 12),
+    "k16_f2_c3_n1100": (dict(n_classes=3, n_points=1100, n_features=2, n_neighbors=16, knn="approximate"), 2, 1100, 13),
+}
+
+
+def make_input(B, N, Fe, seed):
+    rng = np.random.RandomState(seed)
+    x = rng.rand(B, N, 3 + Fe).astype(np.float32)
+    x[..., :3] = x[..., :3] * np.array([0.78, 0.61, 0.55], np.float32) + np.array([-0.44, -0.31, 0.05], np.float32)
+    return x
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return (importlib.import_module("3d_recognizer_b200.modules"), importlib.import_module("3d_recognizer_b200.engine"),
+            importlib.import_module("3d_recognizer_b200.ops"))
+
+
+@pytest.mark.parametrize("B,n,ca,cb,cout,act,gather,tr", [
+    (2, 1000, 3, 0, 8, "lrelu", "shared", False), (3, 517, 8, 0, 8, "lrelu", None, False),
+    (2, 700, 16, 8, 32, "lrelu", None, False), (2, 300, 32, 0, 2, None, None, True),
+    (2, 640, 512, 512, 256, "relu", "per_cloud", False), (1, 2500, 64, 64, 8, "relu", "per_cloud", False),
+    (2, 999, 128, 0, 64, "relu", None, False), (4, 39, 512, 0, 512, "relu", None, False),
+    (2, 333, 8, 0, 64, "relu", "shared", False), (1, 77, 64, 0, 32, "relu", None, False),
+    (2, 100, 5, 0, 8, "lrelu", "shared", False),
+])
+def test_pointwise_vs_torch(mods, B, n, ca, cb, cout, act, gather, tr):
+    _, _, ops = mods
+    g = torch.Generator(device="cuda").manual_seed(ca * 1000 + cout)
+    na = n if gather is None else max(n // 3, 1) if gather == "per_cloud" else n
+    xa = torch.randn(B, na, ca, device="cuda", generator=g)
+    xb = torch.randn(B, n, cb, device="cuda", generator=g) if cb else None
+    wT = torch.randn(ca + cb, cout, device="cuda", generator=g) / (ca + cb) ** 0.5
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    sh = torch.randn(cout, device="cuda", generator=g)
+    gidx = None
+    if gather == "shared":
+        gidx = torch.randperm(n, device="cuda", generator=g).to(torch.int32)
+    elif gather == "per_cloud":
+        gidx = torch.randint(0, na, (B, n), device="cuda", generator=g, dtype=torch.int32)
+    got = ops.pointwise(xa, wT, sc, sh, act, 0.2, gidx=gidx, xb=xb, transpose_out=tr)
+    src = xa
+    if gather == "shared":
+        src = xa[:, gidx.long()]
+    elif gather == "per_cloud":
+        src = torch.gather(xa, 1, gidx.long().unsqueeze(-1).expand(B, n, ca))
+    full = torch.cat((src, xb), dim=-1) if cb else src
+    ref = (full.double() @ wT.double()) * sc.double() + sh.double()
+    ref = F.relu(ref) if act == "relu" else F.leaky_relu(ref, 0.2) if act == "lrelu" else ref
+    if tr:
+        ref = ref.transpose(1, 2)
+    assert got.shape == ref.shape
+    assert rel_err(got.double(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("d,K", [(16, 16), (64, 16), (128, 16), (256, 16), (16, 32), (32, 32), (64, 32), (128, 32),
+                                 (256, 32), (32, 16)])
+@pytest.mark.parametrize("stage", [1, 2])
+def test_lfa_pool_vs_torch(mods, d, K, stage):
+    """One fused LocSE+pooling launch vs the same math in fp64 torch ops (engine.* composition)."""
+    _, engine, ops = mods
+    h = d // 2
+    B, N = 2, 333 if d >= 128 else 1000
+    g = torch.Generator(device="cuda").manual_seed(d + K + stage)
+    xyz = torch.rand(B, N, 3, device="cuda", generator=g)
+    feat = torch.randn(B, N, h, device="cuda", generator=g)
+    nn_ = ops.knn(xyz, xyz, K, idx64=True, idx32=True, dist=True)
+    w1 = torch.randn(h, 10, device="cuda", generator=g)
+    a1 = torch.rand(h, device="cuda", generator=g) + 0.5
+    b1 = torch.randn(h, device="cuda", generator=g) * 0.3
+    w2 = torch.randn(h, h, device="cuda", generator=g) / h ** 0.5
+    a2 = torch.rand(h, device="cuda", generator=g) + 0.5
+    b2 = torch.randn(h, device="cuda", generator=g) * 0.3
+    ws = torch.randn(d, d, device="cuda", generator=g) / d ** 0.5
+    got = ops.lfa_pool(stage, xyz, nn_["idx32"], feat, w1, a1, b1, w2.t().contiguous() if stage == 2 else None,
+                       a2 if stage == 2 else None, b2 if stage == 2 else None, ws.t().contiguous())
+    D = torch.float64
+    rpe = engine.relative_position_encoding(xyz.to(D), nn_["idx64"], nn_["dist"].to(D))
+    r = F.relu(rpe @ w1.to(D).t() * a1.to(D) + b1.to(D))
+    if stage == 2:
+        r = F.relu(r @ w2.to(D).t() * a2.to(D) + b2.to(D))
+    x = torch.cat((r, engine.gather_points(feat.to(D), nn_["idx64"])), dim=-1)
+    ref = (F.softmax(x @ ws.to(D).t(), dim=2) * x).sum(dim=2)
+    assert rel_err(got.to(D), ref) < 5e-6
+
+
+@pytest.mark.parametrize("name", list(E2E))
+def test_eval_forward_vs_reference_golden(mods, name):
+    modules, engine, _ = mods
+    g = np.load(os.path.join(GOLDEN, "e2e_golden.npz"))
+    st, B, N, seed = E2E[name]
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(onet.synth_state_dict(st, seed))
+    net.eval()
+    x = torch.from_numpy(make_input(B, N, st["n_features"], seed)).cuda()
+    np.random.seed(seed)
+    with torch.no_grad():
+        logits = net(x)
+    ref = torch.from_numpy(g[f"{name}/eval_logits"]).cuda()
+    assert logits.shape == ref.shape
+    assert rel_err(logits, ref) < TOL
+    # the kernel path really ran (not the autograd composition)
+    np.random.seed(seed)
+    perm = np.random.permutation(N)
+    with torch.no_grad():
+        a = engine.forward_kernels(net, x, perm)
+        b = engine.forward_autograd(net, x, perm)
+    assert torch.equal(a, logits)
+    assert rel_err(a, b) < TOL
+
+
+def test_eval_forward_larger_cloud_vs_oracle(mods):
+    """N=8192, K=16, B=2: all four levels have full CTAs; checked against the oracle port on the CPU."""
+    modules, _, _ = mods
+    st = dict(n_classes=2, n_points=8192, n_features=0, n_neighbors=16, knn="naive")
+    sd = onet.synth_state_dict(st, 5)
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.from_numpy(make_input(2, 8192, 0, 5))
+    np.random.seed(1)
+    with torch.no_grad():
+        got = net(x.cuda()).cpu()
+    np.random.seed(1)
+    ref = onet.forward({k: v.clone() for k, v in sd.items()}, st, x, training=False)
+    assert rel_err(got, ref) < TOL
+
+
+def test_model_predict_vs_reference_golden(tmp_path):
+    """Model.load(save) round trip + Model.predict on a mock LiDAR cloud vs the reference façade's output."""
+    model_mod = importlib.import_module("3d_recognizer_b200.model")
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+    g = np.load(os.path.join(GOLDEN, "predict_golden.npz"))
+    st = dict(n_classes=2, n_points=2500, n_features=0, n_neighbors=32, knn="naive")
+    m = model_mod.Model(modules.RandLANetSettings(**st), weights=onet.synth_state_dict(st, 21))
+    m.save(tmp_path / "ckpt")
+    for ap in ("nni", "idw"):
+        m2 = model_mod.Model.load(tmp_path / "ckpt", upsampling=ap)
+        assert m2.settings.upsampling == ap
+        np.random.seed(3)
+        conf = m2.predict(g["cloud"])
+        ref = g[f"conf_{ap}"]
+        assert conf.shape == ref.shape
+        assert np.abs(conf - ref).max() < 1e-4

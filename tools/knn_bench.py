@@ -33,6 +33,12 @@ def time_knn(B, Ns, Nq, K, variant, iters=3):
 
 
 if __name__ == "__main__":
+    if "--shape" in sys.argv:      # --shape B,Ns,Nq,K [--variant V] [--iters I]: one shape (ncu captures)
+        shp = tuple(int(v) for v in sys.argv[sys.argv.index("--shape") + 1].split(","))
+        var = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 2
+        its = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 1
+        print(json.dumps(time_knn(*shp, variant=var, iters=its)), flush=True)
+        sys.exit(0)
     quick = "--quick" in sys.argv
     shapes = [(64, 40960, 40960, 16), (1, 1 << 20, 1 << 20, 16), (1, 1 << 20, 1 << 20, 32), (8, 2500, 2500, 16),
               (8, 625, 2500, 1), (64, 10240, 40960, 1)]
