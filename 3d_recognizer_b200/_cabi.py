@@ -30,6 +30,7 @@ SIGNATURES = {
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_knn_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r3d_knn_set_variant": (c_int, [c_int]),
+    "r3d_knn_set_algorithm": (c_int, [c_int]),
     "r3d_lfa_pool": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p]),

@@ -34,9 +34,19 @@
 namespace r3d {
 
 constexpr int kKnnThreads = 256;
-constexpr int kTile = 2048;  // support points per smem stage (3 rows x 8 KB)
+constexpr int kTile = 1024;  // support points per smem stage (3 rows x 4 KB)
 
 static std::atomic<int> g_knn_variant{2};
+static std::atomic<int> g_knn_algorithm{0};  // 0 auto, 1 tiled brute force, 2 uniform grid
+
+// knn_grid.cu
+size_t knn_grid_workspace_bytes(int B, int Ns, int Nq);
+int knn_grid_run(const float* support, long long s_stride, const float* query, long long q_stride, int B, int Ns,
+                 int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq, void* workspace,
+                 cudaStream_t st);
+
+// clouds at least this large go to the grid search in auto mode (measured crossover: profiles/r01_knn_sweep.log)
+constexpr int kGridMinSupport = 2048;
 
 // ------------------------------------------------------------------------------------------- pack
 __global__ void xyz_to_soa_kernel(const float* __restrict__ xyz, long long batch_stride, float* __restrict__ soa,
@@ -121,7 +131,7 @@ __device__ __noinline__ float list_insert(float* ld, int* li, int K, int stride,
 // VARIANT 0: contract d2 for every pair.  1: FMA prefilter, scalar.  2: FMA prefilter, packed f32x2.
 // K1: K == 1, best candidate kept in registers (decoder / post-process 1-NN, modules.py:358).
 template <int VARIANT, int Q, bool K1>
-__global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ sup_soa, int Nsp,
+__global__ void __launch_bounds__(kKnnThreads, 2) knn_kernel(const float* __restrict__ sup_soa, int Nsp,
                                                           const float* __restrict__ query, long long q_stride,
                                                           int Ns, int Nq, int K,
                                                           int64_t* __restrict__ idx64, int32_t* __restrict__ idx32,
@@ -296,8 +306,9 @@ static int dispatch_q(int Q, bool k1, const float* sup_soa, int Nsp, const float
 }
 
 static int pick_q(int B, int Nq, int K) {
-    // shared-memory cap: K*Q*256*8 B of lists + 48 KB of tiles must fit 227 KB
-    int qmax = (K <= 16) ? 4 : (K <= 32) ? 2 : 1;
+    // two CTAs per SM (16 warps) hide the FP32-pipe and shared-memory latencies: K*Q*256*8 B of lists
+    // + 24 KB of tiles must fit half of the 227 KB
+    int qmax = (K <= 8) ? 4 : (K <= 16) ? 2 : 1;
     // do not starve the 148 SMs when there are few queries
     const long long total = (long long)B * Nq;
     int q = qmax;
@@ -314,12 +325,19 @@ extern "C" size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K) {
     (void)K;
     if (B <= 0 || Ns <= 0) return 256;
     const size_t Nsp = (size_t)((Ns + 3) & ~3);
-    return align_up((size_t)B * 3 * Nsp * sizeof(float), 256) + 256;
+    const size_t brute = align_up((size_t)B * 3 * Nsp * sizeof(float), 256) + 256;
+    const size_t grid = knn_grid_workspace_bytes(B, Ns, Nq > 0 ? Nq : 1) + 256;
+    return brute > grid ? brute : grid;
 }
 
 extern "C" int r3d_knn_set_variant(int variant) {
     if (variant < 0 || variant > 2) return g_knn_variant.load();
     return g_knn_variant.exchange(variant);
+}
+
+extern "C" int r3d_knn_set_algorithm(int algorithm) {
+    if (algorithm < 0 || algorithm > 2) return g_knn_algorithm.load();
+    return g_knn_algorithm.exchange(algorithm);
 }
 
 extern "C" int r3d_knn(const float* support, long long support_batch_stride, const float* query,
@@ -337,6 +355,11 @@ extern "C" int r3d_knn(const float* support, long long support_batch_stride, con
     if (query_batch_stride == 0) query_batch_stride = (long long)Nq * 3;
     if (support_batch_stride < (long long)Ns * 3 || query_batch_stride < (long long)Nq * 3) return R3D_EINVAL;
 
+    const int algo = g_knn_algorithm.load();
+    if (algo == 2 || (algo == 0 && Ns >= kGridMinSupport))
+        return knn_grid_run(support, support_batch_stride, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
+                            dist_sq, workspace, st);
+
     const int Nsp = (Ns + 3) & ~3;
     float* soa = static_cast<float*>(workspace);
     {
@@ -345,7 +368,7 @@ extern "C" int r3d_knn(const float* support, long long support_batch_stride, con
         R3D_LAUNCH_CHECK("xyz_to_soa_kernel");
     }
     const bool k1 = (K == 1);
-    const int Q = k1 ? ((long long)B * Nq >= (long long)kNumSMs * kKnnThreads * 4 ? 4 : pick_q(B, Nq, 16))
+    const int Q = k1 ? ((long long)B * Nq >= (long long)kNumSMs * kKnnThreads * 8 ? 4 : pick_q(B, Nq, 8))
                      : pick_q(B, Nq, K);
     switch (g_knn_variant.load()) {
         case 0: return dispatch_q<0>(Q, k1, soa, Nsp, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,

@@ -66,6 +66,8 @@ unsigned long long r3d_launch_count(void);
  *   idx32   (B,Nq,K)  int32   nullable        (what the fused kernels below consume)
  *   dist    (B,Nq,K)  fp32    nullable        sqrt(d2)   — what KNN.forward returns
  *   dist_sq (B,Nq,K)  fp32    nullable        d2         — what knn_tpk.knn returns
+ * Two back-ends with identical results: the tiled brute-force scan (TMA-staged support tiles) and, for
+ * large clouds, a uniform-grid search (counting sort into cubic cells + ring walk per query).
  * workspace: r3d_knn_workspace_bytes(), 256-byte aligned.
  */
 size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K);
@@ -79,6 +81,9 @@ int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq
 /* tuning hook for benchmarks/tests: 0 exact scalar, 1 FMA-prefilter scalar, 2 FMA-prefilter
  * packed f32x2 (default).  All variants return identical results.  Returns the previous value. */
 int r3d_knn_set_variant(int variant);
+/* search algorithm: 0 auto (uniform-grid search for Ns >= 2048, tiled brute force below), 1 tiled brute
+ * force, 2 uniform grid.  Both return identical results.  Returns the previous value. */
+int r3d_knn_set_algorithm(int algorithm);
 
 /* ------------------------------------------------------- fused LocSE + attentive pooling (one LFA half)
  * Replaces, for one half of LocalFeatureAggregation.forward (modules.py:316-319 = stage 1, :321-323 =

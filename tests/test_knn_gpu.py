@@ -11,7 +11,25 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 1, 2]
+# (algorithm, variant): tiled brute force in its three arithmetic variants, and the uniform-grid search
+VARIANTS = [(1, 0), (1, 1), (1, 2), (2, 2)]
+
+
+class _mode:
+    """Forces one KNN back-end (r3d_knn_set_algorithm / r3d_knn_set_variant) for the duration of a test."""
+
+    def __init__(self, mode):
+        from importlib import import_module
+        self.L = import_module("3d_recognizer_b200._cabi").lib()
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = (self.L.r3d_knn_set_algorithm(self.mode[0]), self.L.r3d_knn_set_variant(self.mode[1]))
+
+    def __exit__(self, *exc):
+        self.L.r3d_knn_set_algorithm(self.prev[0])
+        self.L.r3d_knn_set_variant(self.prev[1])
+        return False
 
 
 def _golden():
@@ -32,10 +50,7 @@ def _run(ops, s, q, k, same=False):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_knn_golden_vectors(ops, variant):
-    from importlib import import_module
-    L = import_module("3d_recognizer_b200._cabi").lib()
-    prev = L.r3d_knn_set_variant(variant)
-    try:
+    with _mode(variant):
         g = _golden()
         for name in _cases(g):
             s, q, k = g[name + "/support"], g[name + "/query"], int(g[name + "/k"])
@@ -44,32 +59,43 @@ def test_knn_golden_vectors(ops, variant):
             assert np.array_equal(out["idx64"], g[name + "/idx"].astype(np.int64)), f"{name}: indices differ"
             assert np.array_equal(out["idx32"], g[name + "/idx"]), name
             assert np.array_equal(out["dist"], np.sqrt(g[name + "/d2"])), f"{name}: sqrt not IEEE"
-    finally:
-        L.r3d_knn_set_variant(prev)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("B,Ns,Nq,K", [(1, 40960, 40960, 16), (3, 5000, 1237, 32), (2, 2049, 8196, 1),
                                        (1, 4097, 300, 64), (4, 39, 156, 1), (2, 17, 17, 16), (1, 6000, 6000, 8)])
 def test_knn_vs_oracle_seeded(ops, oracle_built, variant, B, Ns, Nq, K):
-    from importlib import import_module
-    L = import_module("3d_recognizer_b200._cabi").lib()
-    prev = L.r3d_knn_set_variant(variant)
-    try:
+    with _mode(variant):
         rng = np.random.RandomState(B * 1000 + K)
         s = rng.rand(B, Ns, 3).astype(np.float32)
         # quantise half the clouds onto a coarse grid => many exact d2 ties, like LiDAR frames
         s[::2] = np.round(s[::2] * 64) / 64
         same = Ns == Nq
-        q = s if same else rng.rand(B, Nq, 3).astype(np.float32)
+        q = s if same else (rng.rand(B, Nq, 3).astype(np.float32) * 1.2 - 0.1)   # some queries outside the support box
         out = _run(ops, s, q, K, same=same)
         oi, od = oracle_built.knn_exact(s, q, K)
         assert np.array_equal(out["dist_sq"], od)
         assert np.array_equal(out["idx64"], oi)
         if same:
             assert (out["dist_sq"][..., 0] == 0).all(), "self distance must be exactly 0"
-    finally:
-        L.r3d_knn_set_variant(prev)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_knn_degenerate_clouds(ops, oracle_built, variant):
+    """Flat (planar / collinear / single-point) supports, heavy duplication, K == Ns."""
+    with _mode(variant):
+        rng = np.random.RandomState(3)
+        plane = rng.rand(1, 3000, 3).astype(np.float32)
+        plane[..., 2] = 0.25
+        line = np.zeros((1, 2000, 3), np.float32)
+        line[..., 0] = np.round(rng.rand(2000) * 500) / 500
+        same_pt = np.full((1, 64, 3), 0.5, np.float32)
+        lidar = np.load(os.path.join(GOLDEN, "predict_golden.npz"))["cloud"][None, :12000]
+        for s, k in ((plane, 16), (line, 16), (same_pt, 64), (same_pt, 5), (lidar, 16), (lidar, 32)):
+            out = _run(ops, s, s, k, same=True)
+            oi, od = oracle_built.knn_exact(s, s, k)
+            assert np.array_equal(out["dist_sq"], od)
+            assert np.array_equal(out["idx64"], oi)
 
 
 def test_knn_host_dropin(ops, oracle_built):
@@ -98,18 +124,20 @@ def test_knn_errors(ops):
     assert out["idx64"].shape == (2, 0, 4)
 
 
-def test_knn_large_properties(ops):
-    """BASELINE config 5 scale (1M x 1M is bench-only); here 262144 self-search, K=16: checked through
+@pytest.mark.parametrize("algo,n", [(1, 262144), (2, 262144), (2, 1 << 20)])
+def test_knn_large_properties(ops, algo, n):
+    """BASELINE config 5 scale (1M x 1M, grid search; brute force at 262144): checked through
     size-independent properties — self is neighbour 0 at d2 == 0, rows ascending, and a random sample
     of rows equals the oracle."""
     from oracle.knn import knn_exact
     g = torch.Generator(device="cuda").manual_seed(1)
-    s = torch.rand(1, 262144, 3, device="cuda", generator=g)
-    out = ops.knn(s, s, 16, idx64=True, dist_sq=True, dist=False)
+    s = torch.rand(1, n, 3, device="cuda", generator=g)
+    with _mode((algo, 2)):
+        out = ops.knn(s, s, 16, idx64=True, dist_sq=True, dist=False)
     idx, d2 = out["idx64"][0], out["dist_sq"][0]
-    assert (d2[:, 0] == 0).all() and (idx[:, 0] == torch.arange(262144, device="cuda")).all()
+    assert (d2[:, 0] == 0).all() and (idx[:, 0] == torch.arange(n, device="cuda")).all()
     assert (d2[:, 1:] >= d2[:, :-1]).all()
-    rows = torch.randint(0, 262144, (512,), generator=torch.Generator().manual_seed(2))
+    rows = torch.randint(0, n, (512,), generator=torch.Generator().manual_seed(2))
     oi, od = knn_exact(s[0].cpu().numpy(), s[0, rows.cuda()].cpu().numpy(), 16)
     assert np.array_equal(idx[rows.cuda()].cpu().numpy(), oi)
     assert np.array_equal(d2[rows.cuda()].cpu().numpy(), od)
