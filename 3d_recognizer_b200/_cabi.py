@@ -34,6 +34,11 @@ SIGNATURES = {
     "r3d_lfa_pool": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
+                         [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
+                         [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_moments": (c_int, [c_int, c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
+                        [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_pointwise": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
                               ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
                               c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),

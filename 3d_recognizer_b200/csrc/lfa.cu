@@ -22,14 +22,11 @@
 //   cols {g*4..g*4+3} U {d/2 + g*4..+3}.  A operand (neighbourhood matrix) is read with LDS.128
 //   (broadcast inside a point), B operand (weights, streamed through a double-buffered ring by 1-D TMA
 //   bulk copies) with conflict-free LDS.128.
-#include "common.cuh"
-
-#include <math_constants.h>
+#include "lfa_common.cuh"
 
 namespace r3d {
 
 constexpr int kLfaThreads = 128;
-constexpr int kWStageFloats = 4096;  // 16 KB per weight stage
 
 struct LfaArgs {
     const float* xyz;        // (B,N,3)
@@ -45,92 +42,24 @@ struct LfaArgs {
     const float* b_rpe2;
     const float* w_scoreT;   // (d,d)   [in][out]
     float* pooled;           // (B,N,d)
-    float* stats;            // nullable: train-mode statistics target (see lfa_rpe_stats_kernel)
     int B, N;
 };
 
 template <int D, int K>
-struct LfaCfg {
-    static constexpr int H = D / 2;
-    static constexpr int RH = K / 16;
-    static constexpr int CG = D / 8;
-    static constexpr int TPP = RH * CG;                 // threads per point
-    static constexpr int PTS = kLfaThreads / TPP;       // points per CTA
-    static constexpr int PAD = (CG >= 32) ? 0 : 4;
-    static constexpr int PSTRIDE = K + PAD;             // floats per point inside a channel row
-    static constexpr int ROWS_PAD = PTS * PSTRIDE;
-    static constexpr int ROWS = PTS * K;
-    static constexpr int X_FLOATS = D * ROWS_PAD;
-    static constexpr int P_FLOATS = H * 12 + 4 * H;     // w_rpe1 padded to 12 per channel + a1,b1,a2,b2
-    static constexpr size_t SMEM = (size_t)(X_FLOATS + 2 * kWStageFloats + P_FLOATS) * sizeof(float) + 16;
-    static_assert(K % 16 == 0 && K >= 16 && K <= 64, "K must be 16, 32, 48 or 64");
-    static_assert(D % 8 == 0 && TPP <= kLfaThreads && kLfaThreads % TPP == 0, "unsupported width");
+struct LfaFwdSmem {
+    using C = LfaCfg<D, K, kLfaThreads>;
+    static constexpr int P_FLOATS = C::H * 12 + 4 * C::H;     // w_rpe1 padded to 12 per channel + a1,b1,a2,b2
+    static constexpr size_t BYTES = (size_t)(C::X_FLOATS + 2 * C::WSTAGE + P_FLOATS) * sizeof(float) + 16;
 };
-
-// Weight streaming: (rows x width) row-major matrix in global memory -> ring of two smem stages.
-struct WPipe {
-    float* ring;
-    uint64_t* bars;
-    uint32_t count;  // chunks consumed so far by this CTA (selects stage and mbarrier phase)
-};
-
-__device__ __forceinline__ void wpipe_issue(const WPipe& p, uint32_t chunk_no, const float* src, uint32_t floats) {
-    const uint32_t s = chunk_no & 1u;
-    mbar_expect_tx(&p.bars[s], floats * 4u);
-    tma_bulk_g2s(p.ring + s * kWStageFloats, src, floats * 4u, &p.bars[s]);
-}
-
-// acc[16][4*NC] += A[rows 16][Kred] * W[Kred][cols].  A in smem channel-major with leading dim lda;
-// thread columns: for q < NC: q*qstride + g*4 + {0..3}.  Ends with a CTA barrier (ring is free again).
-template <int NC>
-__device__ __forceinline__ void gemm_stream(float (&acc)[16][4 * NC], const float* __restrict__ A, int lda,
-                                            int row0, int Kred, const float* __restrict__ Wg, int width,
-                                            int qstride, int g, WPipe& pipe, int tid) {
-    const int kc = kWStageFloats / width < Kred ? kWStageFloats / width : Kred;  // rows per chunk
-    const int nchunks = (Kred + kc - 1) / kc;
-    if (tid == 0) wpipe_issue(pipe, pipe.count, Wg, (uint32_t)(min(kc, Kred) * width));
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const uint32_t cur = pipe.count + ch;
-        if (tid == 0 && ch + 1 < nchunks) {
-            const int rows_next = min(kc, Kred - (ch + 1) * kc);
-            wpipe_issue(pipe, cur + 1, Wg + (size_t)(ch + 1) * kc * width, (uint32_t)(rows_next * width));
-        }
-        mbar_wait(&pipe.bars[cur & 1u], (cur >> 1) & 1u);
-        const float* Wst = pipe.ring + (cur & 1u) * kWStageFloats;
-        const int rows_here = min(kc, Kred - ch * kc);
-        const float* Ap = A + (size_t)(ch * kc) * lda + row0;
-#pragma unroll 2
-        for (int kk = 0; kk < rows_here; ++kk) {
-            float av[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float4 t = *reinterpret_cast<const float4*>(Ap + (size_t)kk * lda + 4 * v);
-                av[4 * v + 0] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
-            }
-            float wv[4 * NC];
-#pragma unroll
-            for (int q = 0; q < NC; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(Wst + kk * width + q * qstride + g * 4);
-                wv[4 * q + 0] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-#pragma unroll
-                for (int j = 0; j < 4 * NC; ++j) acc[r][j] = fmaf(av[r], wv[j], acc[r][j]);
-        }
-        __syncthreads();
-    }
-    pipe.count += nchunks;
-}
 
 template <int D, int K, int STAGE>
 __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
-    using C = LfaCfg<D, K>;
+    using C = LfaCfg<D, K, kLfaThreads>;
     constexpr int H = C::H;
     extern __shared__ __align__(128) float smem[];
     float* X = smem;                               // [D][ROWS_PAD]
-    float* ring = X + C::X_FLOATS;                 // [2][kWStageFloats]
-    float* Pw1 = ring + 2 * kWStageFloats;         // [H][12]
+    float* ring = X + C::X_FLOATS;                 // [2][WSTAGE]
+    float* Pw1 = ring + 2 * C::WSTAGE;             // [H][12]
     float* Pa1 = Pw1 + H * 12;
     float* Pb1 = Pa1 + H;
     float* Pa2 = Pb1 + H;
@@ -147,14 +76,9 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
         mbar_fence_init();
     }
     // parameters -> smem
-    for (int i = tid; i < H * 12; i += kLfaThreads) {
-        const int ch = i / 12, m = i % 12;
-        Pw1[i] = (m < 10) ? a.w_rpe1[ch * 10 + m] : 0.f;
-    }
-    for (int i = tid; i < H; i += kLfaThreads) {
-        Pa1[i] = a.a_rpe1[i];
-        Pb1[i] = a.b_rpe1[i];
-        if (STAGE == 2) {
+    load_rpe1_params<H, kLfaThreads>(Pw1, Pa1, Pb1, a.w_rpe1, a.a_rpe1, a.b_rpe1, tid);
+    if (STAGE == 2) {
+        for (int i = tid; i < H; i += kLfaThreads) {
             Pa2[i] = a.a_rpe2[i];
             Pb2[i] = a.b_rpe2[i];
         }
@@ -173,25 +97,11 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
         const int p = row / K, k = row % K;
         const int pi = min(p0 + p, a.N - 1);
         const int pj = a.idx[((size_t)b * a.N + pi) * K + k];
-        const float ix = xyz_b[(size_t)pi * 3 + 0], iy = xyz_b[(size_t)pi * 3 + 1], iz = xyz_b[(size_t)pi * 3 + 2];
-        const float jx = xyz_b[(size_t)pj * 3 + 0], jy = xyz_b[(size_t)pj * 3 + 1], jz = xyz_b[(size_t)pj * 3 + 2];
-        // same rounding sequence as the KNN contract, so |p_i - p_j| equals sqrt of the KNN d2 bit for bit
-        const float dx = __fsub_rn(ix, jx), dy = __fsub_rn(iy, jy), dz = __fsub_rn(iz, jz);
-        const float dist =
-            __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        const float rpe[10] = {ix, iy, iz, jx, jy, jz, dx, dy, dz, dist};
+        float rpe[10];
+        rpe_of_row(xyz_b, pi, pj, rpe);
         float* xcol = X + p * C::PSTRIDE + k;
         const int c_lo = part * CH_PER, c_hi = c_lo + CH_PER;
-        for (int ch = c_lo; ch < c_hi; ++ch) {
-            const float4 w0 = *reinterpret_cast<const float4*>(Pw1 + ch * 12);
-            const float4 w1 = *reinterpret_cast<const float4*>(Pw1 + ch * 12 + 4);
-            const float4 w2 = *reinterpret_cast<const float4*>(Pw1 + ch * 12 + 8);
-            float z = w0.x * rpe[0];
-            z = fmaf(w0.y, rpe[1], z); z = fmaf(w0.z, rpe[2], z); z = fmaf(w0.w, rpe[3], z);
-            z = fmaf(w1.x, rpe[4], z); z = fmaf(w1.y, rpe[5], z); z = fmaf(w1.z, rpe[6], z);
-            z = fmaf(w1.w, rpe[7], z); z = fmaf(w2.x, rpe[8], z); z = fmaf(w2.y, rpe[9], z);
-            xcol[(size_t)ch * C::ROWS_PAD] = fmaxf(fmaf(z, Pa1[ch], Pb1[ch]), 0.f);
-        }
+        for (int ch = c_lo; ch < c_hi; ++ch) xcol[(size_t)ch * C::ROWS_PAD] = rpe_mlp1(Pw1, Pa1, Pb1, ch, rpe);
         const float* frow = feat_b + (size_t)pj * H;
         for (int c = c_lo; c < c_hi; c += 4) {
             const float4 t = *reinterpret_cast<const float4*>(frow + c);
@@ -208,7 +118,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
     const int g = (tid / C::RH) % C::CG;
     const int p = tid / C::TPP;
     const int row0 = p * C::PSTRIDE + rh * 16;
-    WPipe pipe{ring, bars, 0u};
+    WPipe pipe{ring, bars, 0u, C::WSTAGE};
 
     // ------------------------------------------------------------------ stage 2: r2 = relu(a2 * (W2 r1) + b2), in place
     if (STAGE == 2) {
@@ -217,7 +127,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
         for (int r = 0; r < 16; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
-        gemm_stream<1>(acc2, X, C::ROWS_PAD, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
+        gemm_stream<1, kLfaThreads>(acc2, X, C::ROWS_PAD, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
         // every thread is past the barrier that ends gemm_stream: r1 may be overwritten
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -243,7 +153,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
     for (int r = 0; r < 16; ++r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-    gemm_stream<2>(acc, X, C::ROWS_PAD, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
+    gemm_stream<2, kLfaThreads>(acc, X, C::ROWS_PAD, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
 
     // ------------------------------------------------------------------ softmax over K + weighted sum
     float outv[8];
@@ -281,11 +191,12 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
 
 template <int D, int K, int STAGE>
 static int launch_lfa(const LfaArgs& a, cudaStream_t st) {
-    using C = LfaCfg<D, K>;
+    using C = LfaCfg<D, K, kLfaThreads>;
     auto kern = lfa_pool_kernel<D, K, STAGE>;
-    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    constexpr size_t smem = LfaFwdSmem<D, K>::BYTES;
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(a.N, C::PTS), a.B);
-    kern<<<grid, kLfaThreads, C::SMEM, st>>>(a);
+    kern<<<grid, kLfaThreads, smem, st>>>(a);
     R3D_LAUNCH_CHECK("lfa_pool_kernel");
     return R3D_OK;
 }
@@ -320,7 +231,7 @@ extern "C" int r3d_lfa_pool(int stage, const float* xyz, long long xyz_bstride, 
         (w_rpe2T && !is_aligned(w_rpe2T, 16)) || (feat_bstride % 4) != 0)
         return R3D_EALIGN;
     LfaArgs a{xyz, xyz_bstride, idx, feat, feat_bstride, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2,
-              w_scoreT, pooled, nullptr, B, N};
+              w_scoreT, pooled, B, N};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return stage == 1 ? dispatch_lfa<1>(d, K, a, st) : dispatch_lfa<2>(d, K, a, st);
 }

@@ -1,0 +1,475 @@
+// Training-mode companions of the fused LocSE + attentive-pooling kernel (lfa.cu), sm_100a:
+//
+//   lfa_pool_bwd_kernel   backward of one r3d_lfa_pool launch.  Mirrors the forward: the CTA rebuilds its
+//                         neighbourhood matrix X = [r ; F[idx]] and the scores S = X Ws^T in shared memory /
+//                         registers, then
+//                             A   = softmax_K(S),  pooled = sum_K A*X
+//                             dS  = A * g * (X - pooled)            (g = d loss / d pooled)
+//                             dX  = g * A + dS Ws                   (second streamed GEMM)
+//                             dWs += dS^T X                         (row reduction, reduce_gemm)
+//                             dF[idx] += dX[:, h:]                  (vector atomics, red.global.add.v4.f32)
+//                             du  = dX[:, :h] * [r > 0]             -> G1 += du1^T [rpe, 1]      (stage 1)
+//                         and, in stage 2, through mlp_rpe2 first:  G2 += du2^T [r1 | rpe, 1],
+//                             dr1 = du2 (a2 . W2),  du1 = dr1 * [r1 > 0].
+//                         The host turns G1/G2 into weight, scale and shift gradients (engine.py).
+//   lfa_moments_kernel    first and second moments of the position encoding (16x16, fp64) and of
+//                         r1 = relu(a1 (W1 rpe) + b1) (h x h, fp64) over all (point, neighbour) rows: the
+//                         train-mode BatchNorm statistics of mlp_rpe1 / mlp_rpe2 (modules.py:86-90) follow
+//                         from them in closed form (mean = W mu, var = diag(W Cov W^T)), which keeps every
+//                         kernel single-pass and lets autograd differentiate the statistics.
+//   lfa_moments_bwd_kernel  backward of the r1 moments: dr1 = g_sum + (G + G^T) r1, du1 = dr1 * [r1 > 0],
+//                         G1 += du1^T [rpe, 1].
+//
+// Reference: autograd of randlanet/utils/modules.py:298-325 driven by trainer.py:115-119.
+#include "lfa_common.cuh"
+
+namespace r3d {
+
+struct LfaBwdArgs {
+    const float* xyz;
+    long long xyz_bstride;
+    const int32_t* idx;
+    const float* feat;
+    long long feat_bstride;
+    const float* w_rpe1;      // (h,10)
+    const float* a_rpe1;
+    const float* b_rpe1;
+    const float* w_rpe2T;     // (h,h) [in][out]           (stage 2)
+    const float* a_rpe2;
+    const float* b_rpe2;
+    const float* w_rpe2s;     // (h,h) [out][in] * a2[out] (stage 2; backward GEMM operand)
+    const float* w_scoreT;    // (d,d) [in][out]
+    const float* w_score;     // (d,d) [out][in]
+    const float* dpooled;     // (B,N,d)
+    float* dfeat;             // (B,N,h)   += (pre-zeroed by the caller)
+    long long dfeat_bstride;
+    float* dw_score;          // (d,d) [out][in] +=
+    float* g1;                // (h,16): [:, :10] += du1^T rpe, [:,10] += sum du1
+    float* g2m;               // (h,h)  += du2^T r1        (stage 2)
+    float* g2c;               // (h,16): [:,10] += sum du2 (stage 2)
+    int B, N;
+};
+
+template <int D, int K, int NT>
+struct LfaBwdSmem {
+    using C = LfaCfg<D, K, NT>;
+    static constexpr int FLOATS = 2 * C::X_FLOATS + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 16 + C::ROWS +
+                                  C::PTS * D;
+    static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
+};
+
+template <int D, int K, int NT, int STAGE>
+__global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
+    using C = LfaCfg<D, K, NT>;
+    constexpr int H = C::H;
+    constexpr int RP = C::ROWS_PAD;
+    extern __shared__ __align__(128) float smem[];
+    float* X = smem;                                  // [D][RP]   neighbourhood matrix, later du
+    float* G = X + C::X_FLOATS;                       // [D][RP]   dS, later r1 / du1 (stage 2)
+    float* RPE = G + C::X_FLOATS;                     // [16][RP]  rpe rows, ones row, zero rows
+    float* ring = RPE + kRpeRows * RP;                // [2][WSTAGE]
+    float* Pw1 = ring + 2 * C::WSTAGE;                // [H][12]
+    float* Pa1 = Pw1 + H * 12;
+    float* Pb1 = Pa1 + H;
+    float* Pa2 = Pb1 + H;
+    float* Pb2 = Pa2 + H;
+    int* idxs = reinterpret_cast<int*>(Pb2 + H);      // [ROWS] neighbour index per row (-1: padding point)
+    float* gp = reinterpret_cast<float*>(idxs + C::ROWS);  // [PTS][D] dpooled tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gp + C::PTS * D);
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * C::PTS;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    load_rpe1_params<H, NT>(Pw1, Pa1, Pb1, a.w_rpe1, a.a_rpe1, a.b_rpe1, tid);
+    if (STAGE == 2) {
+        for (int i = tid; i < H; i += NT) {
+            Pa2[i] = a.a_rpe2[i];
+            Pb2[i] = a.b_rpe2[i];
+        }
+    }
+    for (int i = tid; i < C::PTS * D; i += NT) {
+        const int p = i / D, c = i % D;
+        gp[i] = (p0 + p < a.N) ? a.dpooled[((size_t)b * a.N + p0 + p) * D + c] : 0.f;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ rebuild X = [r1 ; F[idx]], RPE
+    constexpr int NSPLIT = (C::ROWS >= NT) ? 1 : NT / C::ROWS;
+    constexpr int CH_PER = H / NSPLIT;
+    static_assert(NSPLIT == 1 || (H % NSPLIT == 0 && CH_PER % 4 == 0), "channel split");
+    const float* xyz_b = a.xyz + (size_t)b * a.xyz_bstride;
+    const float* feat_b = a.feat + (size_t)b * a.feat_bstride;
+    for (int item = tid; item < C::ROWS * NSPLIT; item += NT) {
+        const int row = item % C::ROWS, part = item / C::ROWS;
+        const int p = row / K, k = row % K;
+        const bool valid = p0 + p < a.N;
+        const int pi = min(p0 + p, a.N - 1);
+        const int pj = a.idx[((size_t)b * a.N + pi) * K + k];
+        float rpe[10];
+        rpe_of_row(xyz_b, pi, pj, rpe);
+        const int off = p * C::PSTRIDE + k;
+        if (part == 0) {
+#pragma unroll
+            for (int m = 0; m < 10; ++m) RPE[m * RP + off] = valid ? rpe[m] : 0.f;
+            RPE[10 * RP + off] = valid ? 1.f : 0.f;
+#pragma unroll
+            for (int m = 11; m < kRpeRows; ++m) RPE[m * RP + off] = 0.f;
+            idxs[row] = valid ? pj : -1;
+        }
+        float* xcol = X + off;
+        const int c_lo = part * CH_PER, c_hi = c_lo + CH_PER;
+        for (int ch = c_lo; ch < c_hi; ++ch) xcol[(size_t)ch * RP] = rpe_mlp1(Pw1, Pa1, Pb1, ch, rpe);
+        const float* frow = feat_b + (size_t)pj * H;
+        for (int c = c_lo; c < c_hi; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(frow + c);
+            xcol[(size_t)(H + c + 0) * RP] = t.x;
+            xcol[(size_t)(H + c + 1) * RP] = t.y;
+            xcol[(size_t)(H + c + 2) * RP] = t.z;
+            xcol[(size_t)(H + c + 3) * RP] = t.w;
+        }
+    }
+    __syncthreads();
+
+    const int rh = tid % C::RH;
+    const int g = (tid / C::RH) % C::CG;
+    const int p = tid / C::TPP;
+    const int row0 = p * C::PSTRIDE + rh * 16;
+    WPipe pipe{ring, bars, 0u, C::WSTAGE};
+
+    // ------------------------------------------------------------------ stage 2: r2 = relu(a2 (W2 r1) + b2) in place
+    if (STAGE == 2) {
+        float acc2[16][4];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
+        gemm_stream<1, NT>(acc2, X, RP, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = g * 4 + j;
+            const float sa = Pa2[col], sb = Pb2[col];
+            float* dst = X + (size_t)col * RP + row0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[r] = fmaxf(fmaf(acc2[r][j], sa, sb), 0.f);
+        }
+        __syncthreads();
+    }
+
+    // ------------------------------------------------------------------ scores, softmax, dS and the direct part of dX
+    float acc[16][8];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+    gemm_stream<2, NT>(acc, X, RP, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = (j < 4) ? (g * 4 + j) : (D / 2 + g * 4 + (j - 4));
+        float m = acc[0][j];
+#pragma unroll
+        for (int r = 1; r < 16; ++r) m = fmaxf(m, acc[r][j]);
+#pragma unroll
+        for (int o = 1; o < C::RH; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float* xc = X + (size_t)col * RP + row0;
+        float xv[16];
+        float se = 0.f, sx = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            xv[r] = xc[r];
+            const float e = __expf(acc[r][j] - m);
+            acc[r][j] = e;
+            se += e;
+            sx = fmaf(e, xv[r], sx);
+        }
+#pragma unroll
+        for (int o = 1; o < C::RH; o <<= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        }
+        const float inv = 1.f / se;
+        const float pooled = sx * inv;
+        const float gv = gp[p * D + col];
+        float* gc = G + (size_t)col * RP + row0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float ga = gv * (acc[r][j] * inv);      // g * A  = direct part of dX
+            gc[r] = ga * (xv[r] - pooled);                // dS
+            acc[r][j] = ga;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ dX = g*A + dS Ws ;  dWs += dS^T X
+    gemm_stream<2, NT>(acc, G, RP, row0, D, a.w_score, D, D / 2, g, pipe, tid);
+    reduce_gemm<D, D, NT, C::PTS, K, C::PSTRIDE, float>(G, X, RP, a.dw_score, D, D, tid);
+    __syncthreads();
+
+    // ------------------------------------------------------------------ feature half: scatter-add to dF[idx]
+    {
+        float* df_b = a.dfeat + (size_t)b * a.dfeat_bstride;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int pj = idxs[p * K + rh * 16 + r];
+            if (pj >= 0)
+                red_add_v4(df_b + (size_t)pj * H + g * 4, make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
+        }
+    }
+    // ------------------------------------------------------------------ encoding half: du = dX * [r > 0], in place over r
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float* xc = X + (size_t)(g * 4 + j) * RP + row0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xc[r] = (xc[r] > 0.f) ? acc[r][j] : 0.f;
+    }
+    __syncthreads();
+
+    if (STAGE == 1) {
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(X, RPE, RP, a.g1, kRpeRows, 11, tid);
+        return;
+    }
+
+    // ------------------------------------------------------------------ stage 2: through mlp_rpe2 back to r1
+    // r1 again (from the buffered encoding) into G[:H]
+    for (int item = tid; item < C::ROWS * NSPLIT; item += NT) {
+        const int row = item % C::ROWS, part = item / C::ROWS;
+        const int off = (row / K) * C::PSTRIDE + (row % K);
+        float rpe[10];
+#pragma unroll
+        for (int m = 0; m < 10; ++m) rpe[m] = RPE[m * RP + off];
+        const int c_lo = part * CH_PER, c_hi = c_lo + CH_PER;
+        for (int ch = c_lo; ch < c_hi; ++ch) G[(size_t)ch * RP + off] = rpe_mlp1(Pw1, Pa1, Pb1, ch, rpe);
+    }
+    __syncthreads();
+    reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, float>(X, G, RP, a.g2m, H, H, tid);
+    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(X, RPE, RP, a.g2c, kRpeRows, 11, tid);
+    {
+        float acc2[16][4];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
+        gemm_stream<1, NT>(acc2, X, RP, row0, H, a.w_rpe2s, H, 0, g, pipe, tid);
+        // every thread is past the barrier that ends gemm_stream, i.e. past its reads of r1 in reduce_gemm
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* gc = G + (size_t)(g * 4 + j) * RP + row0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) gc[r] = (gc[r] > 0.f) ? acc2[r][j] : 0.f;
+        }
+    }
+    __syncthreads();
+    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(G, RPE, RP, a.g1, kRpeRows, 11, tid);
+}
+
+// ---------------------------------------------------------------------------------------- moments
+struct LfaMomArgs {
+    const float* xyz;
+    long long xyz_bstride;
+    const int32_t* idx;
+    const float* w_rpe1;
+    const float* a_rpe1;
+    const float* b_rpe1;
+    double* m_rpe;      // (16,16): [j][c] += sum rpe_j rpe_c (row/col 10 = the ones channel)    MODE 0
+    double* m_r1;       // (h,h)  += sum r1 r1^T                                                  MODE 1
+    double* s_r1;       // (h,16): [:,10] += sum r1                                               MODE 1
+    const float* gsym;  // (h,h) G + G^T, [c][j] (symmetric)                                      MODE 2 (backward)
+    const float* gsum;  // (h)   d loss / d sum r1                                                MODE 2
+    float* g1;          // (h,16) += du1^T [rpe, 1]                                               MODE 2
+    int B, N;
+};
+
+template <int D, int K, int NT>
+struct LfaMomSmem {
+    using C = LfaCfg<D, K, NT>;
+    static constexpr int FLOATS = 2 * C::H * C::ROWS_PAD + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 14 + 4;
+    static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
+};
+
+// MODE 0: rpe moments.  MODE 1: r1 moments.  MODE 2: backward of the r1 moments.
+template <int D, int K, int NT, int MODE>
+__global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
+    using C = LfaCfg<D, K, NT>;
+    constexpr int H = C::H;
+    constexpr int RP = C::ROWS_PAD;
+    extern __shared__ __align__(128) float smem[];
+    float* R1 = smem;                        // [H][RP]
+    float* DU = R1 + H * RP;                 // [H][RP]  (MODE 2)
+    float* RPE = DU + H * RP;                // [16][RP]
+    float* ring = RPE + kRpeRows * RP;       // [2][WSTAGE]
+    float* Pw1 = ring + 2 * C::WSTAGE;       // [H][12]
+    float* Pa1 = Pw1 + H * 12;
+    float* Pb1 = Pa1 + H;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Pb1 + H);
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * C::PTS;
+    if (MODE == 2 && tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    if (MODE != 0) load_rpe1_params<H, NT>(Pw1, Pa1, Pb1, a.w_rpe1, a.a_rpe1, a.b_rpe1, tid);
+    __syncthreads();
+
+    constexpr int NSPLIT = (C::ROWS >= NT) ? 1 : NT / C::ROWS;
+    constexpr int CH_PER = H / NSPLIT;
+    const float* xyz_b = a.xyz + (size_t)b * a.xyz_bstride;
+    for (int item = tid; item < C::ROWS * NSPLIT; item += NT) {
+        const int row = item % C::ROWS, part = item / C::ROWS;
+        const int p = row / K, k = row % K;
+        const bool valid = p0 + p < a.N;
+        const int pi = min(p0 + p, a.N - 1);
+        const int pj = a.idx[((size_t)b * a.N + pi) * K + k];
+        float rpe[10];
+        rpe_of_row(xyz_b, pi, pj, rpe);
+        const int off = p * C::PSTRIDE + k;
+        if (part == 0) {
+#pragma unroll
+            for (int m = 0; m < 10; ++m) RPE[m * RP + off] = valid ? rpe[m] : 0.f;
+            RPE[10 * RP + off] = valid ? 1.f : 0.f;
+#pragma unroll
+            for (int m = 11; m < kRpeRows; ++m) RPE[m * RP + off] = 0.f;
+        }
+        if (MODE != 0) {
+            const int c_lo = part * CH_PER, c_hi = c_lo + CH_PER;
+            for (int ch = c_lo; ch < c_hi; ++ch)
+                R1[(size_t)ch * RP + off] = valid ? rpe_mlp1(Pw1, Pa1, Pb1, ch, rpe) : 0.f;
+        }
+    }
+    __syncthreads();
+
+    if (MODE == 0) {
+        reduce_gemm<kRpeRows, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(RPE, RPE, RP, a.m_rpe, kRpeRows, 11, tid);
+    } else if (MODE == 1) {
+        reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, double>(R1, R1, RP, a.m_r1, H, H, tid);
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(R1, RPE, RP, a.s_r1, kRpeRows, 11, tid);
+    } else {
+        const int rh = tid % C::RH;
+        const int g = (tid / C::RH) % C::CG;
+        const int p = tid / C::TPP;
+        const int row0 = p * C::PSTRIDE + rh * 16;
+        WPipe pipe{ring, bars, 0u, C::WSTAGE};
+        float acc2[16][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gs = a.gsum[g * 4 + j];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc2[r][j] = gs;
+        }
+        gemm_stream<1, NT>(acc2, R1, RP, row0, H, a.gsym, H, 0, g, pipe, tid);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* rc = R1 + (size_t)(g * 4 + j) * RP + row0;
+            float* dc = DU + (size_t)(g * 4 + j) * RP + row0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dc[r] = (rc[r] > 0.f) ? acc2[r][j] : 0.f;   // padding rows: r1 == 0
+        }
+        __syncthreads();
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(DU, RPE, RP, a.g1, kRpeRows, 11, tid);
+    }
+}
+
+// ------------------------------------------------------------------------------------- launchers
+template <int D, int K, int NT, int STAGE>
+static int launch_bwd(const LfaBwdArgs& a, cudaStream_t st) {
+    using C = LfaCfg<D, K, NT>;
+    auto kern = lfa_pool_bwd_kernel<D, K, NT, STAGE>;
+    constexpr size_t smem = LfaBwdSmem<D, K, NT>::BYTES;
+    static_assert(smem <= 232448, "backward tile does not fit shared memory");
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(a.N, C::PTS), a.B);
+    kern<<<grid, NT, smem, st>>>(a);
+    R3D_LAUNCH_CHECK("lfa_pool_bwd_kernel");
+    return R3D_OK;
+}
+
+template <int STAGE>
+static int dispatch_bwd(int d, int K, const LfaBwdArgs& a, cudaStream_t st) {
+#define R3D_CASE(DD, KK, NT) \
+    if (d == DD && K == KK) return launch_bwd<DD, KK, NT, STAGE>(a, st);
+    R3D_CASE(16, 16, 64) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
+    R3D_CASE(16, 32, 64) R3D_CASE(32, 32, 128) R3D_CASE(64, 32, 128) R3D_CASE(128, 32, 128) R3D_CASE(256, 32, 128)
+#undef R3D_CASE
+    return R3D_EUNSUPPORTED;
+}
+
+template <int D, int K, int NT, int MODE>
+static int launch_mom(const LfaMomArgs& a, cudaStream_t st) {
+    using C = LfaCfg<D, K, NT>;
+    auto kern = lfa_moments_kernel<D, K, NT, MODE>;
+    constexpr size_t smem = LfaMomSmem<D, K, NT>::BYTES;
+    static_assert(smem <= 232448, "moments tile does not fit shared memory");
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(a.N, C::PTS), a.B);
+    kern<<<grid, NT, smem, st>>>(a);
+    R3D_LAUNCH_CHECK("lfa_moments_kernel");
+    return R3D_OK;
+}
+
+template <int MODE>
+static int dispatch_mom(int d, int K, const LfaMomArgs& a, cudaStream_t st) {
+#define R3D_CASE(DD, KK, NT) \
+    if (d == DD && K == KK) return launch_mom<DD, KK, NT, MODE>(a, st);
+    R3D_CASE(16, 16, 128) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
+    R3D_CASE(16, 32, 128) R3D_CASE(32, 32, 128) R3D_CASE(64, 32, 128) R3D_CASE(128, 32, 128) R3D_CASE(256, 32, 128)
+#undef R3D_CASE
+    return R3D_EUNSUPPORTED;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstride, const int32_t* idx,
+                                const float* feat, long long feat_bstride, const float* w_rpe1, const float* a_rpe1,
+                                const float* b_rpe1, const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2,
+                                const float* w_rpe2s, const float* w_scoreT, const float* w_score,
+                                const float* dpooled, float* dfeat, long long dfeat_bstride, float* dw_score,
+                                float* g1, float* g2m, float* g2c, int B, int N, int K, int d, r3d_stream_t stream) {
+    if (stage != 1 && stage != 2) return R3D_EINVAL;
+    if (B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
+    if (B == 0 || N == 0) return R3D_OK;
+    if (!xyz || !idx || !feat || !w_rpe1 || !a_rpe1 || !b_rpe1 || !w_scoreT || !w_score || !dpooled || !dfeat ||
+        !dw_score || !g1)
+        return R3D_EINVAL;
+    if (stage == 2 && (!w_rpe2T || !a_rpe2 || !b_rpe2 || !w_rpe2s || !g2m || !g2c)) return R3D_EINVAL;
+    const int h = d / 2;
+    if (xyz_bstride == 0) xyz_bstride = (long long)N * 3;
+    if (feat_bstride == 0) feat_bstride = (long long)N * h;
+    if (dfeat_bstride == 0) dfeat_bstride = (long long)N * h;
+    if (!is_aligned(feat, 16) || !is_aligned(dfeat, 16) || !is_aligned(w_scoreT, 16) || !is_aligned(w_score, 16) ||
+        (w_rpe2T && !is_aligned(w_rpe2T, 16)) || (w_rpe2s && !is_aligned(w_rpe2s, 16)) || (feat_bstride % 4) != 0 ||
+        (dfeat_bstride % 4) != 0)
+        return R3D_EALIGN;
+    LfaBwdArgs a{xyz, xyz_bstride, idx, feat, feat_bstride, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2,
+                 w_rpe2s, w_scoreT, w_score, dpooled, dfeat, dfeat_bstride, dw_score, g1, g2m, g2c, B, N};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return stage == 1 ? dispatch_bwd<1>(d, K, a, st) : dispatch_bwd<2>(d, K, a, st);
+}
+
+extern "C" int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx,
+                               const float* w_rpe1, const float* a_rpe1, const float* b_rpe1, double* m_rpe,
+                               double* m_r1, double* s_r1, const float* gsym, const float* gsum, float* g1, int B,
+                               int N, int K, int d, r3d_stream_t stream) {
+    if (mode < 0 || mode > 2 || B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
+    if (B == 0 || N == 0) return R3D_OK;
+    if (!xyz || !idx) return R3D_EINVAL;
+    if (mode == 0 && !m_rpe) return R3D_EINVAL;
+    if (mode != 0 && (!w_rpe1 || !a_rpe1 || !b_rpe1)) return R3D_EINVAL;
+    if (mode == 1 && (!m_r1 || !s_r1)) return R3D_EINVAL;
+    if (mode == 2 && (!gsym || !gsum || !g1 || !is_aligned(gsym, 16))) return R3D_EINVAL;
+    if (xyz_bstride == 0) xyz_bstride = (long long)N * 3;
+    LfaMomArgs a{xyz, xyz_bstride, idx, w_rpe1, a_rpe1, b_rpe1, m_rpe, m_r1, s_r1, gsym, gsum, g1, B, N};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == 0) return dispatch_mom<0>(d, K, a, st);
+    if (mode == 1) return dispatch_mom<1>(d, K, a, st);
+    return dispatch_mom<2>(d, K, a, st);
+}

@@ -111,6 +111,127 @@ def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch
     return (w.unsqueeze(-1) * gather_points(feat, nn_["idx64"])).sum(dim=2)
 
 
+# ------------------------------------------------------------- training path: fused LFA with autograd
+class _LfaPoolFn(torch.autograd.Function):
+    """One fused LocSE + attentive-pooling launch (ops.lfa_pool) with its mirrored backward kernel
+    (ops.lfa_pool_bwd).  Differentiable inputs: feat, w1 (h,10), a1, c1 (h) [, w2 (h,h), a2, c2], ws (d,d);
+    a*/c* are the per-channel affine maps that BatchNorm (+ conv bias) reduces to."""
+
+    @staticmethod
+    def forward(ctx, stage, xyz, idx32, feat, w1, a1, c1, w2, a2, c2, ws):
+        w1 = w1.contiguous()
+        w2T = w2.t().contiguous() if stage == 2 else None
+        wsT = ws.t().contiguous()
+        pooled = ops.lfa_pool(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
+                              a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None, wsT)
+        ctx.stage = stage
+        ctx.save_for_backward(xyz, idx32, feat, w1, a1, c1, w2 if stage == 2 else None, a2 if stage == 2 else None,
+                              c2 if stage == 2 else None, ws, w2T, wsT)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        xyz, idx32, feat, w1, a1, c1, w2, a2, c2, ws, w2T, wsT = ctx.saved_tensors
+        stage = ctx.stage
+        w2s = (w2 * a2.unsqueeze(1)).contiguous() if stage == 2 else None
+        dfeat, dws, g1, g2m, g2c = ops.lfa_pool_bwd(
+            stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
+            a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None, w2s, wsT,
+            ws.contiguous(), dpooled)
+        gm = g1[:, :10]
+        dw1, da1, dc1 = a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
+        dw2 = da2 = dc2 = None
+        if stage == 2:
+            dw2, da2, dc2 = a2.unsqueeze(1) * g2m, (w2 * g2m).sum(dim=1), g2c[:, 10]
+        return None, None, None, dfeat, dw1, da1, dc1, dw2, da2, dc2, dws
+
+
+class _R1MomentsFn(torch.autograd.Function):
+    """(sum r1 (h), sum r1 r1^T (h,h)) in fp64 over all (point, neighbour) rows, r1 = relu(a1 (W1 rpe) + c1):
+    the statistics mlp_rpe2's train-mode BatchNorm needs."""
+
+    @staticmethod
+    def forward(ctx, xyz, idx32, w1, a1, c1):
+        w1, a1, c1 = w1.contiguous(), a1.contiguous(), c1.contiguous()
+        m_r1, s_r1 = ops.lfa_moments(1, xyz, idx32, 2 * w1.shape[0], w1, a1, c1)
+        ctx.save_for_backward(xyz, idx32, w1, a1, c1)
+        return s_r1[:, 10].clone(), m_r1
+
+    @staticmethod
+    def backward(ctx, g_sum, g_m):
+        xyz, idx32, w1, a1, c1 = ctx.saved_tensors
+        gsym = (g_m + g_m.t()).float().contiguous()
+        g1 = ops.lfa_moments(2, xyz, idx32, 2 * w1.shape[0], w1, a1, c1, gsym=gsym, gsum=g_sum.float().contiguous())
+        gm = g1[:, :10]
+        return None, None, a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
+
+
+def _bn_affine_from_moments(smlp, mean_in: torch.Tensor, cov_in: torch.Tensor, count: float):
+    """Train-mode BatchNorm of y = W x + b expressed through the input moments (fp64): mean_y = W mu + b,
+    var_y = diag(W Cov W^T) (biased, as BatchNorm normalises; modules.py:86-90).  Returns the per-channel
+    affine (a, c) with bn(y) = a * (W x) + c, and updates the running statistics like BatchNorm2d
+    (momentum 0.99, unbiased running variance)."""
+    bn = smlp.batch_norm
+    w = conv_weight_2d(smlp).double()
+    wmu = w @ mean_in
+    var = ((w @ cov_in) * w).sum(dim=1).clamp_min(0.0)
+    a = bn.weight.double() * torch.rsqrt(var + bn.eps)
+    # the conv bias cancels against the batch mean; keep it in the graph so that it receives its (zero) gradient
+    c = bn.bias.double() - a * wmu + 0.0 * smlp.conv.bias.double()
+    if bn.track_running_stats:
+        with torch.no_grad():
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_((wmu + smlp.conv.bias.double()).float(), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var * (count / max(count - 1.0, 1.0))).float(), alpha=m)
+            bn.num_batches_tracked.add_(1)
+    return a.float(), c.float()
+
+
+def _eval_affine(smlp):
+    bn = smlp.batch_norm
+    a = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return a, bn.bias + (smlp.conv.bias - bn.running_mean) * a
+
+
+def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    """LocalFeatureAggregation (modules.py:298-325) with gradients: KNN and the two fused LocSE + pooling
+    halves run on the sm_100a kernels (forward AND backward); the per-point layers around them are
+    differentiable tensor ops.  Works in train mode (batch statistics) and eval mode (running statistics)."""
+    K = lfa._n_neighbors
+    idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
+    f = shared_mlp(lfa.mlp1, feat)
+    w1 = lfa.mlp_rpe1.conv.weight.view(-1, 10)
+    w2 = lfa.mlp_rpe2.conv.weight.view(w1.shape[0], w1.shape[0])
+    d = 2 * w1.shape[0]
+    training = lfa.mlp_rpe1.batch_norm.training
+    if training:
+        m = ops.lfa_moments(0, xyz, idx, d)                      # (16,16) fp64, no parameters involved
+        count = float(xyz.shape[0] * xyz.shape[1] * K)
+        mu = m[10, :10] / count
+        cov = m[:10, :10] / count - torch.outer(mu, mu)
+        a1, c1 = _bn_affine_from_moments(lfa.mlp_rpe1, mu, cov, count)
+    else:
+        a1, c1 = _eval_affine(lfa.mlp_rpe1)
+    ws1, ws2 = lfa.pool1.score_fn[0].weight, lfa.pool2.score_fn[0].weight
+    pooled1 = _LfaPoolFn.apply(1, xyz, idx, f, w1, a1, c1, None, None, None, ws1)
+    p1 = shared_mlp(lfa.pool1.mlp, pooled1)
+    if training:
+        s_r1, m_r1 = _R1MomentsFn.apply(xyz, idx, w1, a1, c1)
+        mu_r = s_r1 / count
+        cov_r = m_r1 / count - torch.outer(mu_r, mu_r)
+        a2, c2 = _bn_affine_from_moments(lfa.mlp_rpe2, mu_r, cov_r, count)
+    else:
+        a2, c2 = _eval_affine(lfa.mlp_rpe2)
+    pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, w1, a1, c1, w2, a2, c2, ws2)
+    p2 = shared_mlp(lfa.pool2.mlp, pooled2)
+    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
+
+
+# LFA implementation used by forward_autograd: the fused kernels, or (tests / debugging) the plain
+# tensor-op composition `lfa_block`
+LFA_IMPL = lfa_block_fused
+
+
 # ------------------------------------------------------------------------------------ full forward
 def forward_autograd(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
     s = net.settings
@@ -128,7 +249,7 @@ def forward_autograd(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.T
     n_l = N
     cur = feat
     for lfa in net.encoder:
-        out = lfa_block(lfa, xyz[:, :n_l], cur)
+        out = LFA_IMPL(lfa, xyz[:, :n_l], cur)
         skips.append(out)
         n_l //= dec
         cur = out[:, :n_l]

@@ -159,3 +159,66 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
                                        _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_pointwise")
     return out
+
+
+def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_rpe2s, w_scoreT,
+                 w_score, dpooled):
+    """Backward of ``lfa_pool`` (C ABI ``r3d_lfa_pool_bwd``).  Returns (dfeat (B,N,h), dw_score (d,d)
+    [out][in], g1 (h,16), g2m (h,h) | None, g2c (h,16) | None) — see include/r3d_b200.h."""
+    xyz, xs = _cloud_view(xyz)
+    feat, fs = _rows_view(feat.detach())
+    B, N, K = idx32.shape
+    h = feat.shape[2]
+    d = 2 * h
+    dev = xyz.device
+    dpooled = dpooled.contiguous()
+    dfeat = torch.zeros((B, N, h), dtype=torch.float32, device=dev)
+    # one zero-filled block for all small accumulators
+    acc = torch.zeros(d * d + h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float32, device=dev)
+    dws = acc[:d * d].view(d, d)
+    g1 = acc[d * d:d * d + h * 16].view(h, 16)
+    g2m = g2c = None
+    if stage == 2:
+        o = d * d + h * 16
+        g2m = acc[o:o + h * h].view(h, h)
+        g2c = acc[o + h * h:].view(h, 16)
+    flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
+    nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_bwd", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_pool_bwd(
+            stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
+            _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T), _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_rpe2s),
+            _cabi.ptr(w_scoreT), _cabi.ptr(w_score), _cabi.ptr(dpooled), _cabi.ptr(dfeat), 0, _cabi.raw(dws),
+            _cabi.raw(g1), _cabi.raw(g2m), _cabi.raw(g2c), B, N, K, d, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_pool_bwd")
+    return dfeat, dws, g1, g2m, g2c
+
+
+def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=None, gsym=None, gsum=None):
+    """BatchNorm moments of the fused LocSE (C ABI ``r3d_lfa_moments``).
+    mode 0 -> m_rpe (16,16) float64; mode 1 -> (m_r1 (h,h), s_r1 (h,16)) float64; mode 2 -> g1 (h,16) float32."""
+    xyz, xs = _cloud_view(xyz)
+    B, N, K = idx32.shape
+    h = d // 2
+    dev = xyz.device
+    m_rpe = m_r1 = s_r1 = g1 = None
+    if mode == 0:
+        m_rpe = torch.zeros((16, 16), dtype=torch.float64, device=dev)
+    elif mode == 1:
+        buf = torch.zeros(h * h + h * 16, dtype=torch.float64, device=dev)
+        m_r1, s_r1 = buf[:h * h].view(h, h), buf[h * h:].view(h, 16)
+    else:
+        g1 = torch.zeros((h, 16), dtype=torch.float32, device=dev)
+    flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
+    nbytes = float(B) * N * (12 + 4 * K)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_moments(mode, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1),
+                                         _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.raw(m_rpe), _cabi.raw(m_r1),
+                                         _cabi.raw(s_r1), _cabi.ptr(gsym), _cabi.ptr(gsum), _cabi.raw(g1), B, N, K, d,
+                                         _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_moments")
+    if mode == 0:
+        return m_rpe
+    if mode == 1:
+        return m_r1, s_r1
+    return g1

@@ -109,6 +109,38 @@ int r3d_lfa_pool(int stage, const float* xyz, long long xyz_bstride, const int32
                  const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,
                  float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
 
+/* Backward of one r3d_lfa_pool launch (autograd of modules.py:316-323 as driven by trainer.py:115-119).
+ * Inputs as in the forward plus
+ *   w_rpe2s  (h,h)  [out][in] mlp_rpe2 weight with row j scaled by a_rpe2[j]         (stage 2)
+ *   w_score  (d,d)  [out][in] score weight (the forward's w_scoreT transposed back)
+ *   dpooled  (B,N,d) gradient of the loss with respect to `pooled`
+ * Outputs, all ACCUMULATED into (the caller zero-fills them):
+ *   dfeat    (B,N,h)  gradient w.r.t. `feat` (scatter-add over neighbour lists, fp32 atomics)
+ *   dw_score (d,d)    [out][in]
+ *   g1       (h,16)   cols 0..9 = sum_rows du1 * rpe, col 10 = sum_rows du1, where du1 is the gradient at
+ *                     the input of mlp_rpe1's ReLU; the host forms dW1 = a1 (.) g1[:, :10],
+ *                     da1 = rowsum(W1 (.) g1[:, :10]), db1 = g1[:,10]
+ *   g2m      (h,h)    sum_rows du2 r1^T      (stage 2: dW2 = a2 (.) g2m, da2 = rowsum(W2 (.) g2m))
+ *   g2c      (h,16)   col 10 = sum_rows du2  (stage 2: db2) */
+int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                     long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                     const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_rpe2s,
+                     const float* w_scoreT, const float* w_score, const float* dpooled, float* dfeat,
+                     long long dfeat_bstride, float* dw_score, float* g1, float* g2m, float* g2c, int B, int N,
+                     int K, int d, r3d_stream_t stream);
+
+/* Moments for the train-mode BatchNorm of mlp_rpe1 / mlp_rpe2 (modules.py:86-90 statistics over all
+ * B*N*K positions), accumulated in fp64 into caller-zeroed buffers:
+ *   mode 0: m_rpe (16,16) += sum_rows e e^T with e = [rpe(10), 1, 0...]: row 10 holds sum rpe, [10][10] the
+ *           row count.  mean/var of W1 rpe follow in closed form (W mu, diag(W Cov W^T)).
+ *   mode 1: m_r1 (h,h) += sum_rows r1 r1^T and s_r1 (h,16)[:,10] += sum_rows r1, r1 = relu(a1 (W1 rpe) + b1).
+ *   mode 2: backward of mode 1: with gsym (h,h) = G + G^T (G = d loss/d m_r1) and gsum (h) = d loss/d sum r1,
+ *           g1 (h,16) += du1^T [rpe, 1] as in r3d_lfa_pool_bwd. */
+int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* w_rpe1,
+                    const float* a_rpe1, const float* b_rpe1, double* m_rpe, double* m_r1, double* s_r1,
+                    const float* gsym, const float* gsum, float* g1, int B, int N, int K, int d,
+                    r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,

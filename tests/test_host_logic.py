@@ -50,6 +50,8 @@ def cpu_product(monkeypatch, r3d):
 
     monkeypatch.setattr(ops, "knn", knn_stub)
     monkeypatch.setattr(engine, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(engine, "LFA_IMPL", engine.lfa_block)      # tensor-op composition instead of the fused kernels
+    monkeypatch.setattr(engine, "forward_kernels", engine.forward_autograd)
     return modules
 
 

@@ -1,0 +1,139 @@
+"""GPU parity of the training path: fused LocSE + attentive-pooling forward/backward kernels
+(r3d_lfa_pool / r3d_lfa_pool_bwd / r3d_lfa_moments) against autograd of the plain tensor-op composition,
+and whole-network train-mode logits, loss, gradients and BatchNorm running statistics against the golden
+vectors written by the REFERENCE modules (oracle/make_golden.py).  Bar: 1e-4 relative (north_star)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import network as onet
+from test_forward_gpu import E2E, make_input, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return (importlib.import_module("3d_recognizer_b200.modules"), importlib.import_module("3d_recognizer_b200.engine"),
+            importlib.import_module("3d_recognizer_b200.ops"))
+
+
+@pytest.mark.parametrize("d,K", [(16, 16), (64, 16), (256, 16), (32, 32)])
+def test_moments_vs_torch(mods, d, K):
+    _, engine, ops = mods
+    h = d // 2
+    B, N = 2, 700
+    g = torch.Generator(device="cuda").manual_seed(d + K)
+    xyz = torch.rand(B, N, 3, device="cuda", generator=g)
+    nn_ = ops.knn(xyz, xyz, K, idx64=True, idx32=True, dist=True)
+    rpe = engine.relative_position_encoding(xyz.double(), nn_["idx64"], nn_["dist"].double()).reshape(-1, 10)
+    m = ops.lfa_moments(0, xyz, nn_["idx32"], d)
+    ext = torch.cat((rpe, torch.ones_like(rpe[:, :1])), dim=1)
+    ref = ext.t() @ ext
+    assert rel_err(m[:11, :11], ref) < 1e-6
+    w1 = torch.randn(h, 10, device="cuda", generator=g)
+    a1 = torch.rand(h, device="cuda", generator=g) + 0.5
+    c1 = torch.randn(h, device="cuda", generator=g) * 0.3
+    m_r1, s_r1 = ops.lfa_moments(1, xyz, nn_["idx32"], d, w1, a1, c1)
+    r1 = torch.relu(rpe @ w1.double().t() * a1.double() + c1.double())
+    assert rel_err(m_r1, r1.t() @ r1) < 1e-5
+    assert rel_err(s_r1[:, 10], r1.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("n_in,d,K,N", [(8, 16, 16, 1000), (32, 64, 16, 625), (128, 128, 16, 300), (256, 256, 16, 150),
+                                        (8, 16, 32, 500), (32, 64, 32, 300), (128, 256, 32, 100)])
+@pytest.mark.parametrize("train", [True, False])
+def test_lfa_block_fused_vs_autograd(mods, n_in, d, K, N, train):
+    """Output, input gradient, every parameter gradient and the BatchNorm running statistics of one
+    LocalFeatureAggregation block: fused kernels vs autograd of the tensor-op composition."""
+    modules, engine, _ = mods
+    B = 2
+    dev = torch.device("cuda")
+    torch.manual_seed(n_in + d + K)
+    lfa_a = modules.LocalFeatureAggregation(n_in, d, K, dev).to(dev)
+    with torch.no_grad():                                     # non-trivial BN affine / running stats
+        for m in lfa_a.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.7, 1.3)
+                m.bias.normal_(0, 0.1)
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    import copy
+    lfa_b = copy.deepcopy(lfa_a)
+    lfa_a.train(train)
+    lfa_b.train(train)
+    xyz = torch.rand(B, N, 3, device=dev)
+    x = torch.randn(B, N, n_in, device=dev)
+    gout = torch.randn(B, N, 2 * d, device=dev)
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    # fp64 run of the same composition = the arbiter when two fp32 results disagree near the bound
+    # (train-mode BatchNorm over few samples amplifies fp32 round-off on nearly-dead ReLU channels)
+    lfa_c = copy.deepcopy(lfa_a).double()
+    lfa_c.train(train)
+    xc = x.double().requires_grad_(True)
+    ya = engine.lfa_block_fused(lfa_a, xyz, xa)
+    yb = engine.lfa_block(lfa_b, xyz, xb)
+    yc = engine.lfa_block(lfa_c, xyz.double(), xc)
+    (ya * gout).sum().backward()
+    (yb * gout).sum().backward()
+    (yc * gout.double()).sum().backward()
+
+    def check(got, plain, exact, what, denom=None):
+        denom = float(exact.abs().max()) if denom is None else denom
+        e_got = float((got.double() - exact).abs().max()) / denom
+        e_plain = float((plain.double() - exact).abs().max()) / denom
+        assert e_got < max(TOL, 3 * e_plain), (what, e_got, e_plain)
+
+    check(ya.detach(), yb.detach(), yc.detach(), "output")
+    check(xa.grad, xb.grad, xc.grad, "input grad")
+    ga = {k: p.grad for k, p in lfa_a.named_parameters()}
+    gb = {k: p.grad for k, p in lfa_b.named_parameters()}
+    gc = {k: p.grad for k, p in lfa_c.named_parameters()}
+    scale = max(float(g_.abs().max()) for g_ in gc.values())
+    for k in gc:
+        assert ga[k] is not None, k
+        # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient
+        denom = scale if (train and k.endswith("conv.bias")) else max(float(gc[k].abs().max()), 1e-6 * scale)
+        check(ga[k], gb[k], gc[k], k, denom)
+    for (k, va), (_, vb) in zip(lfa_a.state_dict().items(), lfa_b.state_dict().items()):
+        if "running" in k:
+            assert torch.allclose(va, vb, rtol=1e-4, atol=1e-6), k
+        if "num_batches" in k:
+            assert int(va) == int(vb), k
+
+
+@pytest.mark.parametrize("name", list(E2E))
+def test_train_step_vs_reference_golden(mods, name):
+    modules, engine, _ = mods
+    assert engine.LFA_IMPL is engine.lfa_block_fused
+    g = np.load(os.path.join(GOLDEN, "e2e_golden.npz"))
+    st, B, N, seed = E2E[name]
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(onet.synth_state_dict(st, seed))
+    x = torch.from_numpy(make_input(B, N, st["n_features"], seed)).cuda()
+    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, st["n_classes"], (B, N))).cuda()
+    net.train()
+    net.fc_end[2].p = 0.0
+    np.random.seed(seed)
+    logits = net(x)
+    ref = torch.from_numpy(g[f"{name}/train_logits"]).cuda()
+    assert rel_err(logits, ref) < TOL
+    loss = onet.dice_loss(logits, labels)
+    assert abs(loss.item() - float(g[f"{name}/train_loss"])) < 1e-5
+    net.zero_grad()
+    loss.backward()
+    got = {k: onet.grad_fixture_view(p.grad) for k, p in net.named_parameters()}
+    refg = {k: torch.from_numpy(g[f"{name}/grad/{k}"]) for k in got}
+    worst, wname = onet.grad_parity(got, refg)
+    assert worst < TOL, (worst, wname)
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert np.allclose(v.cpu().numpy(), g[f"{name}/after/{k}"], rtol=1e-4, atol=1e-5), k
+        if "num_batches_tracked" in k:
+            assert int(v) == 8
