@@ -129,3 +129,49 @@ def test_engine_host_logic_vs_reference_golden(cpu_product, name):
             assert np.allclose(v.numpy(), g[f"{name}/after/{k}"], rtol=1e-4, atol=1e-5), k
         if "num_batches_tracked" in k:
             assert int(v) == 8
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: no file of the product package may import or execute it."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3d_recognizer_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/" not in src and "knn_oracle" not in src, f
+
+
+def test_cabi_exports_every_declared_symbol(built_lib):
+    """include/r3d_b200.h <-> lib/libr3d_b200.so <-> _cabi.SIGNATURES agree (no compute calls)."""
+    import ctypes
+    import re
+    cabi = importlib.import_module("3d_recognizer_b200._cabi")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "r3d_b200.h")).read()
+    declared = set(re.findall(r"\b(r3d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(cabi.SIGNATURES), declared ^ set(cabi.SIGNATURES)
+    handle = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert cabi.lib().r3d_abi_version() == 1
+    assert cabi.lib().r3d_error_string(-2).decode().startswith("Not enough points")
+
+
+def test_sample_points_matches_reference_protocol():
+    """preprocessing.sample_points: same indices as the oracle restatement of preprocessing.py:35-62, global
+    RNG state untouched by consistent draws."""
+    pre = importlib.import_module("3d_recognizer_b200.preprocessing")
+    np.random.seed(123)
+    before = np.random.get_state()[1].copy()
+    a = pre.sample_points(140801, 2500, consistent=True)
+    assert list(a[:5]) == [110048, 47731, 136733, 49407, 61773]          # SURVEY.md §8c probe of the reference
+    assert np.array_equal(np.random.get_state()[1], before)
+    b = onet.sample_points(140801, 2500, consistent=True)
+    assert np.array_equal(a, b)
+    np.random.seed(5)
+    c = pre.sample_points(30, 2500, consistent=False)                     # up-sampling with duplicates (predict.py:22)
+    np.random.seed(5)
+    assert np.array_equal(c, onet.sample_points(30, 2500, consistent=False))
+    assert c.shape == (2500,) and c.max() < 30
