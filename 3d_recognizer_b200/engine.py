@@ -233,11 +233,19 @@ LFA_IMPL = lfa_block_fused
 
 
 # ------------------------------------------------------------------------------------ full forward
-def forward_autograd(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Tensor:
+def _device_permutation(permutation, device) -> torch.Tensor:
+    """The host-drawn permutation (modules.py:571) as an int64 device tensor; a device tensor passes through
+    (CUDA-graph replays update a static permutation buffer instead of copying inside the graph)."""
+    if isinstance(permutation, torch.Tensor):
+        return permutation.to(device=device, dtype=torch.int64)
+    return torch.from_numpy(np.ascontiguousarray(permutation)).to(device, non_blocking=True)
+
+
+def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     s = net.settings
     dec, L = s.decimation, len(s.layer_sizes)
     B, N, _ = inp.shape
-    perm = torch.from_numpy(np.ascontiguousarray(permutation)).to(inp.device, non_blocking=True)
+    perm = _device_permutation(permutation, inp.device)
 
     inp = inp.float()
     feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
@@ -348,7 +356,7 @@ def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Te
     B, N, _ = inp.shape
     P = folded_parameters(net)
     dev = inp.device
-    perm64 = torch.from_numpy(np.ascontiguousarray(permutation)).to(dev, non_blocking=True)
+    perm64 = _device_permutation(permutation, dev)
     perm = perm64.to(torch.int32)
     inp = inp.float().contiguous()
 

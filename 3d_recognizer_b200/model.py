@@ -24,7 +24,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import losses
+from . import engine, losses
 from .modules import RandLANet, RandLANetSettings, UpSampler
 from .preprocessing import sample_points
 
@@ -126,9 +126,10 @@ class Model:
         return predictions
 
     # ------------------------------------------------------------------ training step (trainer.py:107-119)
-    def make_optimizer(self, learning_rate: float = 1e-2) -> torch.optim.Optimizer:
-        """Adam with the trainer's default learning rate (trainer.py:78-81)."""
-        return torch.optim.Adam(self._model.parameters(), lr=learning_rate)
+    def make_optimizer(self, learning_rate: float = 1e-2, capturable: bool = False) -> torch.optim.Optimizer:
+        """Adam with the trainer's default learning rate (trainer.py:78-81).  ``capturable`` keeps the step
+        counter on the device so that the step can live inside a CUDA graph (GraphedTrainStep)."""
+        return torch.optim.Adam(self._model.parameters(), lr=learning_rate, capturable=capturable)
 
     def train_step(self, input, labels, optimizer: torch.optim.Optimizer, loss_function: str = "dice",
                    flat_grads=None) -> torch.Tensor:
@@ -152,3 +153,81 @@ class Model:
             flat_grads.allreduce_mean()
         optimizer.step()
         return loss.detach()
+
+
+class GraphedTrainStep:
+    """The training step of ``Model.train_step`` captured once into CUDA graphs and replayed.
+
+    At the reference's cloud size (2 500 points, train.py:50) a step is a few hundred small launches and is
+    bound by host launch overhead, not by the GPU; replaying a graph removes that.  Per step the host only draws
+    the point permutation from the global numpy RNG (same call, same position in the stream as
+    modules.py:571), copies it and the batch into static device buffers, and replays.  With ``flat_grads``
+    (data parallel) forward+backward and the optimiser step are two graphs with the NCCL all-reduce between.
+    Shapes are fixed at construction; the optimiser must be ``capturable`` (Model.make_optimizer(capturable=True))."""
+
+    def __init__(self, model: "Model", optimizer: torch.optim.Optimizer, batch_shape, loss_function: str = "dice",
+                 flat_grads=None, warmup: int = 3):
+        self.model, self.optimizer, self.flat = model, optimizer, flat_grads
+        net = model.module
+        dev = net.device
+        B, N, C = batch_shape
+        self.x = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((B, N), dtype=torch.int64, device=dev)
+        self.perm = torch.arange(N, dtype=torch.int64, device=dev)
+        self.perm_host = torch.empty(N, dtype=torch.int64).pin_memory()
+        crit = losses.get_loss(loss_function)
+        net.train()
+
+        def fwd_bwd():
+            logits = engine.forward_autograd(net, self.x, self.perm)
+            loss = crit(logits, self.y)
+            loss.backward()
+            return loss.detach()
+
+        # warm-up on a side stream (allocator, cuBLAS handles, lazy kernel attributes), as torch.cuda.graphs asks
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.perm.copy_(torch.from_numpy(np.random.permutation(N)))
+                self._zero()
+                fwd_bwd()
+                if self.flat is not None:
+                    self.flat.rebind()
+                optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
+        with torch.cuda.graph(self.graph):
+            if self.flat is not None:
+                self.flat.zero()
+            self.loss = fwd_bwd()
+            if self.flat is None:
+                optimizer.step()
+        if self.flat is not None:
+            self.flat.rebind()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                optimizer.step()
+
+    def _zero(self):
+        if self.flat is not None:
+            self.flat.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+
+    def __call__(self, input: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """input (B,N,3+F) fp32 and labels (B,N) int64, host (pinned) or device.  Returns the loss (a static
+        device scalar, overwritten by the next call)."""
+        self.perm_host.copy_(torch.from_numpy(np.random.permutation(self.perm.shape[0])))
+        self.perm.copy_(self.perm_host, non_blocking=True)
+        self.x.copy_(input, non_blocking=True)
+        self.y.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        if self.graph_opt is not None:
+            self.flat.allreduce_mean()
+            self.graph_opt.replay()
+        return self.loss

@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="training step eager instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     name = args.workload
@@ -364,6 +365,7 @@ def main():
         batch, gbatch = wl["per_gpu_batch"], wl["per_gpu_batch"] * world
     fp32_peak = measure_fp32_peak(cabi)
     extras = {}
+    eager_step = build_graph = None
 
     if wl["kind"] == "knn":
         metric, unit = "knn_queries_per_sec", "queries/s"
@@ -394,16 +396,30 @@ def main():
         unit = "points/s"
         if wl["kind"] == "train":
             metric = "train_step_points_per_sec"
-            opt = model.make_optimizer(1e-2)
+            opt = model.make_optimizer(1e-2, capturable=not args.no_graph)
             flat = parallel.FlatGradients(model.module) if world > 1 else None
             sink = torch.zeros((), device=dev)
 
-            def dev_step(i):
+            def eager_step(i):
                 sink.copy_(model.train_step(x_d[i % pool], y_d[i % pool], opt, "dice", flat))
 
-            def e2e_step(i):
-                loss = model.train_step(x_h[i % pool], y_h[i % pool], opt, "dice", flat)
-                loss.item()                                            # D2H read of the step's result
+            dev_step = eager_step
+            if args.no_graph:
+                def e2e_step(i):
+                    loss = model.train_step(x_h[i % pool], y_h[i % pool], opt, "dice", flat)
+                    loss.item()                                        # D2H read of the step's result
+            else:
+                gstep = None
+
+                def build_graph():
+                    nonlocal gstep
+                    gstep = model_mod.GraphedTrainStep(model, opt, (batch, n, 3), "dice", flat)
+
+                def dev_step(i):                                       # noqa: F811 (graph replay)
+                    sink.copy_(gstep(x_d[i % pool], y_d[i % pool]))
+
+                def e2e_step(i):
+                    gstep(x_h[i % pool], y_h[i % pool]).item()         # H2D of the batch + D2H of the loss
 
             h2d, d2h = batch * n * (12 + 8), 4
         else:
@@ -423,18 +439,27 @@ def main():
 
             h2d, d2h = batch * n * 12, batch * n * 2 * 4
 
-    # ---- device-resident timed region (value) with per-kernel timers and launch counting
+    # ---- eager instrumented pass: per-kernel CUDA events (C-ABI wrappers) and launch counting
+    eager = eager_step or dev_step
     for i in range(args.warmup):
-        dev_step(i)
+        eager(i)
     torch.cuda.synchronize()
+    n_eager = min(args.steps, 5)
     cabi.KERNEL_TIMERS = {}
     launches0 = L.r3d_launch_count()
-    with ClockSampler(local) as clk:
-        total_ms, wall = timed_steps(dev_step, args.steps, 1, world, flush)
-    launches = L.r3d_launch_count() - launches0
-    launches -= launches // (args.steps + 1)                  # the one extra untimed step inside timed_steps
+    eager_ms, _ = timed_steps(eager, n_eager, 0, world, flush)
+    launches_per_step = (L.r3d_launch_count() - launches0) // n_eager
     tab = kernel_table(cabi.KERNEL_TIMERS)
     cabi.KERNEL_TIMERS = None
+    eager_ms_per_step = eager_ms / n_eager
+    graphed = build_graph is not None
+    if graphed:
+        build_graph()
+
+    # ---- device-resident timed region (value)
+    with ClockSampler(local) as clk:
+        total_ms, wall = timed_steps(dev_step, args.steps, args.warmup, world, flush)
+    launches = launches_per_step * args.steps          # a graph replay re-issues the launches of one eager step
     ms_per_step = total_ms / args.steps
     value = sum_over_ranks(units_per_step, world) / (ms_per_step * 1e-3)
     clocks = clk.summary()
@@ -443,10 +468,11 @@ def main():
     e2e_ms, _ = timed_steps(e2e_step, args.steps, 2, world, flush)
     e2e_value = sum_over_ranks(units_per_step, world) / (e2e_ms / args.steps * 1e-3)
 
-    # the timers saw warm-up launches of timed_steps too: scale totals to the K timed steps
+    # per-kernel shares are relative to the EAGER instrumented step (event records are not capturable)
     for kname in tab:
-        tab[kname]["ms_per_step"] = tab[kname]["ms_total"] / (args.steps + 1)
-        tab[kname]["share_of_step"] = tab[kname]["ms_per_step"] / ms_per_step
+        tab[kname]["ms_per_step"] = tab[kname]["ms_total"] / n_eager
+        tab[kname]["share_of_eager_step"] = tab[kname]["ms_per_step"] / eager_ms_per_step
+        tab[kname]["launches"] //= n_eager
     roof = roofline_of(tab, peaks, fp32_peak)
 
     cpu_base = None
@@ -473,7 +499,9 @@ def main():
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base,
                     kernels={kn: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in kv.items()}
                              for kn, kv in tab.items()},
-                    fp32_peak_tflops=fp32_peak, wall_s_timed_region=wall, extras=extras)
+                    fp32_peak_tflops=fp32_peak, wall_s_timed_region=wall,
+                    execution=("cuda-graph replay" if graphed else "eager"), eager_ms_per_step=eager_ms_per_step,
+                    extras=extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
