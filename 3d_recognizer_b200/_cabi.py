@@ -42,6 +42,17 @@ SIGNATURES = {
     "r3d_pointwise": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
                               ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
                               c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_pointwise_stats": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
+                                    ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
+                                    c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "r3d_bn_apply": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                             ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p,
+                             c_void_p]),
+    "r3d_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int,
+                                  ctypes.c_float, c_void_p, c_void_p]),
+    "r3d_bn_bwd_dz": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, ctypes.c_float,
+                              c_void_p, c_void_p, c_void_p]),
+    "r3d_rowreduce_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p]),
     "r3d_fp32_probe_floats": (c_size_t, []),
     "r3d_fp32_probe": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(ctypes.c_double), c_void_p]),
 }

@@ -27,6 +27,9 @@
 namespace r3d {
 
 constexpr int kLfaThreads = 128;
+// 8 KB weight-ring stages keep the forward tile under 113 KB: two CTAs per SM, so one CTA's gather prologue
+// overlaps the other's GEMM (ncu of the 16 KB version: 1 CTA/SM, issue slots 41 % busy)
+constexpr int kLfaFwdStage = 2048;
 
 struct LfaArgs {
     const float* xyz;        // (B,N,3)
@@ -47,14 +50,14 @@ struct LfaArgs {
 
 template <int D, int K>
 struct LfaFwdSmem {
-    using C = LfaCfg<D, K, kLfaThreads>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
     static constexpr int P_FLOATS = C::H * 12 + 4 * C::H;     // w_rpe1 padded to 12 per channel + a1,b1,a2,b2
     static constexpr size_t BYTES = (size_t)(C::X_FLOATS + 2 * C::WSTAGE + P_FLOATS) * sizeof(float) + 16;
 };
 
 template <int D, int K, int STAGE>
 __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
-    using C = LfaCfg<D, K, kLfaThreads>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
     constexpr int H = C::H;
     extern __shared__ __align__(128) float smem[];
     float* X = smem;                               // [D][ROWS_PAD]
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
 
 template <int D, int K, int STAGE>
 static int launch_lfa(const LfaArgs& a, cudaStream_t st) {
-    using C = LfaCfg<D, K, kLfaThreads>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
     auto kern = lfa_pool_kernel<D, K, STAGE>;
     constexpr size_t smem = LfaFwdSmem<D, K>::BYTES;
     R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -14,7 +14,7 @@ namespace r3d {
 
 constexpr int kRpeRows = 16;  // rpe buffer: 10 encoding channels, a row of ones (col 10), 5 zero rows
 
-template <int D, int K, int THREADS = 128>
+template <int D, int K, int THREADS = 128, int WSTAGE_MAX = 4096>
 struct LfaCfg {
     static constexpr int NT = THREADS;
     static constexpr int H = D / 2;
@@ -28,7 +28,7 @@ struct LfaCfg {
     static constexpr int ROWS_PAD = ROWS_BASE + ((4 - ROWS_BASE % 32) + 32) % 32;
     static constexpr int ROWS = PTS * K;
     static constexpr int X_FLOATS = D * ROWS_PAD;
-    static constexpr int WSTAGE = (D * D < 4096) ? D * D : 4096;   // floats per weight-ring stage
+    static constexpr int WSTAGE = (D * D < WSTAGE_MAX) ? D * D : WSTAGE_MAX;   // floats per weight-ring stage
     static_assert(K % 16 == 0 && K >= 16 && K <= 64, "K must be a multiple of 16 up to 64");
     static_assert(D % 8 == 0 && TPP <= THREADS && THREADS % TPP == 0 && THREADS % 32 == 0, "unsupported width");
 };

@@ -44,6 +44,7 @@ struct PwArgs {
     int B;
     int n;                     // rows per cloud
     int transpose_out;         // 1: write y as (B, cout, n) — the reference's logits layout (modules.py:611)
+    double* stats;             // nullable (2*cout): += per-channel sum and sum of squares of the written values
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -155,9 +156,15 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
     }
 
     // ---- epilogue
+    __shared__ float csum[2][TN];
+    if (a.stats) {
+        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.f;
+        __syncthreads();
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int col = n0 + h * (TN / 2) + tc * 4;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         float sc[4], sh[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -172,7 +179,11 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
             const int b = (int)(m / a.n), n = (int)(m % a.n);
             float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = apply_act(fmaf(acc[i][h * 4 + j], sc[j], sh[j]), a.act, a.slope);
+            for (int j = 0; j < 4; ++j) {
+                o[j] = apply_act(fmaf(acc[i][h * 4 + j], sc[j], sh[j]), a.act, a.slope);
+                s1[j] += o[j];
+                s2[j] = fmaf(o[j], o[j], s2[j]);
+            }
             if (a.transpose_out) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -186,6 +197,22 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
                     for (int j = 0; j < 4; ++j)
                         if (col + j < a.cout) yr[col + j] = o[j];
                 }
+            }
+        }
+        if (a.stats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&csum[0][h * (TN / 2) + tc * 4 + j], s1[j]);
+                atomicAdd(&csum[1][h * (TN / 2) + tc * 4 + j], s2[j]);
+            }
+        }
+    }
+    if (a.stats) {
+        __syncthreads();
+        for (int i = tid; i < TN; i += NT) {
+            if (n0 + i < a.cout) {
+                atomicAdd(a.stats + n0 + i, (double)csum[0][i]);
+                atomicAdd(a.stats + a.cout + n0 + i, (double)csum[1][i]);
             }
         }
     }
@@ -202,8 +229,10 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
     for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x) Ws[i] = a.wT[i];
     __syncthreads();
     const long long M = (long long)a.B * a.n;
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
+    const long long m_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = m_raw < M;
+    if (!live && !a.stats) return;
+    const long long m = live ? m_raw : M - 1;
     const int b = (int)(m / a.n), n = (int)(m % a.n);
     float acc[kPwSmallMaxCout];
 #pragma unroll
@@ -229,10 +258,24 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
         if (j >= a.cout) break;
         const float sc = a.scale ? a.scale[j] : 1.f, sh = a.shift ? a.shift[j] : 0.f;
         const float o = apply_act(fmaf(acc[j], sc, sh), a.act, a.slope);
-        if (a.transpose_out)
-            a.y[(size_t)b * a.y_bstride + (size_t)j * a.n + n] = o;
-        else
-            a.y[(size_t)b * a.y_bstride + (size_t)n * a.y_ld + j] = o;
+        if (live) {
+            if (a.transpose_out)
+                a.y[(size_t)b * a.y_bstride + (size_t)j * a.n + n] = o;
+            else
+                a.y[(size_t)b * a.y_bstride + (size_t)n * a.y_ld + j] = o;
+        }
+        if (a.stats) {
+            float s1 = live ? o : 0.f, s2 = live ? o * o : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(a.stats + j, (double)s1);
+                atomicAdd(a.stats + a.cout + j, (double)s2);
+            }
+        }
     }
 }
 
@@ -240,11 +283,26 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
 
 using namespace r3d;
 
+extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
+                                   long long gidx_bstride, const float* xb, long long xb_bstride, int cb,
+                                   const float* wT, const float* scale, const float* shift, int act, float slope,
+                                   float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
+                                   double* stats, r3d_stream_t stream);
+
 extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
                              long long gidx_bstride, const float* xb, long long xb_bstride, int cb, const float* wT,
                              const float* scale, const float* shift, int act, float slope, float* y,
                              long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
                              r3d_stream_t stream) {
+    return r3d_pointwise_stats(xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
+                               y, y_bstride, y_ld, cout, B, n, transpose_out, nullptr, stream);
+}
+
+extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
+                                   long long gidx_bstride, const float* xb, long long xb_bstride, int cb,
+                                   const float* wT, const float* scale, const float* shift, int act, float slope,
+                                   float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
+                                   double* stats, r3d_stream_t stream) {
     if (B < 0 || n < 0 || ca <= 0 || cb < 0 || cout <= 0 || act < 0 || act > 2) return R3D_EINVAL;
     if (B == 0 || n == 0) return R3D_OK;
     if (!xa || !wT || !y || (cb > 0 && !xb)) return R3D_EINVAL;
@@ -258,7 +316,7 @@ extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, cons
     // vector loads need every source row 16-byte aligned
     if ((ca % 4 == 0 && cb % 4 == 0) && ((xa_bstride % 4) || (cb > 0 && (xb_bstride % 4)))) return R3D_EALIGN;
     PwArgs a{xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
-             y, y_bstride, y_ld, cout, B, n, transpose_out};
+             y, y_bstride, y_ld, cout, B, n, transpose_out, stats};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)B * n;
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {

@@ -1,0 +1,284 @@
+// Train-mode companions of the per-point layer kernel (pointwise.cu), sm_100a.
+//
+// A SharedMLP in training mode (randlanet/utils/modules.py:60-104: 1x1 conv -> BatchNorm2d(eps 1e-6, momentum
+// 0.99) with BATCH statistics -> activation) over M = B*N rows runs as
+//   forward : r3d_pointwise_stats  z = W x, per-channel sum / sum of squares (fp64) in the GEMM epilogue
+//             r3d_bn_apply         y = act(a z + c), a = gamma * rstd, c = beta - a * mean; running statistics
+//   backward: r3d_bn_bwd_reduce    s1 = sum du, s2 = sum du * zhat   (du = dy * act'(a z + c))
+//             r3d_bn_bwd_dz        dz = a (du - s1/M - zhat s2/M)    (BatchNorm backward, batch statistics)
+//             r3d_pointwise        dx = dz W                         (the forward GEMM kernel on the transposed weight)
+//             r3d_rowreduce_gemm   dW = dz^T x                       (row-reduction GEMM, split over row chunks)
+// All tensors are dense row-major (M, C); C is a multiple of 4 for the BatchNorm kernels.
+// Backward reference: autograd of modules.py:92-104 as driven by trainer.py:115-119.
+#include "common.cuh"
+
+namespace r3d {
+
+constexpr int kBnMaxC = 1024;
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+__device__ __forceinline__ float act_grad(float u, int act, float slope) {
+    if (act == 1) return u > 0.f ? 1.f : 0.f;
+    if (act == 2) return u > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// ---------------------------------------------------------------------------------------- bn_apply
+// save: (3, C) = a (gamma * rstd), mean (of z, without the conv bias), rstd
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ z, const double* __restrict__ stats,
+                                                       long long M, int C, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ bias,
+                                                       float eps, float momentum, float* __restrict__ running_mean,
+                                                       float* __restrict__ running_var,
+                                                       long long* __restrict__ num_batches, int act, float slope,
+                                                       float* __restrict__ y, float* __restrict__ save) {
+    __shared__ float sa[kBnMaxC], sc[kBnMaxC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double mean = stats[c] / (double)M;
+        double var = stats[C + c] / (double)M - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float a = gamma[c] * rstd;
+        sa[c] = a;
+        sc[c] = beta[c] - a * (float)mean;
+        if (blockIdx.x == 0) {
+            save[c] = a;
+            save[C + c] = (float)mean;
+            save[2 * C + c] = rstd;
+            if (running_mean) {
+                const double unbiased = var * ((double)M / (double)(M > 1 ? M - 1 : 1));
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mean + (bias ? bias[c] : 0.f));
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
+    __syncthreads();
+    const long long total4 = M * C / 4;
+    const int c4 = C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4) * 4;
+        float4 v = reinterpret_cast<const float4*>(z)[i];
+        v.x = act_fwd(fmaf(v.x, sa[c + 0], sc[c + 0]), act, slope);
+        v.y = act_fwd(fmaf(v.y, sa[c + 1], sc[c + 1]), act, slope);
+        v.z = act_fwd(fmaf(v.z, sa[c + 2], sc[c + 2]), act, slope);
+        v.w = act_fwd(fmaf(v.w, sa[c + 3], sc[c + 3]), act, slope);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------------- bn_bwd_reduce
+// stats2 (2C fp64): [c] += sum du, [C + c] += sum du * zhat
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            long long M, int C, const float* __restrict__ save,
+                                                            const float* __restrict__ beta, int act, float slope,
+                                                            double* __restrict__ stats2) {
+    const int c4n = C / 4;                       // column quads
+    const int rows_per_pass = blockDim.x / c4n;  // >= 1 (C <= 1024)
+    const int q = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+    float a[4], mean[4], rstd[4], cc[4];
+    const bool active = rl < rows_per_pass;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j] = save[q * 4 + j];
+        mean[j] = save[C + q * 4 + j];
+        rstd[j] = save[2 * C + q * 4 + j];
+        cc[j] = beta[q * 4 + j] - a[j] * mean[j];
+    }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        for (long long r = (long long)blockIdx.x * rows_per_pass + rl; r < M; r += (long long)gridDim.x * rows_per_pass) {
+            const float4 g = reinterpret_cast<const float4*>(dy + r * C)[q];
+            const float4 v = reinterpret_cast<const float4*>(z + r * C)[q];
+            const float gv[4] = {g.x, g.y, g.z, g.w}, zv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float du = gv[j] * act_grad(fmaf(zv[j], a[j], cc[j]), act, slope);
+                s1[j] += du;
+                s2[j] = fmaf(du, (zv[j] - mean[j]) * rstd[j], s2[j]);
+            }
+        }
+    }
+    __shared__ float red[2][kBnMaxC];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i < C ? i : kBnMaxC + (i - C)] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&red[0][q * 4 + j], s1[j]);
+            atomicAdd(&red[1][q * 4 + j], s2[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(stats2 + c, (double)red[0][c]);
+        atomicAdd(stats2 + C + c, (double)red[1][c]);
+    }
+}
+
+// --------------------------------------------------------------------------------------- bn_bwd_dz
+__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                        long long M, int C, const float* __restrict__ save,
+                                                        const float* __restrict__ beta, int act, float slope,
+                                                        const double* __restrict__ stats2, float* __restrict__ dz) {
+    __shared__ float sa[kBnMaxC], sm[kBnMaxC], sr[kBnMaxC], sc[kBnMaxC], m1[kBnMaxC], m2[kBnMaxC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        sa[c] = save[c];
+        sm[c] = save[C + c];
+        sr[c] = save[2 * C + c];
+        sc[c] = beta[c] - sa[c] * sm[c];
+        m1[c] = (float)(stats2[c] / (double)M);
+        m2[c] = (float)(stats2[C + c] / (double)M);
+    }
+    __syncthreads();
+    const long long total4 = M * C / 4;
+    const int c4 = C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4) * 4;
+        const float4 g = reinterpret_cast<const float4*>(dy)[i];
+        const float4 v = reinterpret_cast<const float4*>(z)[i];
+        const float gv[4] = {g.x, g.y, g.z, g.w}, zv[4] = {v.x, v.y, v.z, v.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float du = gv[j] * act_grad(fmaf(zv[j], sa[c + j], sc[c + j]), act, slope);
+            const float zh = (zv[j] - sm[c + j]) * sr[c + j];
+            o[j] = sa[c + j] * (du - m1[c + j] - zh * m2[c + j]);
+        }
+        reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ rowreduce_gemm
+// out[ca][cb] += sum_m A[m][ca] * B[m][cb]   (A: M x Ca, B: M x Cb, dense row-major; out: Ca x Cb, ld_out)
+// CTA tile 64 x 64 outputs, 256 threads (4 x 4 per thread), rows chunked over gridDim.z; fp32 atomics.
+constexpr int kRrTile = 64;
+constexpr int kRrKC = 16;
+
+__global__ void __launch_bounds__(256) rowreduce_gemm_kernel(const float* __restrict__ A, int Ca,
+                                                             const float* __restrict__ Bm, int Cb, long long M,
+                                                             long long rows_per_cta, float* __restrict__ out,
+                                                             int ld_out) {
+    __shared__ __align__(16) float As[kRrKC][kRrTile];
+    __shared__ __align__(16) float Bs[kRrKC][kRrTile];
+    const int tid = threadIdx.x;
+    const int a0 = blockIdx.x * kRrTile, b0 = blockIdx.y * kRrTile;
+    const long long r_lo = (long long)blockIdx.z * rows_per_cta;
+    const long long r_hi = min(M, r_lo + rows_per_cta);
+    const int ta = tid / 16, tb = tid % 16;   // thread tile: rows ta*4.., cols tb*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (long long r0 = r_lo; r0 < r_hi; r0 += kRrKC) {
+        // stage 16 rows x 64 columns of both operands (zero-filled outside)
+        for (int i = tid; i < kRrKC * kRrTile; i += 256) {
+            const int k = i / kRrTile, c = i % kRrTile;
+            const long long r = r0 + k;
+            As[k][c] = (r < r_hi && a0 + c < Ca) ? A[r * Ca + a0 + c] : 0.f;
+            Bs[k][c] = (r < r_hi && b0 + c < Cb) ? Bm[r * Cb + b0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kRrKC; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ta * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tb * 4]);
+            const float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ca = a0 + ta * 4 + i, cb = b0 + tb * 4 + j;
+            if (ca < Ca && cb < Cb) atomicAdd(out + (size_t)ca * ld_out + cb, acc[i][j]);
+        }
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+static int grid_for(long long work_items, int per_block) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    const long long cap = (long long)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int r3d_bn_apply(const float* z, const double* stats, long long M, int C, const float* gamma,
+                            const float* beta, const float* bias, float eps, float momentum, float* running_mean,
+                            float* running_var, long long* num_batches, int act, float slope, float* y, float* save,
+                            r3d_stream_t stream) {
+    if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
+    if (M == 0) return R3D_OK;
+    if (!z || !stats || !gamma || !beta || !y || !save) return R3D_EINVAL;
+    if (!is_aligned(z, 16) || !is_aligned(y, 16)) return R3D_EALIGN;
+    bn_apply_kernel<<<grid_for(M * C / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, stats, M, C, gamma, beta, bias, eps, momentum, running_mean, running_var, num_batches, act, slope, y, save);
+    R3D_LAUNCH_CHECK("bn_apply_kernel");
+    return R3D_OK;
+}
+
+extern "C" int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, int C, const float* save,
+                                 const float* beta, int act, float slope, double* stats2, r3d_stream_t stream) {
+    if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
+    if (M == 0) return R3D_OK;
+    if (!dy || !z || !save || !beta || !stats2) return R3D_EINVAL;
+    if (!is_aligned(dy, 16) || !is_aligned(z, 16)) return R3D_EALIGN;
+    const int rows_per_pass = 256 / (C / 4);
+    bn_bwd_reduce_kernel<<<grid_for(M, rows_per_pass * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, z, M, C, save, beta, act, slope, stats2);
+    R3D_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    return R3D_OK;
+}
+
+extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                             int act, float slope, const double* stats2, float* dz, r3d_stream_t stream) {
+    if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
+    if (M == 0) return R3D_OK;
+    if (!dy || !z || !save || !beta || !stats2 || !dz) return R3D_EINVAL;
+    if (!is_aligned(dy, 16) || !is_aligned(z, 16) || !is_aligned(dz, 16)) return R3D_EALIGN;
+    bn_bwd_dz_kernel<<<grid_for(M * C / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, z, M, C, save, beta, act,
+                                                                                             slope, stats2, dz);
+    R3D_LAUNCH_CHECK("bn_bwd_dz_kernel");
+    return R3D_OK;
+}
+
+extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
+                                  r3d_stream_t stream) {
+    if (M < 0 || Ca <= 0 || Cb <= 0) return R3D_EINVAL;
+    if (M == 0) return R3D_OK;
+    if (!A || !Bm || !out) return R3D_EINVAL;
+    if (ld_out == 0) ld_out = Cb;
+    const int ga = ceil_div(Ca, kRrTile), gb = ceil_div(Cb, kRrTile);
+    // enough row chunks to fill the machine, at least 256 rows each
+    long long chunks = ((long long)kNumSMs * 4 + ga * gb - 1) / (ga * gb);
+    const long long max_chunks = (M + 255) / 256;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    long long rows_per_cta = (M + chunks - 1) / chunks;
+    rows_per_cta = (rows_per_cta + kRrKC - 1) / kRrKC * kRrKC;
+    chunks = (M + rows_per_cta - 1) / rows_per_cta;
+    dim3 grid(ga, gb, (unsigned)chunks);
+    rowreduce_gemm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, rows_per_cta, out,
+                                                                               ld_out);
+    R3D_LAUNCH_CHECK("rowreduce_gemm_kernel");
+    return R3D_OK;
+}

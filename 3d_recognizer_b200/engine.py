@@ -55,12 +55,74 @@ def batch_norm_lastdim(bn: torch.nn.BatchNorm2d, y: torch.Tensor) -> torch.Tenso
     return out.view_as(y)
 
 
+class _SharedMLPTrainFn(torch.autograd.Function):
+    """SharedMLP with train-mode BatchNorm on dense rows x (M,Cin): the sm_100a per-point kernels forward
+    (GEMM + batch statistics, normalise + activation) and backward (BatchNorm backward, dx GEMM, dW row-reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, bn, act, slope):
+        x = x.contiguous()
+        cout = w.shape[0]
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device)
+        z = ops.pointwise(x.unsqueeze(0), w.t().contiguous(), stats=stats).squeeze(0)
+        y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
+        ctx.act, ctx.slope = act, slope
+        ctx.save_for_backward(x, w, z, save, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z, save, beta = ctx.saved_tensors
+        dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope)
+        dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
+        dw = ops.rowreduce_gemm(dz, x)
+        # the conv bias cancels against the batch mean: its gradient is exactly zero
+        return dx, dw, torch.zeros_like(dgamma), dgamma, dbeta, None, None, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on dense rows (SharedMLP without BatchNorm: the class logits, modules.py:525-527)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x = x.contiguous()
+        ctx.save_for_backward(x, w)
+        return ops.pointwise(x.unsqueeze(0), w.t().contiguous(), None, bias.contiguous()).squeeze(0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.pointwise(dy.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
+        return dx, ops.rowreduce_gemm(dy, x), dy.sum(dim=0)
+
+
+def _kernel_layer_ok(x: torch.Tensor, bn) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and (bn is None or (bn.training and bn.weight.shape[0] % 4 == 0))
+
+
 def shared_mlp(smlp, x: torch.Tensor) -> torch.Tensor:
-    """SharedMLP on a channel-last tensor (..., C_in) -> (..., C_out)."""
+    """SharedMLP on a channel-last tensor (..., C_in) -> (..., C_out).  Train mode on a CUDA device runs the
+    per-point kernels (forward and backward); otherwise (eval with gradients, CPU host-logic tests, fp64
+    arbiters) the same math as differentiable tensor ops."""
+    bn = smlp.batch_norm
+    if USE_POINTWISE_KERNELS and _kernel_layer_ok(x, bn):
+        w = conv_weight_2d(smlp)
+        x2 = x.reshape(-1, x.shape[-1])
+        if bn is None:
+            y = _LinearFn.apply(x2, w, smlp.conv.bias)
+            return _activation(y, smlp.activation).view(*x.shape[:-1], w.shape[0])
+        act, slope = _act_of(smlp)
+        y = _SharedMLPTrainFn.apply(x2, w, smlp.conv.bias, bn.weight, bn.bias, bn, act, slope)
+        return y.view(*x.shape[:-1], w.shape[0])
     y = F.linear(x, conv_weight_2d(smlp), smlp.conv.bias)
-    if smlp.batch_norm is not None:
-        y = batch_norm_lastdim(smlp.batch_norm, y)
+    if bn is not None:
+        y = batch_norm_lastdim(bn, y)
     return _activation(y, smlp.activation)
+
+
+# train-mode per-point layers on the sm_100a kernels (False: differentiable tensor ops, for A/B tests)
+USE_POINTWISE_KERNELS = True
 
 
 def gather_points(feat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
@@ -248,8 +310,13 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     perm = _device_permutation(permutation, inp.device)
 
     inp = inp.float()
-    feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
-    feat = F.leaky_relu(batch_norm_lastdim(net.bn_start[0], feat), net.bn_start[1].negative_slope)
+    bn0 = net.bn_start[0]
+    if USE_POINTWISE_KERNELS and _kernel_layer_ok(inp, bn0):
+        feat = _SharedMLPTrainFn.apply(inp.reshape(B * N, -1), net.fc_start.weight, net.fc_start.bias, bn0.weight,
+                                       bn0.bias, bn0, "lrelu", float(net.bn_start[1].negative_slope)).view(B, N, -1)
+    else:
+        feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
+        feat = F.leaky_relu(batch_norm_lastdim(bn0, feat), net.bn_start[1].negative_slope)
     xyz = inp[..., :3].index_select(1, perm).contiguous()
     feat = feat.index_select(1, perm)
 

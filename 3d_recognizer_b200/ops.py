@@ -58,7 +58,7 @@ def knn(support: torch.Tensor, query: torch.Tensor, k: int, *, idx64: bool = Tru
             out["dist_sq"] = torch.empty((B, Nq, k), dtype=torch.float32, device=dev)
         wbytes = L.r3d_knn_workspace_bytes(B, Ns, Nq, k)
         ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
-        with _cabi.kernel_timer("knn_k1" if k == 1 else "knn", flops=8.0 * B * Ns * Nq,
+        with _cabi.kernel_timer(f"knn_k{k}[Ns={Ns}]", flops=8.0 * B * Ns * Nq,
                                 bytes=4.0 * B * (3 * Ns + 3 * Nq + Nq * k * (len(out) + ("idx64" in out)))):
             rc = L.r3d_knn(ctypes.c_void_p(support.data_ptr()), s_stride, ctypes.c_void_p(query.data_ptr()),
                            q_stride, B, Ns, Nq, k,
@@ -114,7 +114,7 @@ def lfa_pool(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Ten
     # algorithmic work per point: flops 2K(10h + d^2 + d) [+ 2K h^2 in stage 2]
     flops = float(B) * N * (2 * K * (10 * h + d * d + d + (h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d)
-    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}", flops=flops, bytes=nbytes):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_pool(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
                                       _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T),
                                       _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_scoreT), _cabi.ptr(pooled),
@@ -128,7 +128,8 @@ _ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2}
 
 def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=None, slope: float = 0.0,
               gidx: Optional[torch.Tensor] = None, xb: Optional[torch.Tensor] = None, n_rows: Optional[int] = None,
-              transpose_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              transpose_out: bool = False, out: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-point layer y = act(scale * (W [xa[g] ; xb]) + shift) (C ABI ``r3d_pointwise``).
     xa (B,na,ca) [gathered through gidx int32 (n,) shared or (B,n) per cloud], xb (B,n,cb) optional,
     wT (ca+cb, cout).  Returns (B,n,cout), or (B,cout,n) with ``transpose_out``."""
@@ -153,11 +154,65 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
     flops = 2.0 * B * n * (ca + cb) * cout
     nbytes = 4.0 * B * n * (ca + cb + cout)
     with torch.cuda.device(dev), _cabi.kernel_timer("pointwise", flops=flops, bytes=nbytes):
-        rc = _cabi.lib().r3d_pointwise(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
-                                       _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act], float(slope),
-                                       _cabi.ptr(out), 0, 0, cout, B, n, 1 if transpose_out else 0,
-                                       _cabi.stream_ptr(dev))
+        rc = _cabi.lib().r3d_pointwise_stats(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
+                                             _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act],
+                                             float(slope), _cabi.ptr(out), 0, 0, cout, B, n,
+                                             1 if transpose_out else 0, _cabi.ptr(stats), _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_pointwise")
+    return out
+
+
+def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bias: Optional[torch.Tensor], act,
+             slope: float = 0.0):
+    """Train-mode BatchNorm + activation of a per-point layer (C ABI ``r3d_bn_apply``): z (M,C) conv output without
+    bias, stats (2C) fp64 from ``pointwise(..., stats=)``.  Updates bn's running statistics in place.
+    Returns (y (M,C), save (3,C) = a, mean, rstd)."""
+    M, C = z.shape
+    y = torch.empty_like(z)
+    save = torch.empty((3, C), dtype=torch.float32, device=z.device)
+    track = bn.track_running_stats and bn.running_mean is not None
+    with torch.cuda.device(z.device), _cabi.kernel_timer("bn_apply", flops=4.0 * M * C, bytes=8.0 * M * C):
+        rc = _cabi.lib().r3d_bn_apply(_cabi.ptr(z), _cabi.ptr(stats), M, C, _cabi.ptr(bn.weight.detach()),
+                                      _cabi.ptr(bn.bias.detach()), _cabi.ptr(bias.detach()) if bias is not None else None,
+                                      float(bn.eps), float(bn.momentum),
+                                      _cabi.ptr(bn.running_mean) if track else None,
+                                      _cabi.ptr(bn.running_var) if track else None,
+                                      _cabi.ptr(bn.num_batches_tracked) if track else None, _ACT[act], float(slope),
+                                      _cabi.ptr(y), _cabi.ptr(save), _cabi.stream_ptr(z.device))
+    _cabi.check(rc, "r3d_bn_apply")
+    return y, save
+
+
+def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0):
+    """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd_reduce`` + ``r3d_bn_bwd_dz``).
+    Returns (dz (M,C), dgamma (C), dbeta (C))."""
+    M, C = z.shape
+    dy = dy.contiguous()
+    stats2 = torch.zeros(2 * C, dtype=torch.float64, device=z.device)
+    dz = torch.empty_like(z)
+    L = _cabi.lib()
+    with torch.cuda.device(z.device), _cabi.kernel_timer("bn_backward", flops=12.0 * M * C, bytes=20.0 * M * C):
+        rc = L.r3d_bn_bwd_reduce(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
+                                 float(slope), _cabi.ptr(stats2), _cabi.stream_ptr(z.device))
+        _cabi.check(rc, "r3d_bn_bwd_reduce")
+        rc = L.r3d_bn_bwd_dz(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
+                             float(slope), _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.stream_ptr(z.device))
+    _cabi.check(rc, "r3d_bn_bwd_dz")
+    s2 = stats2.float()
+    return dz, s2[C:], s2[:C]
+
+
+def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a (M,Ca), b (M,Cb) dense -> a^T b (Ca,Cb): the weight gradient of a per-point layer (``r3d_rowreduce_gemm``)."""
+    a, b = a.contiguous(), b.contiguous()
+    M, Ca = a.shape
+    Cb = b.shape[1]
+    out = torch.zeros((Ca, Cb), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _cabi.kernel_timer("rowreduce_gemm", flops=2.0 * M * Ca * Cb,
+                                                         bytes=4.0 * M * (Ca + Cb)):
+        rc = _cabi.lib().r3d_rowreduce_gemm(_cabi.ptr(a), Ca, _cabi.ptr(b), Cb, M, _cabi.ptr(out), Cb,
+                                            _cabi.stream_ptr(a.device))
+    _cabi.check(rc, "r3d_rowreduce_gemm")
     return out
 
 
@@ -184,7 +239,7 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
         g2c = acc[o + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
-    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_bwd", flops=flops, bytes=nbytes):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_pool_bwd(
             stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
             _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T), _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_rpe2s),
@@ -211,7 +266,7 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
         g1 = torch.zeros((h, 16), dtype=torch.float32, device=dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
-    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}", flops=flops, bytes=nbytes):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_moments(mode, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1),
                                          _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.raw(m_rpe), _cabi.raw(m_r1),
                                          _cabi.raw(s_r1), _cabi.ptr(gsym), _cabi.ptr(gsum), _cabi.raw(g1), B, N, K, d,

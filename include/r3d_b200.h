@@ -158,6 +158,31 @@ int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* 
                   const float* shift, int act, float slope, float* y, long long y_bstride, int y_ld, int cout,
                   int B, int n, int transpose_out, r3d_stream_t stream);
 
+/* r3d_pointwise that also accumulates, per output channel, the sum and the sum of squares (fp64, stats[2*cout],
+ * caller-zeroed) of the values it writes: the batch statistics of a train-mode BatchNorm (modules.py:86-90). */
+int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int32_t* gidx, long long gidx_bstride,
+                        const float* xb, long long xb_bstride, int cb, const float* wT, const float* scale,
+                        const float* shift, int act, float slope, float* y, long long y_bstride, int y_ld, int cout,
+                        int B, int n, int transpose_out, double* stats, r3d_stream_t stream);
+
+/* ------------------------------------------------------------- train-mode BatchNorm of a per-point layer
+ * Forward tail of SharedMLP in training mode (modules.py:92-104): z (M,C) = conv output WITHOUT bias, stats from
+ * r3d_pointwise_stats.  y = act(a z + c) with a = gamma*rstd, c = beta - a*mean (the conv bias cancels against
+ * the batch mean); running_mean/var (nullable) are updated like BatchNorm2d (momentum, unbiased variance; the
+ * bias is added back to the mean), *num_batches (nullable) is incremented; save (3,C) = a, mean, rstd. */
+int r3d_bn_apply(const float* z, const double* stats, long long M, int C, const float* gamma, const float* beta,
+                 const float* bias, float eps, float momentum, float* running_mean, float* running_var,
+                 long long* num_batches, int act, float slope, float* y, float* save, r3d_stream_t stream);
+/* Backward: du = dy * act'(a z + c); stats2[2C] (fp64, caller-zeroed) += (sum du, sum du*zhat) = (dbeta, dgamma);
+ * then dz = a (du - mean(du) - zhat * mean(du*zhat)). */
+int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                      int act, float slope, double* stats2, r3d_stream_t stream);
+int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
+                  float slope, const double* stats2, float* dz, r3d_stream_t stream);
+/* Weight gradient of a per-point layer: out (Ca,Cb; ld_out, caller-zeroed) += A^T B for A (M,Ca), B (M,Cb). */
+int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
+                       r3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------ FP32 peak probe
  * Roofline denominator of the CUDA-core kernels, measured live by bench.py (MEASURED_PEAKS.json has
  * HBM and bf16 tensor peaks only).  mode 0 = scalar FFMA, 1 = packed FFMA2 (f32x2).  `out` is a device

@@ -72,10 +72,14 @@ def _lfa_block_case(mods, n_in, d, K, N, train, seed):
     xb = x.clone().requires_grad_(True)
     xc = x.double().requires_grad_(True)
     ya = engine.lfa_block_fused(lfa_a, xyz, xa)
-    yb = engine.lfa_block(lfa_b, xyz, xb)
-    yc = engine.lfa_block(lfa_c, xyz.double(), xc)
     (ya * gout).sum().backward()
-    (yb * gout).sum().backward()
+    engine.USE_POINTWISE_KERNELS = False            # plain composition: tensor ops only (KNN excepted)
+    try:
+        yb = engine.lfa_block(lfa_b, xyz, xb)
+        (yb * gout).sum().backward()
+    finally:
+        engine.USE_POINTWISE_KERNELS = True
+    yc = engine.lfa_block(lfa_c, xyz.double(), xc)
     (yc * gout.double()).sum().backward()
     fails = []
 
@@ -122,6 +126,45 @@ def test_lfa_block_fused_vs_autograd(mods, n_in, d, K, N, train):
             return
         history.append(fails[:3])
     raise AssertionError(history)
+
+
+@pytest.mark.parametrize("M,cin,cout,act", [(5000, 8, 8, "lrelu"), (1237, 3, 8, "lrelu"), (2048, 64, 32, "relu"),
+                                            (700, 512, 512, "relu"), (333, 1024, 256, "relu"), (40000, 16, 32, None)])
+def test_shared_mlp_train_kernels_vs_torch(mods, M, cin, cout, act):
+    """Train-mode SharedMLP (GEMM + batch-stat BatchNorm + activation) forward, dx, dW, dgamma, dbeta and the
+    running statistics: sm_100a per-point kernels vs fp64 tensor ops."""
+    import copy
+    modules, engine, _ = mods
+    dev = torch.device("cuda")
+    torch.manual_seed(M + cin)
+    activation = {"relu": torch.nn.ReLU(), "lrelu": torch.nn.LeakyReLU(0.2), None: None}[act]
+    la = modules.SharedMLP(cin, cout, activation=activation).to(dev)
+    with torch.no_grad():
+        la.batch_norm.weight.uniform_(0.7, 1.3)
+        la.batch_norm.bias.normal_(0, 0.1)
+    lc = copy.deepcopy(la).double()
+    la.train()
+    lc.train()
+    x = torch.randn(2, M // 2, cin, device=dev) * 0.7 + 0.3
+    g = torch.randn(2, M // 2, cout, device=dev)
+    xa = x.clone().requires_grad_(True)
+    xc = x.double().requires_grad_(True)
+    ya = engine.shared_mlp(la, xa)
+    yc = engine.shared_mlp(lc, xc)
+    assert rel_err(ya.detach(), yc.detach()) < 1e-5
+    (ya * g).sum().backward()
+    (yc * g.double()).sum().backward()
+    assert rel_err(xa.grad, xc.grad) < TOL
+    for (k, pa), (_, pc) in zip(la.named_parameters(), lc.named_parameters()):
+        if k == "conv.bias":
+            assert float(pa.grad.abs().max()) == 0.0
+            continue
+        assert rel_err(pa.grad, pc.grad) < TOL, k
+    for (k, va), (_, vc) in zip(la.state_dict().items(), lc.state_dict().items()):
+        if "running" in k:
+            assert torch.allclose(va.double(), vc, rtol=1e-5, atol=1e-6), k
+        if "num_batches" in k:
+            assert int(va) == int(vc) == 1
 
 
 @pytest.mark.parametrize("name", list(E2E))
