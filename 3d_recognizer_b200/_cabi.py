@@ -39,12 +39,17 @@ SIGNATURES = {
                          [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_moments": (c_int, [c_int, c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
                         [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_bn_from_moments": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
+                                    c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_bn_from_moments_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double] +
+                                [c_void_p] * 10 + [c_void_p]),
     "r3d_pointwise": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
                               ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
                               c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_pointwise_stats": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
                                     ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
-                                    c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+                                    c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "r3d_bn_apply": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float,
                              ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p,
                              c_void_p]),

@@ -127,10 +127,39 @@ __device__ __noinline__ float list_insert(float* ld, int* li, int K, int stride,
     return ld[(K - 1) * stride];
 }
 
+// Same insertion without a loop-carried shared-memory dependency, for a compile-time list length KT: all KT
+// entries are read with independent loads, the insertion point is a count, and the shifted tail is written back
+// with predicated stores.  (ncu of the loop version: the dependent LDS chain of up to K iterations, paid by the
+// whole warp for its slowest lane, dominated small clouds — 206 us for 8 x 625 points.)
+template <int KT>
+__device__ __noinline__ float list_insert_t(float* ld, int* li, int stride, float d, int id) {
+    float vd[KT];
+    int vi[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        vd[k] = ld[k * stride];
+        vi[k] = li[k * stride];
+    }
+    int pos = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) pos += (vd[k] <= d) ? 1 : 0;   // stable: an equal d2 keeps the earlier (lower) index first
+#pragma unroll
+    for (int k = KT - 1; k >= 1; --k) {
+        if (k > pos) {
+            ld[k * stride] = vd[k - 1];
+            li[k * stride] = vi[k - 1];
+        }
+    }
+    ld[pos * stride] = d;     // pos <= KT-1 because the caller admitted d < vd[KT-1]
+    li[pos * stride] = id;
+    return (pos == KT - 1) ? d : vd[KT - 2];
+}
+
 // ------------------------------------------------------------------------------------- the kernel
 // VARIANT 0: contract d2 for every pair.  1: FMA prefilter, scalar.  2: FMA prefilter, packed f32x2.
 // K1: K == 1, best candidate kept in registers (decoder / post-process 1-NN, modules.py:358).
-template <int VARIANT, int Q, bool K1>
+// KT: compile-time K (16 or 32) for the loop-free insertion, 0 = any K (loop version).
+template <int VARIANT, int Q, bool K1, int KT = 0>
 __global__ void __launch_bounds__(kKnnThreads, 2) knn_kernel(const float* __restrict__ sup_soa, int Nsp,
                                                           const float* __restrict__ query, long long q_stride,
                                                           int Ns, int Nq, int K,
@@ -242,8 +271,13 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_kernel(const float* __rest
                                 thr[q] = d;
                                 best_i[q] = base + j + u;
                             } else {
-                                thr[q] = list_insert(list_d + q * kKnnThreads + tid, list_i + q * kKnnThreads + tid, K,
-                                                     stride, d, base + j + u);
+                                if (KT > 1)
+                                    thr[q] = list_insert_t<(KT > 1 ? KT : 2)>(list_d + q * kKnnThreads + tid,
+                                                                              list_i + q * kKnnThreads + tid, stride, d,
+                                                                              base + j + u);
+                                else
+                                    thr[q] = list_insert(list_d + q * kKnnThreads + tid,
+                                                         list_i + q * kKnnThreads + tid, K, stride, d, base + j + u);
                             }
                             thr_hi[q] = (VARIANT == 0) ? thr[q] : inflate(thr[q]);
                         }
@@ -276,10 +310,10 @@ static size_t knn_smem_bytes(int K, int Q, bool k1) {
     return 2 * 3 * kTile * sizeof(float) + 16 + (k1 ? 0 : (size_t)K * Q * kKnnThreads * 8);
 }
 
-template <int VARIANT, int Q, bool K1>
+template <int VARIANT, int Q, bool K1, int KT = 0>
 static int launch_knn(const float* sup_soa, int Nsp, const float* query, long long q_stride, int B, int Ns, int Nq,
                       int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq, cudaStream_t st) {
-    auto kern = knn_kernel<VARIANT, Q, K1>;
+    auto kern = knn_kernel<VARIANT, Q, K1, KT>;
     const size_t smem = knn_smem_bytes(K, Q, K1);
     R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(Nq, Q * kKnnThreads), B);
@@ -292,16 +326,19 @@ template <int VARIANT>
 static int dispatch_q(int Q, bool k1, const float* sup_soa, int Nsp, const float* query, long long q_stride, int B,
                       int Ns, int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
                       cudaStream_t st) {
-#define R3D_KNN_CASE(QQ)                                                                                      \
-    if (Q == QQ)                                                                                              \
-        return k1 ? launch_knn<VARIANT, QQ, true>(sup_soa, Nsp, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist,  \
-                                                  dist_sq, st)                                                \
-                  : launch_knn<VARIANT, QQ, false>(sup_soa, Nsp, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist, \
-                                                   dist_sq, st);
+#define R3D_KNN_ARGS sup_soa, Nsp, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist, dist_sq, st
+#define R3D_KNN_CASE(QQ)                                                              \
+    if (Q == QQ) {                                                                    \
+        if (k1) return launch_knn<VARIANT, QQ, true>(R3D_KNN_ARGS);                   \
+        if (K == 16) return launch_knn<VARIANT, QQ, false, 16>(R3D_KNN_ARGS);         \
+        if (K == 32 && QQ == 1) return launch_knn<VARIANT, QQ, false, 32>(R3D_KNN_ARGS); \
+        return launch_knn<VARIANT, QQ, false>(R3D_KNN_ARGS);                          \
+    }
     R3D_KNN_CASE(1)
     R3D_KNN_CASE(2)
     R3D_KNN_CASE(4)
 #undef R3D_KNN_CASE
+#undef R3D_KNN_ARGS
     return R3D_EINVAL;
 }
 

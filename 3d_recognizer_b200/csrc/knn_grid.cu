@@ -248,7 +248,34 @@ __device__ __forceinline__ void kbest_insert(KBest& L, float d, int id) {
     L.thr_id = L.id[(L.K - 1) * kGridThreads];
 }
 
-template <bool K1>
+// loop-free lexicographic insertion for a compile-time list length (see knn.cu list_insert_t)
+template <int KT>
+__device__ __noinline__ void kbest_insert_t(KBest& L, float d, int id) {
+    if (!(d < L.thr || (d == L.thr && id < L.thr_id))) return;
+    float vd[KT];
+    int vi[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        vd[k] = L.d[k * kGridThreads];
+        vi[k] = L.id[k * kGridThreads];
+    }
+    int pos = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) pos += (vd[k] < d || (vd[k] == d && vi[k] < id)) ? 1 : 0;
+#pragma unroll
+    for (int k = KT - 1; k >= 1; --k) {
+        if (k > pos) {
+            L.d[k * kGridThreads] = vd[k - 1];
+            L.id[k * kGridThreads] = vi[k - 1];
+        }
+    }
+    L.d[pos * kGridThreads] = d;
+    L.id[pos * kGridThreads] = id;
+    L.thr = (pos == KT - 1) ? d : vd[KT - 2];
+    L.thr_id = (pos == KT - 1) ? id : vi[KT - 2];
+}
+
+template <bool K1, int KT = 0>
 __global__ void __launch_bounds__(kGridThreads) knn_grid_kernel(
     const float4* __restrict__ pts, const int* __restrict__ starts, int cells_alloc, const GridHdr* __restrict__ hdr,
     const float* __restrict__ query, long long q_stride, const int* __restrict__ qorder /* nullable: self search */,
@@ -301,6 +328,8 @@ __global__ void __launch_bounds__(kGridThreads) knn_grid_kernel(
                     best_d = d;
                     best_i = id;
                 }
+            } else if (KT > 1) {
+                kbest_insert_t<(KT > 1 ? KT : 2)>(L, d, id);
             } else {
                 kbest_insert(L, d, id);
             }
@@ -445,10 +474,12 @@ int knn_grid_run(const float* support, long long s_stride, const float* query, l
                                                              Ns, Nq, K, idx64, idx32, dist, dist_sq);
     } else {
         const size_t smem = (size_t)K * kGridThreads * 8;
-        R3D_CUDA_TRY(cudaFuncSetAttribute(knn_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        knn_grid_kernel<false><<<grid, kGridThreads, smem, st>>>(pts, counts, p.cells_alloc, hdr, query, q_stride,
-                                                                 qorder, Ns, Nq, K, idx64, idx32, dist, dist_sq);
+        // the ring walk meets candidates roughly in order of distance, so insertions land near the list tail and
+        // the short shift loop beats the loop-free version (measured: 1M x 1M K=16 1.99 ms vs 3.85 ms)
+        auto kern = knn_grid_kernel<false, 0>;
+        R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kGridThreads, smem, st>>>(pts, counts, p.cells_alloc, hdr, query, q_stride, qorder, Ns, Nq, K,
+                                               idx64, idx32, dist, dist_sq);
     }
     R3D_LAUNCH_CHECK("knn_grid_kernel");
     return R3D_OK;

@@ -45,6 +45,7 @@ struct PwArgs {
     int n;                     // rows per cloud
     int transpose_out;         // 1: write y as (B, cout, n) — the reference's logits layout (modules.py:611)
     double* stats;             // nullable (2*cout): += per-channel sum and sum of squares of the written values
+    int w_out_in;              // 0: wT is (cin, cout);  1: the weight is stored (cout, cin) (conv / Linear layout)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -121,22 +122,31 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
             for (int u = 0; u < 4; ++u) As[c4 * 4 + u][r] = v[u];
         }
         // ---- stage W chunk
-        for (int i = tid; i < W_ITEMS; i += NT) {
-            const int kk = i / (TN / 4), j4 = i % (TN / 4);
-            const int c = c0 + kk, col = n0 + j4 * 4;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < cin) {
-                const float* wr = a.wT + (size_t)c * a.cout;
-                if ((a.cout & 3) == 0 && col + 3 < a.cout) {
-                    t = *reinterpret_cast<const float4*>(wr + col);
-                } else {
-                    if (col + 0 < a.cout) t.x = wr[col + 0];
-                    if (col + 1 < a.cout) t.y = wr[col + 1];
-                    if (col + 2 < a.cout) t.z = wr[col + 2];
-                    if (col + 3 < a.cout) t.w = wr[col + 3];
-                }
+        if (a.w_out_in) {
+            // weight rows are output channels: read along cin, store transposed
+            for (int i = tid; i < TN * kPwKC; i += NT) {
+                const int col = i / kPwKC, kk = i % kPwKC;
+                const int c = c0 + kk, oc = n0 + col;
+                Ws[kk][col] = (c < cin && oc < a.cout) ? a.wT[(size_t)oc * cin + c] : 0.f;
             }
-            *reinterpret_cast<float4*>(&Ws[kk][j4 * 4]) = t;
+        } else {
+            for (int i = tid; i < W_ITEMS; i += NT) {
+                const int kk = i / (TN / 4), j4 = i % (TN / 4);
+                const int c = c0 + kk, col = n0 + j4 * 4;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < cin) {
+                    const float* wr = a.wT + (size_t)c * a.cout;
+                    if ((a.cout & 3) == 0 && col + 3 < a.cout) {
+                        t = *reinterpret_cast<const float4*>(wr + col);
+                    } else {
+                        if (col + 0 < a.cout) t.x = wr[col + 0];
+                        if (col + 1 < a.cout) t.y = wr[col + 1];
+                        if (col + 2 < a.cout) t.z = wr[col + 2];
+                        if (col + 3 < a.cout) t.w = wr[col + 3];
+                    }
+                }
+                *reinterpret_cast<float4*>(&Ws[kk][j4 * 4]) = t;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -218,6 +228,208 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
     }
 }
 
+// ------------------------------------------------------------------------- pipelined GEMM kernel
+// Same math as pw_gemm_kernel for channel counts that are multiples of 4, restructured for latency: source row
+// pointers (gather, batch stride) are resolved once per thread, and the global loads of chunk c+1 are issued
+// into registers before the FMAs of chunk c (double-buffered shared memory, ONE barrier per chunk).  The launch
+// list of the small-cloud training step showed the unpipelined kernel at 61 us per launch (24 % of the step):
+// 16..64 chunks of load -> barrier -> 16 k-steps -> barrier on a handful of CTAs.
+// RT = register tile edge (8: 8x8 per thread; 4: 4x4 per thread, more threads/CTAs for small row counts).
+template <int TM, int TN, int RT>
+__global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwArgs a) {
+    constexpr int NT = (TM / RT) * (TN / RT);
+    constexpr int KC = kPwKC;
+    constexpr int TMP = TM + 4;
+    constexpr int A_PER = TM * (KC / 4) / NT;
+    constexpr int W_PER = KC * TN / 4 / NT;
+    static_assert(A_PER >= 1 && W_PER >= 1 && (TM * (KC / 4)) % NT == 0 && (KC * TN / 4) % NT == 0, "tile/threads");
+    __shared__ __align__(16) float As[2][KC][TMP];
+    __shared__ __align__(16) float Ws[2][KC][TN];
+    __shared__ float csum[2][TN];
+
+    const int tid = threadIdx.x;
+    const int tr = tid / (TN / RT);
+    const int tc = tid % (TN / RT);
+    const long long M = (long long)a.B * a.n;
+    const long long m0 = (long long)blockIdx.x * TM;
+    const int n0 = blockIdx.y * TN;
+    const int cin = a.ca + a.cb;
+
+    // ---- per-thread source rows
+    const float* rowA[A_PER];
+    const float* rowB[A_PER];
+#pragma unroll
+    for (int k = 0; k < A_PER; ++k) {
+        const int r = (tid + k * NT) / (KC / 4);
+        const long long m = m0 + r;
+        rowA[k] = nullptr;
+        rowB[k] = nullptr;
+        if (m < M) {
+            const int b = (int)(m / a.n), n = (int)(m % a.n);
+            rowA[k] = src_row(a, b, n, false);
+            if (a.cb > 0) rowB[k] = src_row(a, b, n, true);
+        }
+    }
+    float4 ra[A_PER], rw[W_PER];
+    auto load = [&](int c0) {
+#pragma unroll
+        for (int k = 0; k < A_PER; ++k) {
+            const int c = c0 + ((tid + k * NT) % (KC / 4)) * 4;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowA[k] && c < cin) t = *reinterpret_cast<const float4*>(c < a.ca ? rowA[k] + c : rowB[k] + (c - a.ca));
+            ra[k] = t;
+        }
+#pragma unroll
+        for (int k = 0; k < W_PER; ++k) {
+            const int i = tid + k * NT;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.w_out_in) {                       // (cout, cin): float4 along cin
+                const int col = i / (KC / 4), c = c0 + (i % (KC / 4)) * 4;
+                if (c < cin && n0 + col < a.cout) t = *reinterpret_cast<const float4*>(a.wT + (size_t)(n0 + col) * cin + c);
+            } else {                                // (cin, cout): float4 along cout
+                const int kk = i / (TN / 4), col = n0 + (i % (TN / 4)) * 4;
+                if (c0 + kk < cin) {
+                    const float* wr = a.wT + (size_t)(c0 + kk) * a.cout;
+                    if ((a.cout & 3) == 0 && col + 3 < a.cout) {
+                        t = *reinterpret_cast<const float4*>(wr + col);
+                    } else {
+                        if (col + 0 < a.cout) t.x = wr[col + 0];
+                        if (col + 1 < a.cout) t.y = wr[col + 1];
+                        if (col + 2 < a.cout) t.z = wr[col + 2];
+                        if (col + 3 < a.cout) t.w = wr[col + 3];
+                    }
+                }
+            }
+            rw[k] = t;
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < A_PER; ++k) {
+            const int i = tid + k * NT;
+            const int c4 = i % (KC / 4), r = i / (KC / 4);
+            As[buf][c4 * 4 + 0][r] = ra[k].x;
+            As[buf][c4 * 4 + 1][r] = ra[k].y;
+            As[buf][c4 * 4 + 2][r] = ra[k].z;
+            As[buf][c4 * 4 + 3][r] = ra[k].w;
+        }
+#pragma unroll
+        for (int k = 0; k < W_PER; ++k) {
+            const int i = tid + k * NT;
+            if (a.w_out_in) {
+                const int col = i / (KC / 4), k4 = (i % (KC / 4)) * 4;
+                Ws[buf][k4 + 0][col] = rw[k].x;
+                Ws[buf][k4 + 1][col] = rw[k].y;
+                Ws[buf][k4 + 2][col] = rw[k].z;
+                Ws[buf][k4 + 3][col] = rw[k].w;
+            } else {
+                const int kk = i / (TN / 4), j4 = i % (TN / 4);
+                *reinterpret_cast<float4*>(&Ws[buf][kk][j4 * 4]) = rw[k];
+            }
+        }
+    };
+
+    float acc[RT][RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
+
+    if (a.stats)
+        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.f;
+    load(0);
+    store(0);
+    __syncthreads();
+    const int nchunks = (cin + KC - 1) / KC;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) load((ch + 1) * KC);
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            float av[RT], wv[RT];
+            if (RT == 8) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tr * 8]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][tr * 8 + 4]);
+                const float4 w0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tc * 4]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][TN / 2 + tc * 4]);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+                av[RT - 4] = a1.x; av[RT - 3] = a1.y; av[RT - 2] = a1.z; av[RT - 1] = a1.w;
+                wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+                wv[RT - 4] = w1.x; wv[RT - 3] = w1.y; wv[RT - 2] = w1.z; wv[RT - 1] = w1.w;
+            } else {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tr * 4]);
+                const float4 w0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tc * 4]);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+                wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+#pragma unroll
+                for (int j = 0; j < RT; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        if (ch + 1 < nchunks) store(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue
+    constexpr int NH = RT / 4;   // column quads per thread
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        const int lcol = (RT == 8 ? h * (TN / 2) : 0) + tc * 4;
+        const int col = n0 + lcol;
+        float sc[4], sh[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = col + j < a.cout;
+            sc[j] = (a.scale && ok) ? a.scale[col + j] : 1.f;
+            sh[j] = (a.shift && ok) ? a.shift[col + j] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const long long m = m0 + tr * RT + i;
+            if (m >= M) continue;
+            const int b = (int)(m / a.n), n = (int)(m % a.n);
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[j] = apply_act(fmaf(acc[i][h * 4 + j], sc[j], sh[j]), a.act, a.slope);
+                s1[j] += o[j];
+                s2[j] = fmaf(o[j], o[j], s2[j]);
+            }
+            if (a.transpose_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < a.cout) a.y[(size_t)b * a.y_bstride + (size_t)(col + j) * a.n + n] = o[j];
+            } else {
+                float* yr = a.y + (size_t)b * a.y_bstride + (size_t)n * a.y_ld;
+                if (col + 3 < a.cout && (a.y_ld & 3) == 0 && (a.y_bstride & 3) == 0) {
+                    *reinterpret_cast<float4*>(yr + col) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < a.cout) yr[col + j] = o[j];
+                }
+            }
+        }
+        if (a.stats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&csum[0][lcol + j], s1[j]);
+                atomicAdd(&csum[1][lcol + j], s2[j]);
+            }
+        }
+    }
+    if (a.stats) {
+        __syncthreads();
+        for (int i = tid; i < TN; i += NT) {
+            if (n0 + i < a.cout) {
+                atomicAdd(a.stats + n0 + i, (double)csum[0][i]);
+                atomicAdd(a.stats + a.cout + n0 + i, (double)csum[1][i]);
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------- small kernel
 // Cout <= 16: one thread per output row; weights (cin x cout) live in shared memory.
 constexpr int kPwSmallMaxCout = 16;
@@ -226,7 +438,8 @@ constexpr int kPwSmallMaxW = 4096;  // floats of weights staged in smem (cin*cou
 __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
     __shared__ float Ws[kPwSmallMaxW];
     const int cin = a.ca + a.cb;
-    for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x) Ws[i] = a.wT[i];
+    for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x)
+        Ws[i] = a.w_out_in ? a.wT[(size_t)(i % a.cout) * cin + i / a.cout] : a.wT[i];
     __syncthreads();
     const long long M = (long long)a.B * a.n;
     const long long m_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,7 +500,7 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
                                    long long gidx_bstride, const float* xb, long long xb_bstride, int cb,
                                    const float* wT, const float* scale, const float* shift, int act, float slope,
                                    float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
-                                   double* stats, r3d_stream_t stream);
+                                   double* stats, int w_out_in, r3d_stream_t stream);
 
 extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
                              long long gidx_bstride, const float* xb, long long xb_bstride, int cb, const float* wT,
@@ -295,14 +508,14 @@ extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, cons
                              long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
                              r3d_stream_t stream) {
     return r3d_pointwise_stats(xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
-                               y, y_bstride, y_ld, cout, B, n, transpose_out, nullptr, stream);
+                               y, y_bstride, y_ld, cout, B, n, transpose_out, nullptr, 0, stream);
 }
 
 extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
                                    long long gidx_bstride, const float* xb, long long xb_bstride, int cb,
                                    const float* wT, const float* scale, const float* shift, int act, float slope,
                                    float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
-                                   double* stats, r3d_stream_t stream) {
+                                   double* stats, int w_out_in, r3d_stream_t stream) {
     if (B < 0 || n < 0 || ca <= 0 || cb < 0 || cout <= 0 || act < 0 || act > 2) return R3D_EINVAL;
     if (B == 0 || n == 0) return R3D_OK;
     if (!xa || !wT || !y || (cb > 0 && !xb)) return R3D_EINVAL;
@@ -316,7 +529,7 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     // vector loads need every source row 16-byte aligned
     if ((ca % 4 == 0 && cb % 4 == 0) && ((xa_bstride % 4) || (cb > 0 && (xb_bstride % 4)))) return R3D_EALIGN;
     PwArgs a{xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
-             y, y_bstride, y_ld, cout, B, n, transpose_out, stats};
+             y, y_bstride, y_ld, cout, B, n, transpose_out, stats, w_out_in};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)B * n;
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
@@ -324,15 +537,23 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
         R3D_LAUNCH_CHECK("pw_small_kernel");
         return R3D_OK;
     }
-    if (cout <= 32) {
-        dim3 grid((unsigned)((M + 255) / 256), (cout + 31) / 32);
-        pw_gemm_kernel<256, 32><<<grid, 128, 0, st>>>(a);
-    } else if (cout <= 64 || M < 64 * 148) {
+    const bool aligned = (ca % 4 == 0) && (cb % 4 == 0);
+    if (!aligned) {
         dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
         pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
+    } else if (M <= 64 * 4 * kNumSMs / ((cout + 63) / 64)) {
+        // few rows: 64x64 tiles of 256 threads (4x4 per thread) put more CTAs and warps on the machine
+        dim3 grid((unsigned)((M + 63) / 64), (cout + 63) / 64);
+        pw_gemm_fast_kernel<64, 64, 4><<<grid, 256, 0, st>>>(a);
+    } else if (cout <= 32) {
+        dim3 grid((unsigned)((M + 255) / 256), (cout + 31) / 32);
+        pw_gemm_fast_kernel<256, 32, 8><<<grid, 128, 0, st>>>(a);
+    } else if (cout <= 64 || M < 64 * 148) {
+        dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
+        pw_gemm_fast_kernel<128, 64, 8><<<grid, 128, 0, st>>>(a);
     } else {
         dim3 grid((unsigned)((M + 63) / 64), (cout + 127) / 128);
-        pw_gemm_kernel<64, 128><<<grid, 128, 0, st>>>(a);
+        pw_gemm_fast_kernel<64, 128, 8><<<grid, 128, 0, st>>>(a);
     }
     R3D_LAUNCH_CHECK("pw_gemm_kernel");
     return R3D_OK;

@@ -64,7 +64,7 @@ class _SharedMLPTrainFn(torch.autograd.Function):
         x = x.contiguous()
         cout = w.shape[0]
         stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device)
-        z = ops.pointwise(x.unsqueeze(0), w.t().contiguous(), stats=stats).squeeze(0)
+        z = ops.pointwise(x.unsqueeze(0), w.contiguous(), stats=stats, w_out_in=True).squeeze(0)
         y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
         ctx.act, ctx.slope = act, slope
         ctx.save_for_backward(x, w, z, save, beta)
@@ -87,7 +87,7 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, w, bias):
         x = x.contiguous()
         ctx.save_for_backward(x, w)
-        return ops.pointwise(x.unsqueeze(0), w.t().contiguous(), None, bias.contiguous()).squeeze(0)
+        return ops.pointwise(x.unsqueeze(0), w.contiguous(), None, bias.contiguous(), w_out_in=True).squeeze(0)
 
     @staticmethod
     def backward(ctx, dy):
@@ -228,25 +228,28 @@ class _R1MomentsFn(torch.autograd.Function):
         return None, None, a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
 
 
-def _bn_affine_from_moments(smlp, mean_in: torch.Tensor, cov_in: torch.Tensor, count: float):
-    """Train-mode BatchNorm of y = W x + b expressed through the input moments (fp64): mean_y = W mu + b,
-    var_y = diag(W Cov W^T) (biased, as BatchNorm normalises; modules.py:86-90).  Returns the per-channel
-    affine (a, c) with bn(y) = a * (W x) + c, and updates the running statistics like BatchNorm2d
-    (momentum 0.99, unbiased running variance)."""
-    bn = smlp.batch_norm
-    w = conv_weight_2d(smlp).double()
-    wmu = w @ mean_in
-    var = ((w @ cov_in) * w).sum(dim=1).clamp_min(0.0)
-    a = bn.weight.double() * torch.rsqrt(var + bn.eps)
-    # the conv bias cancels against the batch mean; keep it in the graph so that it receives its (zero) gradient
-    c = bn.bias.double() - a * wmu + 0.0 * smlp.conv.bias.double()
-    if bn.track_running_stats:
-        with torch.no_grad():
-            m = bn.momentum
-            bn.running_mean.mul_(1 - m).add_((wmu + smlp.conv.bias.double()).float(), alpha=m)
-            bn.running_var.mul_(1 - m).add_((var * (count / max(count - 1.0, 1.0))).float(), alpha=m)
-            bn.num_batches_tracked.add_(1)
-    return a.float(), c.float()
+class _BnFromMomentsFn(torch.autograd.Function):
+    """Train-mode BatchNorm of y = W x + b expressed through the input moments (sums s, second-moment sums m over
+    ``count`` rows, fp64): mean_y = W mu + b, var_y = diag(W Cov W^T) (biased, as BatchNorm normalises;
+    modules.py:86-90).  Returns the per-channel affine (a, c) with bn(y) = a (W x) + c and updates the running
+    statistics like BatchNorm2d (momentum 0.99, unbiased running variance).  One small kernel forward, one or
+    two backward (ops.bn_from_moments*)."""
+
+    @staticmethod
+    def forward(ctx, w, bias, gamma, beta, s, m, bn, count):
+        w = w.contiguous()
+        a, c, save = ops.bn_from_moments(w, s, m, count, bn, bias)
+        ctx.count = count
+        ctx.save_for_backward(w, gamma, s, m, save)
+        return a, c
+
+    @staticmethod
+    def backward(ctx, ga, gc):
+        w, gamma, s, m, save = ctx.saved_tensors
+        need = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        dw, dgamma, dbeta, dm, ds = ops.bn_from_moments_bwd(w, s, m, ctx.count, gamma.contiguous(), save, ga, gc, need)
+        # the conv bias cancels against the batch mean: exactly zero gradient
+        return dw, torch.zeros_like(dgamma), dgamma, dbeta, ds, dm, None, None
 
 
 def _eval_affine(smlp):
@@ -269,9 +272,9 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     if training:
         m = ops.lfa_moments(0, xyz, idx, d)                      # (16,16) fp64, no parameters involved
         count = float(xyz.shape[0] * xyz.shape[1] * K)
-        mu = m[10, :10] / count
-        cov = m[:10, :10] / count - torch.outer(mu, mu)
-        a1, c1 = _bn_affine_from_moments(lfa.mlp_rpe1, mu, cov, count)
+        r1m = lfa.mlp_rpe1
+        a1, c1 = _BnFromMomentsFn.apply(w1, r1m.conv.bias, r1m.batch_norm.weight, r1m.batch_norm.bias, m[10], m,
+                                        r1m.batch_norm, count)
     else:
         a1, c1 = _eval_affine(lfa.mlp_rpe1)
     ws1, ws2 = lfa.pool1.score_fn[0].weight, lfa.pool2.score_fn[0].weight
@@ -279,9 +282,9 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     p1 = shared_mlp(lfa.pool1.mlp, pooled1)
     if training:
         s_r1, m_r1 = _R1MomentsFn.apply(xyz, idx, w1, a1, c1)
-        mu_r = s_r1 / count
-        cov_r = m_r1 / count - torch.outer(mu_r, mu_r)
-        a2, c2 = _bn_affine_from_moments(lfa.mlp_rpe2, mu_r, cov_r, count)
+        r2m = lfa.mlp_rpe2
+        a2, c2 = _BnFromMomentsFn.apply(w2, r2m.conv.bias, r2m.batch_norm.weight, r2m.batch_norm.bias, s_r1, m_r1,
+                                        r2m.batch_norm, count)
     else:
         a2, c2 = _eval_affine(lfa.mlp_rpe2)
     pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, w1, a1, c1, w2, a2, c2, ws2)

@@ -129,7 +129,7 @@ _ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2}
 def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=None, slope: float = 0.0,
               gidx: Optional[torch.Tensor] = None, xb: Optional[torch.Tensor] = None, n_rows: Optional[int] = None,
               transpose_out: bool = False, out: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+              stats: Optional[torch.Tensor] = None, w_out_in: bool = False) -> torch.Tensor:
     """Per-point layer y = act(scale * (W [xa[g] ; xb]) + shift) (C ABI ``r3d_pointwise``).
     xa (B,na,ca) [gathered through gidx int32 (n,) shared or (B,n) per cloud], xb (B,n,cb) optional,
     wT (ca+cb, cout).  Returns (B,n,cout), or (B,cout,n) with ``transpose_out``."""
@@ -142,8 +142,8 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
         xb, xbs = _rows_view(xb.detach())
         cb = xb.shape[2]
         assert xb.shape[1] >= n
-    cout = wT.shape[1]
-    assert wT.shape[0] == ca + cb and wT.is_contiguous()
+    cout = wT.shape[0] if w_out_in else wT.shape[1]
+    assert wT.shape[1 if w_out_in else 0] == ca + cb and wT.is_contiguous()
     dev = xa.device
     if out is None:
         out = torch.empty((B, cout, n) if transpose_out else (B, n, cout), dtype=torch.float32, device=dev)
@@ -157,7 +157,8 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
         rc = _cabi.lib().r3d_pointwise_stats(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
                                              _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act],
                                              float(slope), _cabi.ptr(out), 0, 0, cout, B, n,
-                                             1 if transpose_out else 0, _cabi.ptr(stats), _cabi.stream_ptr(dev))
+                                             1 if transpose_out else 0, _cabi.ptr(stats), 1 if w_out_in else 0,
+                                             _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_pointwise")
     return out
 
@@ -277,3 +278,44 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
     if mode == 1:
         return m_r1, s_r1
     return g1
+
+
+def bn_from_moments(w: torch.Tensor, s: torch.Tensor, m: torch.Tensor, count: float, bn, bias):
+    """BatchNorm affine (a, c) of y = W x from the input moments (C ABI ``r3d_bn_from_moments``): w (cout,cin),
+    s (>=cin) fp64 sums, m (ld,ld) fp64 second-moment sums (ld >= cin), ``count`` rows.  Updates bn's running
+    statistics.  Returns (a, c, save)."""
+    cout, cin = w.shape
+    dev = w.device
+    a = torch.empty(cout, dtype=torch.float32, device=dev)
+    c = torch.empty(cout, dtype=torch.float32, device=dev)
+    save = torch.empty((5, cout), dtype=torch.float64, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    with torch.cuda.device(dev), _cabi.kernel_timer("bn_from_moments", flops=2.0 * cout * cin * cin, bytes=8.0 * cin * cin):
+        rc = _cabi.lib().r3d_bn_from_moments(
+            _cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0), float(count),
+            _cabi.ptr(bn.weight.detach()), _cabi.ptr(bn.bias.detach()),
+            _cabi.ptr(bias.detach()) if bias is not None else None, float(bn.eps), float(bn.momentum),
+            _cabi.ptr(bn.running_mean) if track else None, _cabi.ptr(bn.running_var) if track else None,
+            _cabi.ptr(bn.num_batches_tracked) if track else None, _cabi.ptr(a), _cabi.ptr(c), _cabi.ptr(save),
+            _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_bn_from_moments")
+    return a, c, save
+
+
+def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments: bool):
+    """Backward of ``bn_from_moments``.  Returns (dW, dgamma, dbeta, dM | None, dS | None)."""
+    cout, cin = w.shape
+    dev = w.device
+    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+    dgb = torch.empty((2, cout), dtype=torch.float32, device=dev)
+    scal = torch.empty((2, cout), dtype=torch.float64, device=dev)
+    dm = torch.empty((cin, cin), dtype=torch.float64, device=dev) if need_moments else None
+    ds = torch.empty(cin, dtype=torch.float64, device=dev) if need_moments else None
+    with torch.cuda.device(dev), _cabi.kernel_timer("bn_from_moments_bwd", flops=4.0 * cout * cin * cin,
+                                                    bytes=8.0 * cin * cin):
+        rc = _cabi.lib().r3d_bn_from_moments_bwd(
+            _cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0), float(count),
+            _cabi.ptr(gamma), _cabi.ptr(save), _cabi.ptr(ga.contiguous()), _cabi.ptr(gc.contiguous()), _cabi.ptr(dw),
+            _cabi.raw(dgb[0]), _cabi.raw(dgb[1]), _cabi.ptr(scal), _cabi.ptr(dm), _cabi.ptr(ds), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_bn_from_moments_bwd")
+    return dw, dgb[0], dgb[1], dm, ds

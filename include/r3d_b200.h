@@ -141,6 +141,22 @@ int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride, const int
                     const float* gsym, const float* gsum, float* g1, int B, int N, int K, int d,
                     r3d_stream_t stream);
 
+/* Train-mode BatchNorm of y = W x (+bias) from the input moments S = sum x (stride s_stride), M = sum x x^T
+ * (ldm), R rows (r3d_lfa_moments): a = gamma/sqrt(var+eps), c = beta - a (W mu) with mean = W mu,
+ * var = diag(W Cov W^T).  W (cout,cin) [out][in], cin <= 128.  Updates running_mean/var/num_batches (nullable)
+ * like BatchNorm2d; save (5,cout) fp64 is scratch for the backward.
+ * Backward: ga, gc (cout) -> dW (cout,cin), dgamma, dbeta; scal (2,cout) fp64 scratch; when dM (cin,cin) and
+ * dS (cin) are given (fp64) they receive the gradient w.r.t. the moments (mlp_rpe2: r1's moments depend on
+ * mlp_rpe1's parameters; they feed r3d_lfa_moments mode 2). */
+int r3d_bn_from_moments(const float* W, int cout, int cin, const double* S, int s_stride, const double* M, int ldm,
+                        double R, const float* gamma, const float* beta, const float* bias, float eps,
+                        float momentum, float* running_mean, float* running_var, long long* num_batches,
+                        float* a_out, float* c_out, double* save, r3d_stream_t stream);
+int r3d_bn_from_moments_bwd(const float* W, int cout, int cin, const double* S, int s_stride, const double* M,
+                            int ldm, double R, const float* gamma, const double* save, const float* ga,
+                            const float* gc, float* dW, float* dgamma, float* dbeta, double* scal, double* dM,
+                            double* dS, r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,
@@ -159,11 +175,12 @@ int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* 
                   int B, int n, int transpose_out, r3d_stream_t stream);
 
 /* r3d_pointwise that also accumulates, per output channel, the sum and the sum of squares (fp64, stats[2*cout],
- * caller-zeroed) of the values it writes: the batch statistics of a train-mode BatchNorm (modules.py:86-90). */
+ * caller-zeroed, nullable) of the values it writes: the batch statistics of a train-mode BatchNorm
+ * (modules.py:86-90).  w_out_in = 1: `wT` points at the weight in its stored (cout, cin) layout (no transposed copy). */
 int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int32_t* gidx, long long gidx_bstride,
                         const float* xb, long long xb_bstride, int cb, const float* wT, const float* scale,
                         const float* shift, int act, float slope, float* y, long long y_bstride, int y_ld, int cout,
-                        int B, int n, int transpose_out, double* stats, r3d_stream_t stream);
+                        int B, int n, int transpose_out, double* stats, int w_out_in, r3d_stream_t stream);
 
 /* ------------------------------------------------------------- train-mode BatchNorm of a per-point layer
  * Forward tail of SharedMLP in training mode (modules.py:92-104): z (M,C) = conv output WITHOUT bias, stats from
