@@ -30,6 +30,8 @@ constexpr int kLfaThreads = 128;
 // 8 KB weight-ring stages keep the forward tile under 113 KB: two CTAs per SM, so one CTA's gather prologue
 // overlaps the other's GEMM (ncu of the 16 KB version: 1 CTA/SM, issue slots 41 % busy)
 constexpr int kLfaFwdStage = 2048;
+// narrow layers (d = 16: a 16x16 score matrix) get 4-row register tiles: 8 threads per point instead of 2, so a
+// 128-thread CTA needs a 4x smaller shared-memory tile and 4-8 CTAs fit an SM (ncu: 2 warps/SM with 16-row tiles)
 
 struct LfaArgs {
     const float* xyz;        // (B,N,3)
@@ -50,15 +52,16 @@ struct LfaArgs {
 
 template <int D, int K>
 struct LfaFwdSmem {
-    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage, lfa_rows_per_thread(D)>;
     static constexpr int P_FLOATS = C::H * 12 + 4 * C::H;     // w_rpe1 padded to 12 per channel + a1,b1,a2,b2
     static constexpr size_t BYTES = (size_t)(C::X_FLOATS + 2 * C::WSTAGE + P_FLOATS) * sizeof(float) + 16;
 };
 
 template <int D, int K, int STAGE>
 __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
-    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage, lfa_rows_per_thread(D)>;
     constexpr int H = C::H;
+    constexpr int RT = C::RT;
     extern __shared__ __align__(128) float smem[];
     float* X = smem;                               // [D][ROWS_PAD]
     float* ring = X + C::X_FLOATS;                 // [2][WSTAGE]
@@ -120,17 +123,17 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
     const int rh = tid % C::RH;
     const int g = (tid / C::RH) % C::CG;
     const int p = tid / C::TPP;
-    const int row0 = p * C::PSTRIDE + rh * 16;
+    const int row0 = p * C::PSTRIDE + rh * RT;
     WPipe pipe{ring, bars, 0u, C::WSTAGE};
 
     // ------------------------------------------------------------------ stage 2: r2 = relu(a2 * (W2 r1) + b2), in place
     if (STAGE == 2) {
-        float acc2[16][4];
+        float acc2[RT][4];
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
-        gemm_stream<1, kLfaThreads>(acc2, X, C::ROWS_PAD, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
+        gemm_stream<1, kLfaThreads, RT>(acc2, X, C::ROWS_PAD, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
         // every thread is past the barrier that ends gemm_stream: r1 may be overwritten
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
             const float sa = Pa2[col], sb = Pb2[col];
             float* dst = X + (size_t)col * C::ROWS_PAD + row0;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < RT / 4; ++v) {
                 float4 t;
                 t.x = fmaxf(fmaf(acc2[4 * v + 0][j], sa, sb), 0.f);
                 t.y = fmaxf(fmaf(acc2[4 * v + 1][j], sa, sb), 0.f);
@@ -151,12 +154,12 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
     }
 
     // ------------------------------------------------------------------ score GEMM  S = X^T Ws^T
-    float acc[16][8];
+    float acc[RT][8];
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-    gemm_stream<2, kLfaThreads>(acc, X, C::ROWS_PAD, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
+    gemm_stream<2, kLfaThreads, RT>(acc, X, C::ROWS_PAD, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
 
     // ------------------------------------------------------------------ softmax over K + weighted sum
     float outv[8];
@@ -165,13 +168,13 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
         const int col = (j < 4) ? (g * 4 + j) : (D / 2 + g * 4 + (j - 4));
         float m = acc[0][j];
 #pragma unroll
-        for (int r = 1; r < 16; ++r) m = fmaxf(m, acc[r][j]);
+        for (int r = 1; r < RT; ++r) m = fmaxf(m, acc[r][j]);
 #pragma unroll
         for (int o = 1; o < C::RH; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float* xc = X + (size_t)col * C::ROWS_PAD + row0;
         float se = 0.f, sx = 0.f;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < RT / 4; ++v) {
             const float4 t = *reinterpret_cast<const float4*>(xc + 4 * v);
             const float e0 = __expf(acc[4 * v + 0][j] - m), e1 = __expf(acc[4 * v + 1][j] - m);
             const float e2 = __expf(acc[4 * v + 2][j] - m), e3 = __expf(acc[4 * v + 3][j] - m);
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
 
 template <int D, int K, int STAGE>
 static int launch_lfa(const LfaArgs& a, cudaStream_t st) {
-    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage>;
+    using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage, lfa_rows_per_thread(D)>;
     auto kern = lfa_pool_kernel<D, K, STAGE>;
     constexpr size_t smem = LfaFwdSmem<D, K>::BYTES;
     R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

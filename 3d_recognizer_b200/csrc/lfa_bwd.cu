@@ -51,8 +51,11 @@ struct LfaBwdArgs {
 };
 
 template <int D, int K, int NT>
+using LfaBwdCfg = LfaCfg<D, K, NT, 4096, lfa_rows_per_thread(D)>;
+
+template <int D, int K, int NT>
 struct LfaBwdSmem {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     static constexpr int FLOATS = 2 * C::X_FLOATS + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 16 + C::ROWS +
                                   C::PTS * D;
     static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
@@ -60,8 +63,9 @@ struct LfaBwdSmem {
 
 template <int D, int K, int NT, int STAGE>
 __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     constexpr int H = C::H;
+    constexpr int RT = C::RT;
     constexpr int RP = C::ROWS_PAD;
     extern __shared__ __align__(128) float smem[];
     float* X = smem;                                  // [D][RP]   neighbourhood matrix, later du
@@ -139,49 +143,49 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     const int rh = tid % C::RH;
     const int g = (tid / C::RH) % C::CG;
     const int p = tid / C::TPP;
-    const int row0 = p * C::PSTRIDE + rh * 16;
+    const int row0 = p * C::PSTRIDE + rh * RT;
     WPipe pipe{ring, bars, 0u, C::WSTAGE};
 
     // ------------------------------------------------------------------ stage 2: r2 = relu(a2 (W2 r1) + b2) in place
     if (STAGE == 2) {
-        float acc2[16][4];
+        float acc2[RT][4];
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
-        gemm_stream<1, NT>(acc2, X, RP, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
+        gemm_stream<1, NT, RT>(acc2, X, RP, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = g * 4 + j;
             const float sa = Pa2[col], sb = Pb2[col];
             float* dst = X + (size_t)col * RP + row0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dst[r] = fmaxf(fmaf(acc2[r][j], sa, sb), 0.f);
+            for (int r = 0; r < RT; ++r) dst[r] = fmaxf(fmaf(acc2[r][j], sa, sb), 0.f);
         }
         __syncthreads();
     }
 
     // ------------------------------------------------------------------ scores, softmax, dS and the direct part of dX
-    float acc[16][8];
+    float acc[RT][8];
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-    gemm_stream<2, NT>(acc, X, RP, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
+    gemm_stream<2, NT, RT>(acc, X, RP, row0, D, a.w_scoreT, D, D / 2, g, pipe, tid);
 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int col = (j < 4) ? (g * 4 + j) : (D / 2 + g * 4 + (j - 4));
         float m = acc[0][j];
 #pragma unroll
-        for (int r = 1; r < 16; ++r) m = fmaxf(m, acc[r][j]);
+        for (int r = 1; r < RT; ++r) m = fmaxf(m, acc[r][j]);
 #pragma unroll
         for (int o = 1; o < C::RH; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float* xc = X + (size_t)col * RP + row0;
-        float xv[16];
+        float xv[RT];
         float se = 0.f, sx = 0.f;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
+        for (int r = 0; r < RT; ++r) {
             xv[r] = xc[r];
             const float e = __expf(acc[r][j] - m);
             acc[r][j] = e;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
         const float gv = gp[p * D + col];
         float* gc = G + (size_t)col * RP + row0;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
+        for (int r = 0; r < RT; ++r) {
             const float ga = gv * (acc[r][j] * inv);      // g * A  = direct part of dX
             gc[r] = ga * (xv[r] - pooled);                // dS
             acc[r][j] = ga;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     __syncthreads();
 
     // ------------------------------------------------------------------ dX = g*A + dS Ws ;  dWs += dS^T X
-    gemm_stream<2, NT>(acc, G, RP, row0, D, a.w_score, D, D / 2, g, pipe, tid);
+    gemm_stream<2, NT, RT>(acc, G, RP, row0, D, a.w_score, D, D / 2, g, pipe, tid);
     reduce_gemm<D, D, NT, C::PTS, K, C::PSTRIDE, float>(G, X, RP, a.dw_score, D, D, tid);
     __syncthreads();
 
@@ -215,8 +219,8 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     {
         float* df_b = a.dfeat + (size_t)b * a.dfeat_bstride;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int pj = idxs[p * K + rh * 16 + r];
+        for (int r = 0; r < RT; ++r) {
+            const int pj = idxs[p * K + rh * RT + r];
             if (pj >= 0)
                 red_add_v4(df_b + (size_t)pj * H + g * 4, make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
         }
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     for (int j = 0; j < 4; ++j) {
         float* xc = X + (size_t)(g * 4 + j) * RP + row0;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) xc[r] = (xc[r] > 0.f) ? acc[r][j] : 0.f;
+        for (int r = 0; r < RT; ++r) xc[r] = (xc[r] > 0.f) ? acc[r][j] : 0.f;
     }
     __syncthreads();
 
@@ -250,18 +254,18 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, float>(X, G, RP, a.g2m, H, H, tid);
     reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(X, RPE, RP, a.g2c, kRpeRows, 11, tid);
     {
-        float acc2[16][4];
+        float acc2[RT][4];
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
-        gemm_stream<1, NT>(acc2, X, RP, row0, H, a.w_rpe2s, H, 0, g, pipe, tid);
+        gemm_stream<1, NT, RT>(acc2, X, RP, row0, H, a.w_rpe2s, H, 0, g, pipe, tid);
         // every thread is past the barrier that ends gemm_stream, i.e. past its reads of r1 in reduce_gemm
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float* gc = G + (size_t)(g * 4 + j) * RP + row0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) gc[r] = (gc[r] > 0.f) ? acc2[r][j] : 0.f;
+            for (int r = 0; r < RT; ++r) gc[r] = (gc[r] > 0.f) ? acc2[r][j] : 0.f;
         }
     }
     __syncthreads();
@@ -287,7 +291,7 @@ struct LfaMomArgs {
 
 template <int D, int K, int NT>
 struct LfaMomSmem {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     static constexpr int FLOATS = 2 * C::H * C::ROWS_PAD + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 14 + 4;
     static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
 };
@@ -295,8 +299,9 @@ struct LfaMomSmem {
 // MODE 0: rpe moments.  MODE 1: r1 moments.  MODE 2: backward of the r1 moments.
 template <int D, int K, int NT, int MODE>
 __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     constexpr int H = C::H;
+    constexpr int RT = C::RT;
     constexpr int RP = C::ROWS_PAD;
     extern __shared__ __align__(128) float smem[];
     float* R1 = smem;                        // [H][RP]
@@ -355,22 +360,22 @@ __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
         const int rh = tid % C::RH;
         const int g = (tid / C::RH) % C::CG;
         const int p = tid / C::TPP;
-        const int row0 = p * C::PSTRIDE + rh * 16;
+        const int row0 = p * C::PSTRIDE + rh * RT;
         WPipe pipe{ring, bars, 0u, C::WSTAGE};
-        float acc2[16][4];
+        float acc2[RT][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gs = a.gsum[g * 4 + j];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc2[r][j] = gs;
+            for (int r = 0; r < RT; ++r) acc2[r][j] = gs;
         }
-        gemm_stream<1, NT>(acc2, R1, RP, row0, H, a.gsym, H, 0, g, pipe, tid);
+        gemm_stream<1, NT, RT>(acc2, R1, RP, row0, H, a.gsym, H, 0, g, pipe, tid);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float* rc = R1 + (size_t)(g * 4 + j) * RP + row0;
             float* dc = DU + (size_t)(g * 4 + j) * RP + row0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dc[r] = (rc[r] > 0.f) ? acc2[r][j] : 0.f;   // padding rows: r1 == 0
+            for (int r = 0; r < RT; ++r) dc[r] = (rc[r] > 0.f) ? acc2[r][j] : 0.f;   // padding rows: r1 == 0
         }
         __syncthreads();
         reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(DU, RPE, RP, a.g1, kRpeRows, 11, tid);
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
 // ------------------------------------------------------------------------------------- launchers
 template <int D, int K, int NT, int STAGE>
 static int launch_bwd(const LfaBwdArgs& a, cudaStream_t st) {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     auto kern = lfa_pool_bwd_kernel<D, K, NT, STAGE>;
     constexpr size_t smem = LfaBwdSmem<D, K, NT>::BYTES;
     static_assert(smem <= 232448, "backward tile does not fit shared memory");
@@ -395,15 +400,15 @@ template <int STAGE>
 static int dispatch_bwd(int d, int K, const LfaBwdArgs& a, cudaStream_t st) {
 #define R3D_CASE(DD, KK, NT) \
     if (d == DD && K == KK) return launch_bwd<DD, KK, NT, STAGE>(a, st);
-    R3D_CASE(16, 16, 64) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
-    R3D_CASE(16, 32, 64) R3D_CASE(32, 32, 128) R3D_CASE(64, 32, 128) R3D_CASE(128, 32, 128) R3D_CASE(256, 32, 128)
+    R3D_CASE(16, 16, 128) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
+    R3D_CASE(16, 32, 128) R3D_CASE(32, 32, 128) R3D_CASE(64, 32, 128) R3D_CASE(128, 32, 128) R3D_CASE(256, 32, 128)
 #undef R3D_CASE
     return R3D_EUNSUPPORTED;
 }
 
 template <int D, int K, int NT, int MODE>
 static int launch_mom(const LfaMomArgs& a, cudaStream_t st) {
-    using C = LfaCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT>;
     auto kern = lfa_moments_kernel<D, K, NT, MODE>;
     constexpr size_t smem = LfaMomSmem<D, K, NT>::BYTES;
     static_assert(smem <= 232448, "moments tile does not fit shared memory");

@@ -12,13 +12,17 @@
 
 namespace r3d {
 
+// rows of the per-thread register tile by layer width (see lfa.cu)
+__host__ __device__ constexpr int lfa_rows_per_thread(int d) { return d <= 16 ? 4 : (d <= 32 ? 8 : 16); }
+
 constexpr int kRpeRows = 16;  // rpe buffer: 10 encoding channels, a row of ones (col 10), 5 zero rows
 
-template <int D, int K, int THREADS = 128, int WSTAGE_MAX = 4096>
+template <int D, int K, int THREADS = 128, int WSTAGE_MAX = 4096, int ROWS_PER_THREAD = 16>
 struct LfaCfg {
     static constexpr int NT = THREADS;
     static constexpr int H = D / 2;
-    static constexpr int RH = K / 16;                   // 16-row halves per point
+    static constexpr int RT = ROWS_PER_THREAD;          // rows of the register tile (16; 4 for narrow layers: more threads per point)
+    static constexpr int RH = K / RT;                   // row groups per point
     static constexpr int CG = D / 8;                    // column groups (8 columns per thread)
     static constexpr int TPP = RH * CG;                 // threads per point
     static constexpr int PTS = THREADS / TPP;           // points per CTA
@@ -29,7 +33,7 @@ struct LfaCfg {
     static constexpr int ROWS = PTS * K;
     static constexpr int X_FLOATS = D * ROWS_PAD;
     static constexpr int WSTAGE = (D * D < WSTAGE_MAX) ? D * D : WSTAGE_MAX;   // floats per weight-ring stage
-    static_assert(K % 16 == 0 && K >= 16 && K <= 64, "K must be a multiple of 16 up to 64");
+    static_assert(K % 16 == 0 && K >= 16 && K <= 64 && K % RT == 0 && RT % 4 == 0, "K must be a multiple of 16 up to 64");
     static_assert(D % 8 == 0 && TPP <= THREADS && THREADS % TPP == 0 && THREADS % 32 == 0, "unsupported width");
 };
 
@@ -48,11 +52,11 @@ __device__ __forceinline__ void wpipe_issue(const WPipe& p, uint32_t chunk_no, c
     tma_bulk_g2s(p.ring + s * p.stage_floats, src, floats * 4u, &p.bars[s]);
 }
 
-// acc[16][4*NC] += A[16 rows][Kred] * W[Kred][cols].  A in shared memory channel-major with leading
-// dimension lda (rows row0..row0+15 of channel kk at A[kk*lda + row0 ..]); W (Kred x width) row-major in
+// acc[RT][4*NC] += A[RT rows][Kred] * W[Kred][cols].  A in shared memory channel-major with leading
+// dimension lda (rows row0..row0+RT-1 of channel kk at A[kk*lda + row0 ..]); W (Kred x width) row-major in
 // global memory.  Thread columns: for q < NC: q*qstride + g*4 + {0..3}.  Ends with a CTA barrier.
-template <int NC, int NT>
-__device__ __forceinline__ void gemm_stream(float (&acc)[16][4 * NC], const float* __restrict__ A, int lda,
+template <int NC, int NT, int RT>
+__device__ __forceinline__ void gemm_stream(float (&acc)[RT][4 * NC], const float* __restrict__ A, int lda,
                                             int row0, int Kred, const float* __restrict__ Wg, int width,
                                             int qstride, int g, WPipe& pipe, int tid) {
     const int kc_max = pipe.stage_floats / width;
@@ -71,9 +75,9 @@ __device__ __forceinline__ void gemm_stream(float (&acc)[16][4 * NC], const floa
         const float* Ap = A + (size_t)(ch * kc) * lda + row0;
 #pragma unroll 2
         for (int kk = 0; kk < rows_here; ++kk) {
-            float av[16];
+            float av[RT];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < RT / 4; ++v) {
                 const float4 t = *reinterpret_cast<const float4*>(Ap + (size_t)kk * lda + 4 * v);
                 av[4 * v + 0] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
             }
@@ -84,7 +88,7 @@ __device__ __forceinline__ void gemm_stream(float (&acc)[16][4 * NC], const floa
                 wv[4 * q + 0] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
             }
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
+            for (int r = 0; r < RT; ++r)
 #pragma unroll
                 for (int j = 0; j < 4 * NC; ++j) acc[r][j] = fmaf(av[r], wv[j], acc[r][j]);
         }
