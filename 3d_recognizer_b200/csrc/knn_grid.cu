@@ -318,22 +318,32 @@ __global__ void __launch_bounds__(kGridThreads) knn_grid_kernel(
         }
     }
 
-    auto scan = [&](int lo, int hi) {
-        for (int j = lo; j < hi; ++j) {
-            const float4 p = __ldg(&P[j]);
-            const float d = d2_contract_g(qx, qy, qz, p.x, p.y, p.z);
-            const int id = __float_as_int(p.w);
-            if (K1) {
-                if (d < best_d || (d == best_d && id < best_i)) {
-                    best_d = d;
-                    best_i = id;
-                }
-            } else if (KT > 1) {
-                kbest_insert_t<(KT > 1 ? KT : 2)>(L, d, id);
-            } else {
-                kbest_insert(L, d, id);
+    auto consider = [&](const float4 p) {
+        const float d = d2_contract_g(qx, qy, qz, p.x, p.y, p.z);
+        const int id = __float_as_int(p.w);
+        if (K1) {
+            if (d < best_d || (d == best_d && id < best_i)) {
+                best_d = d;
+                best_i = id;
             }
+        } else if (KT > 1) {
+            kbest_insert_t<(KT > 1 ? KT : 2)>(L, d, id);
+        } else {
+            kbest_insert(L, d, id);
         }
+    };
+    // candidates four at a time: the loads are independent of the insertions, so issuing them together hides the
+    // L1/L2 latency that a one-at-a-time loop pays per candidate (small clouds run one warp per scheduler)
+    auto scan = [&](int lo, int hi) {
+        int j = lo;
+        for (; j + 4 <= hi; j += 4) {
+            const float4 p0 = __ldg(&P[j]), p1 = __ldg(&P[j + 1]), p2 = __ldg(&P[j + 2]), p3 = __ldg(&P[j + 3]);
+            consider(p0);
+            consider(p1);
+            consider(p2);
+            consider(p3);
+        }
+        for (; j < hi; ++j) consider(__ldg(&P[j]));
     };
 
     const int gx = h.g[0], gy = h.g[1], gz = h.g[2];

@@ -51,7 +51,7 @@ struct LfaBwdArgs {
 };
 
 template <int D, int K, int NT>
-using LfaBwdCfg = LfaCfg<D, K, NT, 4096, lfa_rows_per_thread(D)>;
+using LfaBwdCfg = LfaCfg<D, K, NT, (D <= 64 ? 2048 : 4096), lfa_rows_per_thread(D)>;
 
 template <int D, int K, int NT>
 struct LfaBwdSmem {

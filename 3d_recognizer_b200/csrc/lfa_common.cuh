@@ -13,7 +13,7 @@
 namespace r3d {
 
 // rows of the per-thread register tile by layer width (see lfa.cu)
-__host__ __device__ constexpr int lfa_rows_per_thread(int d) { return d <= 16 ? 4 : (d <= 32 ? 8 : 16); }
+__host__ __device__ constexpr int lfa_rows_per_thread(int d) { return d <= 16 ? 4 : (d <= 64 ? 8 : 16); }
 
 constexpr int kRpeRows = 16;  // rpe buffer: 10 encoding channels, a row of ones (col 10), 5 zero rows
 

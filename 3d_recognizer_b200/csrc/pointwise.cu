@@ -437,6 +437,8 @@ constexpr int kPwSmallMaxW = 4096;  // floats of weights staged in smem (cin*cou
 
 __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
     __shared__ float Ws[kPwSmallMaxW];
+    __shared__ float cta_sum[2][kPwSmallMaxCout];
+    if (threadIdx.x < 2 * kPwSmallMaxCout) (&cta_sum[0][0])[threadIdx.x] = 0.f;
     const int cin = a.ca + a.cb;
     for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x)
         Ws[i] = a.w_out_in ? a.wT[(size_t)(i % a.cout) * cin + i / a.cout] : a.wT[i];
@@ -451,27 +453,55 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
 #pragma unroll
     for (int j = 0; j < kPwSmallMaxCout; ++j) acc[j] = 0.f;
     const float* ra = src_row(a, b, n, false);
-    for (int c = 0; c < a.ca; ++c) {
-        const float x = ra[c];
+    if ((a.ca & 3) == 0) {                       // rows are 16-byte aligned (checked by the host): vector loads
+        for (int c = 0; c < a.ca; c += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(ra + c);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int j = 0; j < kPwSmallMaxCout; ++j)
-            if (j < a.cout) acc[j] = fmaf(x, Ws[c * a.cout + j], acc[j]);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < kPwSmallMaxCout; ++j)
+                    if (j < a.cout) acc[j] = fmaf(xv[u], Ws[(c + u) * a.cout + j], acc[j]);
+        }
+    } else {
+        for (int c = 0; c < a.ca; ++c) {
+            const float x = ra[c];
+#pragma unroll
+            for (int j = 0; j < kPwSmallMaxCout; ++j)
+                if (j < a.cout) acc[j] = fmaf(x, Ws[c * a.cout + j], acc[j]);
+        }
     }
     if (a.cb > 0) {
         const float* rb = src_row(a, b, n, true);
-        for (int c = 0; c < a.cb; ++c) {
-            const float x = rb[c];
+        if ((a.cb & 3) == 0) {
+            for (int c = 0; c < a.cb; c += 4) {
+                const float4 x4 = *reinterpret_cast<const float4*>(rb + c);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-            for (int j = 0; j < kPwSmallMaxCout; ++j)
-                if (j < a.cout) acc[j] = fmaf(x, Ws[(a.ca + c) * a.cout + j], acc[j]);
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < kPwSmallMaxCout; ++j)
+                        if (j < a.cout) acc[j] = fmaf(xv[u], Ws[(a.ca + c + u) * a.cout + j], acc[j]);
+            }
+        } else {
+            for (int c = 0; c < a.cb; ++c) {
+                const float x = rb[c];
+#pragma unroll
+                for (int j = 0; j < kPwSmallMaxCout; ++j)
+                    if (j < a.cout) acc[j] = fmaf(x, Ws[(a.ca + c) * a.cout + j], acc[j]);
+            }
         }
     }
+    // whole output rows as 16-byte stores when the layout allows (a row is cout contiguous floats)
+    const bool vec_out = !a.transpose_out && (a.cout & 3) == 0 && (a.y_ld & 3) == 0 && (a.y_bstride & 3) == 0;
+    float outv[kPwSmallMaxCout];
 #pragma unroll
     for (int j = 0; j < kPwSmallMaxCout; ++j) {
         if (j >= a.cout) break;
         const float sc = a.scale ? a.scale[j] : 1.f, sh = a.shift ? a.shift[j] : 0.f;
         const float o = apply_act(fmaf(acc[j], sc, sh), a.act, a.slope);
-        if (live) {
+        outv[j] = o;
+        if (live && !vec_out) {
             if (a.transpose_out)
                 a.y[(size_t)b * a.y_bstride + (size_t)j * a.n + n] = o;
             else
@@ -485,10 +515,23 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
                 s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
             if ((threadIdx.x & 31) == 0) {
-                atomicAdd(a.stats + j, (double)s1);
-                atomicAdd(a.stats + a.cout + j, (double)s2);
+                atomicAdd(&cta_sum[0][j], s1);
+                atomicAdd(&cta_sum[1][j], s2);
             }
         }
+    }
+    if (a.stats) {          // one global (fp64) atomic per channel and CTA, not per warp: the 2*cout addresses are hot
+        __syncthreads();
+        if (threadIdx.x < a.cout) {
+            atomicAdd(a.stats + threadIdx.x, (double)cta_sum[0][threadIdx.x]);
+            atomicAdd(a.stats + a.cout + threadIdx.x, (double)cta_sum[1][threadIdx.x]);
+        }
+    }
+    if (live && vec_out) {
+        float* yr = a.y + (size_t)b * a.y_bstride + (size_t)n * a.y_ld;
+#pragma unroll
+        for (int j = 0; j < kPwSmallMaxCout; j += 4)
+            if (j < a.cout) *reinterpret_cast<float4*>(yr + j) = make_float4(outv[j], outv[j + 1], outv[j + 2], outv[j + 3]);
     }
 }
 
@@ -527,7 +570,7 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     if (!is_aligned(xa, 16) || (xb && !is_aligned(xb, 16)) || !is_aligned(wT, 16) || !is_aligned(y, 16))
         return R3D_EALIGN;
     // vector loads need every source row 16-byte aligned
-    if ((ca % 4 == 0 && cb % 4 == 0) && ((xa_bstride % 4) || (cb > 0 && (xb_bstride % 4)))) return R3D_EALIGN;
+    if ((ca % 4 == 0 && (xa_bstride % 4)) || (cb > 0 && cb % 4 == 0 && (xb_bstride % 4))) return R3D_EALIGN;
     PwArgs a{xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
              y, y_bstride, y_ld, cout, B, n, transpose_out, stats, w_out_in};
     cudaStream_t st = static_cast<cudaStream_t>(stream);

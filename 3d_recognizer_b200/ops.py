@@ -153,7 +153,7 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
         gs = 0 if gidx.dim() == 1 else gidx.stride(0)
     flops = 2.0 * B * n * (ca + cb) * cout
     nbytes = 4.0 * B * n * (ca + cb + cout)
-    with torch.cuda.device(dev), _cabi.kernel_timer("pointwise", flops=flops, bytes=nbytes):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"pointwise[M={B * n},{ca + cb}->{cout}]" if _cabi.TIMER_SHAPES else "pointwise", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_pointwise_stats(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
                                              _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act],
                                              float(slope), _cabi.ptr(out), 0, 0, cout, B, n,
@@ -209,7 +209,7 @@ def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     M, Ca = a.shape
     Cb = b.shape[1]
     out = torch.zeros((Ca, Cb), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device), _cabi.kernel_timer("rowreduce_gemm", flops=2.0 * M * Ca * Cb,
+    with torch.cuda.device(a.device), _cabi.kernel_timer(f"rowreduce_gemm[M={M},{Ca}x{Cb}]" if _cabi.TIMER_SHAPES else "rowreduce_gemm", flops=2.0 * M * Ca * Cb,
                                                          bytes=4.0 * M * (Ca + Cb)):
         rc = _cabi.lib().r3d_rowreduce_gemm(_cabi.ptr(a), Ca, _cabi.ptr(b), Cb, M, _cabi.ptr(out), Cb,
                                             _cabi.stream_ptr(a.device))
