@@ -66,7 +66,7 @@ SIGNATURES = {
 # ---- per-kernel device timing (bench.py's roofline): when KERNEL_TIMERS is a dict, every ops wrapper
 # brackets its C-ABI call with CUDA events on the launching stream and files them under a kernel name.
 KERNEL_TIMERS = None
-TIMER_SHAPES = False   # per-point layer timers keyed by shape (tools/layer_table.py) instead of one aggregate
+TIMER_SHAPES = True    # per-point layer timers keyed by shape (tools/layer_table.py) instead of one aggregate
 
 
 class kernel_timer:

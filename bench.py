@@ -452,6 +452,25 @@ def main():
     tab = kernel_table(cabi.KERNEL_TIMERS)
     cabi.KERNEL_TIMERS = None
     eager_ms_per_step = eager_ms / n_eager
+    if wl["kind"] == "knn":
+        # The default search for clouds this large is the uniform-grid back-end, whose work is O(N K), not the
+        # 8 N^2 flop of the exhaustive scan, so it has no FP32 roofline to speak of.  The roofline entry is taken
+        # on the tiled brute-force kernel (same results, forced through r3d_knn_set_algorithm), timed here.
+        prev = L.r3d_knn_set_algorithm(1)
+        cabi.KERNEL_TIMERS = {}
+        for i in range(3):
+            ops.knn(s_d, q_d, k, idx64=True, dist=False, dist_sq=True)
+        torch.cuda.synchronize()
+        brute = kernel_table(cabi.KERNEL_TIMERS)
+        cabi.KERNEL_TIMERS = None
+        L.r3d_knn_set_algorithm(prev)
+        for kn, kv in brute.items():
+            kv["ms_total"] = kv["ms_avg"] * n_eager * 1.0      # comparable with the per-step table below
+            tab["brute_force_" + kn] = kv
+        grid_name = next(kn for kn in tab if not kn.startswith("brute_force_"))
+        extras["default_search"] = "uniform grid (r3d_knn algorithm 0/2)"
+        extras["brute_force_queries_per_sec"] = units_per_step / (next(iter(brute.values()))["ms_avg"] * 1e-3)
+        extras["grid_ms_per_launch"] = tab[grid_name]["ms_avg"]
     graphed = build_graph is not None
     if graphed:
         build_graph()
