@@ -1,0 +1,142 @@
+"""GPU tests of the reference-facing module API beyond the golden cases: KNN / UpSampler modules, error
+behaviour, a training step on a configuration the goldens do not cover (K=32, point features, 3 classes)
+against the oracle port run on the CPU, and CUDA-graph replay of the training step against eager execution."""
+import copy
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as onet
+from oracle.knn import knn_exact
+from test_forward_gpu import make_input, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return (importlib.import_module("3d_recognizer_b200.modules"), importlib.import_module("3d_recognizer_b200.engine"),
+            importlib.import_module("3d_recognizer_b200.model"))
+
+
+def test_knn_module_contract(mods):
+    """KNN.forward (modules.py:107-150): int64 indices, NON-squared distances, any back-end name, ValueError
+    on an unknown one; inputs may live on the CPU (the reference moves them itself)."""
+    modules, _, _ = mods
+    dev = torch.device("cuda")
+    knn = modules.KNN(dev)
+    rng = np.random.RandomState(0)
+    s, q = rng.rand(2, 900, 3).astype(np.float32), rng.rand(2, 300, 3).astype(np.float32)
+    oi, od = knn_exact(s, q, 8)
+    for approach in ("kdtree", "approximate", "naive"):
+        idx, dist = knn(torch.from_numpy(s), torch.from_numpy(q), 8, approach)
+        assert idx.dtype == torch.int64 and dist.dtype == torch.float32 and idx.is_cuda
+        assert np.array_equal(idx.cpu().numpy(), oi)
+        assert np.array_equal(dist.cpu().numpy(), np.sqrt(od))
+    with pytest.raises(ValueError):
+        knn(torch.from_numpy(s), torch.from_numpy(q), 8, "ball_tree")
+
+
+@pytest.mark.parametrize("approach", ["none", "nni", "nna", "idw", "isdw"])
+def test_upsampler_vs_oracle(mods, approach):
+    """UpSampler (modules.py:328-456) on (B,F,N1,1) features: all modes vs the oracle restatement."""
+    modules, _, _ = mods
+    rng = np.random.RandomState(4)
+    feat = torch.from_numpy(rng.randn(2, 5, 700, 1).astype(np.float32))
+    xyz = torch.from_numpy(rng.rand(2, 700, 3).astype(np.float32))
+    xyz_up = torch.from_numpy(rng.rand(2, 3000, 3).astype(np.float32))
+    up = modules.UpSampler(approach, torch.device("cuda"))
+    got = up(feat.cuda(), xyz.cuda(), xyz_up.cuda()).cpu()
+    ref = onet.upsample(approach, feat, xyz, xyz_up)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-5
+    with pytest.raises(ValueError):
+        modules.UpSampler("cubic", torch.device("cuda"))(feat.cuda(), xyz.cuda(), xyz_up.cuda())
+
+
+def test_forward_asserts_on_gpu(mods):
+    modules, _, _ = mods
+    net = modules.RandLANet(modules.RandLANetSettings(n_classes=2, n_neighbors=16), torch.device("cuda"))
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 1024, 4, device="cuda"))            # dim != 3 + F
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 1023, 3, device="cuda"))            # fewer than max(16*64, 2*256) points
+    assert net.device.type == "cuda" and net.settings.n_neighbors == 16
+
+
+def test_train_step_k32_features_vs_oracle_port(mods):
+    """K=32, 2 point features, 3 classes, N=2560, B=2 — not among the golden cases: logits, loss, gradients and
+    running statistics of one training step vs the oracle port (pinned to the reference) on the CPU."""
+    modules, _, _ = mods
+    st = dict(n_classes=3, n_points=2560, n_features=2, n_neighbors=32, knn="kdtree")
+    sd = onet.synth_state_dict(st, 31)
+    x = torch.from_numpy(make_input(2, 2560, 2, 31))
+    labels = torch.from_numpy(np.random.RandomState(31).randint(0, 3, (2, 2560)))
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    leaves = {}
+    for k, v in sd_ref.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            leaves[k] = v
+    np.random.seed(77)
+    ref_logits = onet.forward(sd_ref, st, x, training=True, dropout_p=0.0)
+    ref_loss = onet.dice_loss(ref_logits, labels)
+    ref_loss.backward()
+    history = []
+    for _ in range(3):                                          # kink flips: see test_train_gpu
+        net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+        net.load_state_dict(sd)
+        net.train()
+        net.fc_end[2].p = 0.0
+        np.random.seed(77)
+        logits = net(x.cuda())
+        loss = onet.dice_loss(logits, labels.cuda())
+        loss.backward()
+        fails = []
+        if not rel_err(logits.detach().cpu(), ref_logits.detach()) < TOL:
+            fails.append("logits")
+        if not abs(loss.item() - ref_loss.item()) < 1e-5:
+            fails.append("loss")
+        worst, wname = onet.grad_parity({k: p.grad for k, p in net.named_parameters()},
+                                        {k: v.grad for k, v in leaves.items()})
+        if not worst < TOL:
+            fails.append(("grad", worst, wname))
+        for k, v in net.state_dict().items():
+            if "running" in k and not torch.allclose(v.cpu(), sd_ref[k].detach(), rtol=1e-4, atol=1e-5):
+                fails.append(("running", k))
+        if not fails:
+            return
+        history.append(fails)
+    raise AssertionError(history)
+
+
+def test_graphed_train_step_matches_eager(mods):
+    """GraphedTrainStep (CUDA-graph replay) follows the same loss trajectory as eager Model.train_step from the
+    same weights, data and numpy seed (Dropout off so that both paths are deterministic functions of those)."""
+    modules, _, model_mod = mods
+    syn = importlib.import_module("3d_recognizer_b200.synthetic")
+    st = modules.RandLANetSettings(n_classes=2, n_points=1024, n_features=0, n_neighbors=16, knn="naive")
+    torch.manual_seed(3)
+    a = model_mod.Model(st)
+    b = model_mod.Model(st, weights=copy.deepcopy(a.module.state_dict()))
+    for m in (a, b):
+        m.module.fc_end[2].p = 0.0
+    x, y = syn.fingertip_batch(5, 4, 1024, n_raw=20000)
+    x, y = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    opt_a = a.make_optimizer(1e-3)
+    opt_b = b.make_optimizer(1e-3, capturable=True)
+    np.random.seed(11)
+    gstep = model_mod.GraphedTrainStep(b, opt_b, (4, 1024, 3), warmup=0)
+    np.random.seed(12)
+    eager = [float(a.train_step(x, y, opt_a)) for _ in range(4)]
+    np.random.seed(12)
+    graphed = [float(gstep(x, y)) for _ in range(4)]
+    assert np.allclose(eager, graphed, rtol=2e-3, atol=1e-5), (eager, graphed)
+    pa = torch.cat([p.detach().flatten() for p in a.module.parameters()])
+    pb = torch.cat([p.detach().flatten() for p in b.module.parameters()])
+    # Adam normalises every gradient to a step of about lr, also where the gradient is pure round-off, so after four
+    # steps two correct runs may differ by up to ~2 * 4 * lr in such parameters; the loss trajectory above is the check
+    assert float((pa - pb).abs().max()) < 2 * 4 * 1e-3 + 1e-4
