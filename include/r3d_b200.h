@@ -200,6 +200,12 @@ int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const flo
 int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
                        r3d_stream_t stream);
 
+/* ------------------------------------------------------------------------ tcgen05 tensor-core GEMM
+ * C (M,N) = A (M,K) W (N,K)^T with tcgen05.mma kind::tf32, accumulators in TMEM.  terms = 3: fp32-accurate
+ * 3xTF32 (operands split hi/lo on the fly, three MMAs per K step); terms = 1: plain TF32.
+ * N a multiple of 32 in [32,256], K a multiple of 4; A, W, C dense, 16-byte aligned.  (csrc/tc_gemm.cu) */
+int r3d_tc_gemm(const float* A, const float* W, float* C, int M, int N, int K, int terms, r3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------ FP32 peak probe
  * Roofline denominator of the CUDA-core kernels, measured live by bench.py (MEASURED_PEAKS.json has
  * HBM and bf16 tensor peaks only).  mode 0 = scalar FFMA, 1 = packed FFMA2 (f32x2).  `out` is a device
