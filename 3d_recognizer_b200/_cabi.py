@@ -34,6 +34,9 @@ SIGNATURES = {
     "r3d_lfa_pool": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_pool_tc": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
                          [c_int, c_int, c_int, c_int, c_void_p]),

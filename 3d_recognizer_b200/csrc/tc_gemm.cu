@@ -15,55 +15,13 @@
 //     two blocks later while the tensor core keeps running;
 //   * accumulators live in TMEM (N columns x 128 lanes); the epilogue reads them back with tcgen05.ld (warp w owns
 //     lanes 32w..32w+31 = rows) and stores C.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace r3d {
 
 constexpr int kTcThreads = 128;
 constexpr int kTcKB = 32;          // K block per stage
 constexpr int kTcMaxN = 256;
-
-__device__ __forceinline__ uint64_t umma_desc(const void* smem, uint32_t lbo16, uint32_t sbo16) {
-    const uint32_t addr = smem_u32(smem);
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);            // start address, 16-byte units
-    d |= (uint64_t)(lbo16 & 0x3FFF) << 16;            // leading-dimension byte offset (K direction), 16-byte units
-    d |= (uint64_t)(sbo16 & 0x3FFF) << 32;            // stride byte offset (8-row groups), 16-byte units
-    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    return d;                                         // base offset 0, layout type 0 = no swizzle
-}
-
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-    uint32_t d = 0;
-    d |= 1u << 4;                 // accumulator format F32
-    d |= 2u << 7;                 // A format TF32
-    d |= 2u << 10;                // B format TF32
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(M >> 4) << 24;
-    return d;                     // K-major A and B, no negate, dense
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
-    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-}
 
 // smem: Ahi[2][8][128] float4, Alo same, Whi[2][8][Np] float4, Wlo same, then barriers + tmem slot
 __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W,

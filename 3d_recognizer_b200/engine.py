@@ -184,8 +184,14 @@ class _LfaPoolFn(torch.autograd.Function):
         w1 = w1.contiguous()
         w2T = w2.t().contiguous() if stage == 2 else None
         wsT = ws.t().contiguous()
-        pooled = ops.lfa_pool(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
-                              a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None, wsT)
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+            pooled = ops.lfa_pool_tc(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(),
+                                     w2.contiguous() if stage == 2 else None, a2.contiguous() if stage == 2 else None,
+                                     c2.contiguous() if stage == 2 else None, ws.contiguous())
+        else:
+            pooled = ops.lfa_pool(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
+                                  a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None,
+                                  wsT)
         ctx.stage = stage
         ctx.save_for_backward(xyz, idx32, feat, w1, a1, c1, w2 if stage == 2 else None, a2 if stage == 2 else None,
                               c2 if stage == 2 else None, ws, w2T, wsT)
@@ -401,6 +407,10 @@ def folded_parameters(net) -> dict:
             e["rpe2"] = _fold(lfa.mlp_rpe2)                                 # wT (h,h) [in][out]
             e["score1"] = lfa.pool1.score_fn[0].weight.detach().t().contiguous()
             e["score2"] = lfa.pool2.score_fn[0].weight.detach().t().contiguous()
+            # stored [out][in] layouts for the tensor-core kernel
+            e["score1_oi"] = lfa.pool1.score_fn[0].weight.detach().contiguous()
+            e["score2_oi"] = lfa.pool2.score_fn[0].weight.detach().contiguous()
+            e["rpe2_oi"] = conv_weight_2d(lfa.mlp_rpe2).detach().contiguous()
             e["pool1"] = _fold(lfa.pool1.mlp)
             e["pool2"] = _fold(lfa.pool2.mlp)
             # residual sum mlp2(p2) + shortcut(x) as ONE layer over [p2 ; x]: BN scales folded into W
@@ -445,10 +455,13 @@ def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Te
         f = ops.pointwise(x, w, sc, sh, "lrelu", 0.2)
         w1, a1, b1 = e["rpe1"]
         w2T, a2, b2 = e["rpe2"]
-        pooled = ops.lfa_pool(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1"])
+        tc = ops.lfa_pool_tc_supported(2 * w1.shape[0], k)
+        pooled = (ops.lfa_pool_tc(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1_oi"]) if tc else
+                  ops.lfa_pool(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1"]))
         w, sc, sh = e["pool1"]
         p1 = ops.pointwise(pooled, w, sc, sh, "relu")
-        pooled = ops.lfa_pool(2, xyz_l, idx, p1, w1, a1, b1, w2T, a2, b2, e["score2"])
+        pooled = (ops.lfa_pool_tc(2, xyz_l, idx, p1, w1, a1, b1, e["rpe2_oi"], a2, b2, e["score2_oi"]) if tc else
+                  ops.lfa_pool(2, xyz_l, idx, p1, w1, a1, b1, w2T, a2, b2, e["score2"]))
         w, sc, sh = e["pool2"]
         p2 = ops.pointwise(pooled, w, sc, sh, "relu")
         w, sc, sh = e["res"]

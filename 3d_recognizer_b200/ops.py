@@ -99,6 +99,41 @@ def _rows_view(x: torch.Tensor):
     return x, (x.stride(0) if B > 1 else n * C)
 
 
+# tcgen05 path of the fused forward (d in TC_WIDTHS, K in TC_NEIGHBORS).  Parity-green (1e-6 relative against the
+# CUDA-core kernel) but OFF by default: with one thread per row its gather prologue and shuffle softmax are latency
+# bound at 4 warps/SM, and it measures 2x slower than the register-tiled FP32 kernel at d = 64/128
+# (profiles/r01_lfa_tc_vs_cuda_core.log).  It pays only once prologue, MMA and epilogue of successive tiles overlap
+# (warp-specialised persistent kernel) — see DESIGN.md.
+USE_TENSOR_CORES = False
+TC_WIDTHS, TC_NEIGHBORS = (64, 128), (16, 32)
+
+
+def lfa_pool_tc_supported(d: int, k: int) -> bool:
+    return USE_TENSOR_CORES and d in TC_WIDTHS and k in TC_NEIGHBORS
+
+
+def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Tensor, w_rpe1, a_rpe1, b_rpe1,
+                w_rpe2, a_rpe2, b_rpe2, w_score) -> torch.Tensor:
+    """``lfa_pool`` on the tensor cores (C ABI ``r3d_lfa_pool_tc``): weights in their stored [out][in] layout."""
+    _cabi.require_cuda(xyz, "xyz")
+    xyz, xs = _cloud_view(xyz)
+    feat, fs = _rows_view(feat.detach())
+    B, N, K = idx32.shape
+    h = feat.shape[2]
+    d = 2 * h
+    dev = xyz.device
+    pooled = torch.empty((B, N, d), dtype=torch.float32, device=dev)
+    flops = float(B) * N * (2 * K * (10 * h + d * d + d + (h * h if stage == 2 else 0)))
+    nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_tc[N={N},d={d}]", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_pool_tc(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
+                                         _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2),
+                                         _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_score), _cabi.ptr(pooled),
+                                         B, N, K, d, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_pool_tc")
+    return pooled
+
+
 def lfa_pool(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Tensor, w_rpe1, a_rpe1, b_rpe1,
              w_rpe2T, a_rpe2, b_rpe2, w_scoreT) -> torch.Tensor:
     """Fused LocSE + attentive pooling of one LFA half (C ABI ``r3d_lfa_pool``; modules.py:316-323).

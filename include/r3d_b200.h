@@ -109,6 +109,14 @@ int r3d_lfa_pool(int stage, const float* xyz, long long xyz_bstride, const int32
                  const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,
                  float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
 
+/* r3d_lfa_pool with the score GEMM (and mlp_rpe2) on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in
+ * TMEM: fp32-level accuracy).  Same operator and arguments, except that the weights come in their stored
+ * [out][in] layout: w_rpe2 (h,h), w_score (d,d).  Supported: d in {64,128}, K in {16,32}; else R3D_EUNSUPPORTED. */
+int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                    long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                    const float* w_rpe2, const float* a_rpe2, const float* b_rpe2, const float* w_score,
+                    float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
+
 /* Backward of one r3d_lfa_pool launch (autograd of modules.py:316-323 as driven by trainer.py:115-119).
  * Inputs as in the forward plus
  *   w_rpe2s  (h,h)  [out][in] mlp_rpe2 weight with row j scaled by a_rpe2[j]         (stage 2)

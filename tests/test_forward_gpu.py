@@ -165,3 +165,46 @@ def test_model_predict_vs_reference_golden(tmp_path):
         ref = g[f"conf_{ap}"]
         assert conf.shape == ref.shape
         assert np.abs(conf - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 8), (1000, 64, 64), (777, 128, 128), (4096, 256, 256), (300, 256, 1024)])
+def test_tcgen05_gemm_3xtf32_matches_fp64(M, N, K):
+    """r3d_tc_gemm (tcgen05.mma kind::tf32, TMEM accumulators): the 3xTF32 split reaches fp32-level accuracy, the
+    single-term variant shows plain TF32 error — i.e. the tensor-core path really ran and the split is what fixes it."""
+    cabi = importlib.import_module("3d_recognizer_b200._cabi")
+    L = cabi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    ref = A.double() @ W.double().t()
+    errs = {}
+    for terms in (1, 3):
+        C = torch.zeros(M, N, device="cuda")
+        cabi.check(L.r3d_tc_gemm(cabi.ptr(A), cabi.ptr(W), cabi.ptr(C), M, N, K, terms, cabi.stream_ptr(A.device)), "r3d_tc_gemm")
+        errs[terms] = rel_err(C.double(), ref)
+    assert errs[3] < 2e-5, errs
+    assert 1e-5 < errs[1] < 5e-3, errs
+
+
+@pytest.mark.parametrize("d,K", [(64, 16), (128, 16), (64, 32), (128, 32)])
+@pytest.mark.parametrize("stage", [1, 2])
+def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage):
+    """r3d_lfa_pool_tc (score GEMM + mlp_rpe2 on tcgen05, 3xTF32) against the FP32 CUDA-core kernel."""
+    _, _, ops = mods
+    h = d // 2
+    B, N = 2, 1000
+    g = torch.Generator(device="cuda").manual_seed(d + K + stage)
+    xyz = torch.rand(B, N, 3, device="cuda", generator=g)
+    feat = torch.randn(B, N, h, device="cuda", generator=g)
+    idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
+    w1 = torch.randn(h, 10, device="cuda", generator=g)
+    a1 = torch.rand(h, device="cuda", generator=g) + 0.5
+    b1 = torch.randn(h, device="cuda", generator=g) * 0.3
+    w2 = (torch.randn(h, h, device="cuda", generator=g) / h ** 0.5).contiguous()
+    ws = (torch.randn(d, d, device="cuda", generator=g) / d ** 0.5).contiguous()
+    s2 = stage == 2
+    ref = ops.lfa_pool(stage, xyz, idx, feat, w1, a1, b1, w2.t().contiguous() if s2 else None, a1 if s2 else None,
+                       b1 if s2 else None, ws.t().contiguous())
+    got = ops.lfa_pool_tc(stage, xyz, idx, feat, w1, a1, b1, w2 if s2 else None, a1 if s2 else None,
+                          b1 if s2 else None, ws)
+    assert rel_err(got, ref) < 1e-5

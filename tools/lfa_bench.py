@@ -59,7 +59,17 @@ def main():
             ms_b = timeit(lambda: ops.lfa_pool_bwd(stage, xyz, idx, feat, w1, a1, b1, w2T if s2 else None,
                                                    a1 if s2 else None, b1 if s2 else None, w2 if s2 else None, wsT,
                                                    ws, dp), iters)
-            print(json.dumps(dict(level=l, N=N, d=d, K=K, B=B, stage=stage, fwd_ms=ms_f, fwd_tflops=f_flops / ms_f * 1e-9,
+            tcd = {}
+            if ops.lfa_pool_tc_supported(d, K):
+                ms_t = timeit(lambda: ops.lfa_pool_tc(stage, xyz, idx, feat, w1, a1, b1, w2 if s2 else None,
+                                                      a1 if s2 else None, b1 if s2 else None, ws), iters)
+                ref = ops.lfa_pool(stage, xyz, idx, feat, w1, a1, b1, w2T if s2 else None, a1 if s2 else None,
+                                   b1 if s2 else None, wsT)
+                got = ops.lfa_pool_tc(stage, xyz, idx, feat, w1, a1, b1, w2 if s2 else None, a1 if s2 else None,
+                                      b1 if s2 else None, ws)
+                tcd = dict(tc_fwd_ms=ms_t, tc_fwd_tflops=f_flops / ms_t * 1e-9,
+                           tc_vs_cuda_core_rel=float((got - ref).abs().max() / ref.abs().max()))
+            print(json.dumps(dict(level=l, N=N, d=d, K=K, B=B, stage=stage, **tcd, fwd_ms=ms_f, fwd_tflops=f_flops / ms_f * 1e-9,
                                   bwd_ms=ms_b, bwd_tflops=b_flops / ms_b * 1e-9)), flush=True)
         ms0 = timeit(lambda: ops.lfa_moments(0, xyz, idx, d), iters)
         ms1 = timeit(lambda: ops.lfa_moments(1, xyz, idx, d, w1, a1, b1), iters)
