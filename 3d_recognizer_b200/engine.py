@@ -63,21 +63,24 @@ class _SharedMLPTrainFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, gamma, beta, bn, act, slope):
         x = x.contiguous()
         cout = w.shape[0]
-        stats = torch.zeros(2 * cout, dtype=torch.float64, device=x.device)
+        scratch = torch.zeros(4 * cout, dtype=torch.float64, device=x.device)   # forward stats | backward stats
+        stats = scratch[:2 * cout]
         z = ops.pointwise(x.unsqueeze(0), w.contiguous(), stats=stats, w_out_in=True).squeeze(0)
         y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
         ctx.act, ctx.slope = act, slope
-        ctx.save_for_backward(x, w, z, save, beta)
+        ctx.save_for_backward(x, w, z, save, beta, scratch)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, z, save, beta = ctx.saved_tensors
-        dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope)
+        x, w, z, save, beta, scratch = ctx.saved_tensors
+        cout = w.shape[0]
+        dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope, stats2=scratch[2 * cout:])
         dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
         dw = ops.rowreduce_gemm(dz, x)
-        # the conv bias cancels against the batch mean: its gradient is exactly zero
-        return dx, dw, torch.zeros_like(dgamma), dgamma, dbeta, None, None, None
+        # the conv bias cancels against the batch mean: its gradient is exactly zero and is reported as None (the
+        # optimiser then leaves the parameter alone, which is what a zero gradient does)
+        return dx, dw, None, dgamma, dbeta, None, None, None
 
 
 class _LinearFn(torch.autograd.Function):
@@ -254,8 +257,8 @@ class _BnFromMomentsFn(torch.autograd.Function):
         w, gamma, s, m, save = ctx.saved_tensors
         need = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
         dw, dgamma, dbeta, dm, ds = ops.bn_from_moments_bwd(w, s, m, ctx.count, gamma.contiguous(), save, ga, gc, need)
-        # the conv bias cancels against the batch mean: exactly zero gradient
-        return dw, torch.zeros_like(dgamma), dgamma, dbeta, ds, dm, None, None
+        # the conv bias cancels against the batch mean: exactly zero gradient, reported as None
+        return dw, None, dgamma, dbeta, ds, dm, None, None
 
 
 def _eval_affine(smlp):

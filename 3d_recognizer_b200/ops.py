@@ -58,7 +58,12 @@ def knn(support: torch.Tensor, query: torch.Tensor, k: int, *, idx64: bool = Tru
             out["dist_sq"] = torch.empty((B, Nq, k), dtype=torch.float32, device=dev)
         wbytes = L.r3d_knn_workspace_bytes(B, Ns, Nq, k)
         ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
-        with _cabi.kernel_timer(f"knn_k{k}[Ns={Ns}]", flops=8.0 * B * Ns * Nq,
+        # the uniform-grid back-end does O(N K) work: crediting it with the 8 Nq Ns flop of the exhaustive scan would
+        # put it far above any roofline, so only the brute-force kernel carries algorithmic flops
+        algo = L.r3d_knn_set_algorithm(-1)
+        grid = algo == 2 or (algo == 0 and Ns >= 2048)
+        with _cabi.kernel_timer(f"knn_{'grid' if grid else 'brute'}_k{k}[Ns={Ns}]",
+                                flops=0.0 if grid else 8.0 * B * Ns * Nq,
                                 bytes=4.0 * B * (3 * Ns + 3 * Nq + Nq * k * (len(out) + ("idx64" in out)))):
             rc = L.r3d_knn(ctypes.c_void_p(support.data_ptr()), s_stride, ctypes.c_void_p(query.data_ptr()),
                            q_stride, B, Ns, Nq, k,
@@ -207,7 +212,7 @@ def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bia
     y = torch.empty_like(z)
     save = torch.empty((3, C), dtype=torch.float32, device=z.device)
     track = bn.track_running_stats and bn.running_mean is not None
-    with torch.cuda.device(z.device), _cabi.kernel_timer("bn_apply", flops=4.0 * M * C, bytes=8.0 * M * C):
+    with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_apply[M={M},C={C}]", flops=4.0 * M * C, bytes=8.0 * M * C):
         rc = _cabi.lib().r3d_bn_apply(_cabi.ptr(z), _cabi.ptr(stats), M, C, _cabi.ptr(bn.weight.detach()),
                                       _cabi.ptr(bn.bias.detach()), _cabi.ptr(bias.detach()) if bias is not None else None,
                                       float(bn.eps), float(bn.momentum),
@@ -219,15 +224,18 @@ def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bia
     return y, save
 
 
-def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0):
+def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0,
+                stats2: Optional[torch.Tensor] = None):
     """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd_reduce`` + ``r3d_bn_bwd_dz``).
-    Returns (dz (M,C), dgamma (C), dbeta (C))."""
+    ``stats2``: optional zero-filled (2C) fp64 scratch (the forward allocates it together with its own statistics
+    buffer: one fill instead of two).  Returns (dz (M,C), dgamma (C), dbeta (C))."""
     M, C = z.shape
     dy = dy.contiguous()
-    stats2 = torch.zeros(2 * C, dtype=torch.float64, device=z.device)
+    if stats2 is None:
+        stats2 = torch.zeros(2 * C, dtype=torch.float64, device=z.device)
     dz = torch.empty_like(z)
     L = _cabi.lib()
-    with torch.cuda.device(z.device), _cabi.kernel_timer("bn_backward", flops=12.0 * M * C, bytes=20.0 * M * C):
+    with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_backward[M={M},C={C}]", flops=12.0 * M * C, bytes=20.0 * M * C):
         rc = L.r3d_bn_bwd_reduce(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
                                  float(slope), _cabi.ptr(stats2), _cabi.stream_ptr(z.device))
         _cabi.check(rc, "r3d_bn_bwd_reduce")
@@ -263,14 +271,15 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
     d = 2 * h
     dev = xyz.device
     dpooled = dpooled.contiguous()
-    dfeat = torch.zeros((B, N, h), dtype=torch.float32, device=dev)
-    # one zero-filled block for all small accumulators
-    acc = torch.zeros(d * d + h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float32, device=dev)
-    dws = acc[:d * d].view(d, d)
-    g1 = acc[d * d:d * d + h * 16].view(h, 16)
+    # one zero-filled block for the feature gradient and all small accumulators
+    n_df = B * N * h
+    acc = torch.zeros(n_df + d * d + h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float32, device=dev)
+    dfeat = acc[:n_df].view(B, N, h)
+    dws = acc[n_df:n_df + d * d].view(d, d)
+    g1 = acc[n_df + d * d:n_df + d * d + h * 16].view(h, 16)
     g2m = g2c = None
     if stage == 2:
-        o = d * d + h * 16
+        o = n_df + d * d + h * 16
         g2m = acc[o:o + h * h].view(h, h)
         g2c = acc[o + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
@@ -279,7 +288,7 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
         rc = _cabi.lib().r3d_lfa_pool_bwd(
             stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
             _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T), _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_rpe2s),
-            _cabi.ptr(w_scoreT), _cabi.ptr(w_score), _cabi.ptr(dpooled), _cabi.ptr(dfeat), 0, _cabi.raw(dws),
+            _cabi.ptr(w_scoreT), _cabi.ptr(w_score), _cabi.ptr(dpooled), _cabi.raw(dfeat), 0, _cabi.raw(dws),
             _cabi.raw(g1), _cabi.raw(g2m), _cabi.raw(g2c), B, N, K, d, _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_lfa_pool_bwd")
     return dfeat, dws, g1, g2m, g2c
@@ -325,7 +334,7 @@ def bn_from_moments(w: torch.Tensor, s: torch.Tensor, m: torch.Tensor, count: fl
     c = torch.empty(cout, dtype=torch.float32, device=dev)
     save = torch.empty((5, cout), dtype=torch.float64, device=dev)
     track = bn.track_running_stats and bn.running_mean is not None
-    with torch.cuda.device(dev), _cabi.kernel_timer("bn_from_moments", flops=2.0 * cout * cin * cin, bytes=8.0 * cin * cin):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"bn_from_moments[{cout}x{cin}]", flops=2.0 * cout * cin * cin, bytes=8.0 * cin * cin):
         rc = _cabi.lib().r3d_bn_from_moments(
             _cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0), float(count),
             _cabi.ptr(bn.weight.detach()), _cabi.ptr(bn.bias.detach()),
@@ -346,7 +355,7 @@ def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments
     scal = torch.empty((2, cout), dtype=torch.float64, device=dev)
     dm = torch.empty((cin, cin), dtype=torch.float64, device=dev) if need_moments else None
     ds = torch.empty(cin, dtype=torch.float64, device=dev) if need_moments else None
-    with torch.cuda.device(dev), _cabi.kernel_timer("bn_from_moments_bwd", flops=4.0 * cout * cin * cin,
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"bn_from_moments_bwd[{cout}x{cin}]", flops=4.0 * cout * cin * cin,
                                                     bytes=8.0 * cin * cin):
         rc = _cabi.lib().r3d_bn_from_moments_bwd(
             _cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0), float(count),

@@ -466,8 +466,8 @@ def main():
         L.r3d_knn_set_algorithm(prev)
         for kn, kv in brute.items():
             kv["ms_total"] = kv["ms_avg"] * n_eager * 1.0      # comparable with the per-step table below
-            tab["brute_force_" + kn] = kv
-        grid_name = next(kn for kn in tab if not kn.startswith("brute_force_"))
+            tab["forced_" + kn] = kv
+        grid_name = next(kn for kn in tab if kn.startswith("knn_grid"))
         extras["default_search"] = "uniform grid (r3d_knn algorithm 0/2)"
         extras["brute_force_queries_per_sec"] = units_per_step / (next(iter(brute.values()))["ms_avg"] * 1e-3)
         extras["grid_ms_per_launch"] = tab[grid_name]["ms_avg"]

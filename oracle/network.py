@@ -304,7 +304,10 @@ def grad_parity(got: "Dict[str, torch.Tensor]", ref: "Dict[str, torch.Tensor]", 
     scale = max(float(g.abs().max()) for g in ref.values())
     worst, worst_name = 0.0, ""
     for name, g in ref.items():
-        diff = (got[name].detach().cpu().float().reshape(-1) - g.reshape(-1)).abs()
+        mine = got[name]
+        if mine is None:              # "no gradient" stands for an exactly zero gradient
+            mine = torch.zeros_like(g)
+        diff = (mine.detach().cpu().float().reshape(-1) - g.reshape(-1)).abs()
         cancelled = name == "fc_start.bias" or (          # fc_start feeds bn_start (modules.py:565-566)
             name.endswith(".conv.bias") and (name[:-len("conv.bias")] + "batch_norm.weight") in ref)
         denom = scale if cancelled else max(float(g.abs().max()), 1e-30)
@@ -321,6 +324,8 @@ def grad_parity(got: "Dict[str, torch.Tensor]", ref: "Dict[str, torch.Tensor]", 
 def grad_fixture_view(g: torch.Tensor, limit: int = 1024) -> torch.Tensor:
     """Golden fixtures keep gradients whole up to ``limit`` elements and a strided sample of the
     flattened tensor beyond that (keeps tests/golden small); tests view both sides through this."""
+    if g is None:
+        return None
     flat = g.detach().reshape(-1)
     if flat.numel() <= limit:
         return flat
