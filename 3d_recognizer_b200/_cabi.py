@@ -40,6 +40,11 @@ SIGNATURES = {
     "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
                          [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_tile_points": (c_int, [c_int, c_int]),
+    "r3d_lfa_pool2_bwd_train": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
+                                [c_void_p] * 9 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 3 +
+                                [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_bn2_bwd": (c_int, [c_void_p, ctypes.c_longlong] + [c_void_p] * 10 + [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_moments": (c_int, [c_int, c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
                         [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_bn_from_moments": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
@@ -53,6 +58,7 @@ SIGNATURES = {
     "r3d_pointwise_stats": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_void_p,
                                     ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float,
                                     c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "r3d_pointwise_set_tensor_cores": (c_int, [c_int]),
     "r3d_bn_apply": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float,
                              ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p,
                              c_void_p]),

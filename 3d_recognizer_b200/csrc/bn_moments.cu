@@ -68,21 +68,21 @@ __global__ void __launch_bounds__(kBnmThreads) bnm_fwd_kernel(
 // scal (2, cout) doubles: gq, gwmu
 __global__ void __launch_bounds__(kBnmThreads) bnm_bwd_kernel(
     const float* __restrict__ W, int cin, const double* __restrict__ S, int s_stride, const double* __restrict__ M,
-    int ldm, double R, const float* __restrict__ gamma, const double* __restrict__ save, const float* __restrict__ ga,
-    const float* __restrict__ gc, float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    int ldm, double R, const float* __restrict__ gamma, const double* __restrict__ save, const double* __restrict__ ga,
+    const double* __restrict__ gc, double* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta,
     double* __restrict__ scal, int cout) {
     const int j = blockIdx.x, i = threadIdx.x;
     const float* w = W + (size_t)j * cin;
     const double wmu = save[j], rstd = save[2 * cout + j], a = save[3 * cout + j];
-    const double gc_j = (double)gc[j];
-    const double ga1 = (double)ga[j] - gc_j * wmu;                 // total gradient at a_j
+    const double gc_j = gc[j];
+    const double ga1 = ga[j] - gc_j * wmu;                 // total gradient at a_j
     const double gvar = ga1 * (double)gamma[j] * (-0.5) * rstd * rstd * rstd;
     const double gq = gvar / R;
     const double gwmu = -gc_j * a - 2.0 * wmu * gvar;
     if (i < cin) {
         double t = 0.0;
         for (int k = 0; k < cin; ++k) t += (M[(size_t)i * ldm + k] + M[(size_t)k * ldm + i]) * (double)w[k];
-        dW[(size_t)j * cin + i] = (float)(gq * t + gwmu * S[(size_t)i * s_stride] / R);
+        dW[(size_t)j * cin + i] = gq * t + gwmu * S[(size_t)i * s_stride] / R;
     }
     if (i == 0) {
         dgamma[j] = (float)(ga1 * rstd);
@@ -129,7 +129,7 @@ extern "C" int r3d_bn_from_moments(const float* W, int cout, int cin, const doub
 
 extern "C" int r3d_bn_from_moments_bwd(const float* W, int cout, int cin, const double* S, int s_stride,
                                        const double* M, int ldm, double R, const float* gamma, const double* save,
-                                       const float* ga, const float* gc, float* dW, float* dgamma, float* dbeta,
+                                       const double* ga, const double* gc, double* dW, float* dgamma, float* dbeta,
                                        double* scal, double* dM, double* dS, r3d_stream_t stream) {
     if (cout <= 0 || cin <= 0 || !(R > 0.0)) return R3D_EINVAL;
     if (cin > kBnmMaxCin) return R3D_EUNSUPPORTED;

@@ -44,9 +44,13 @@ struct LfaBwdArgs {
     float* dfeat;             // (B,N,h)   += (pre-zeroed by the caller)
     long long dfeat_bstride;
     float* dw_score;          // (d,d) [out][in] +=
-    float* g1;                // (h,16): [:, :10] += du1^T rpe, [:,10] += sum du1
-    float* g2m;               // (h,h)  += du2^T r1        (stage 2)
-    float* g2c;               // (h,16): [:,10] += sum du2 (stage 2)
+    double* g1;               // (h,16): [:, :10] += du1^T rpe, [:,10] += sum du1   (fp64: these sums cancel against the
+    double* g2m;              // (h,h)  += du2^T r1        (stage 2)               BatchNorm mean/variance terms)
+    double* g2c;              // (h,16): [:,10] += sum du2 (stage 2)
+    // train-mode stage 2 (batch-statistics BatchNorm behind mlp_rpe2): instead of going on to r1, the kernel
+    // hands du2 to the two-pass BatchNorm backward (lfa_moments_kernel MODE 3)
+    float* du2_tiles;         // nullable; [b][tile][h][PTS*K] du2 of every tile
+    double* sum_du2;          // (2,h): += sum du2, += sum du2 * r2
     int B, N;
 };
 
@@ -226,16 +230,44 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
         }
     }
     // ------------------------------------------------------------------ encoding half: du = dX * [r > 0], in place over r
+    float pr2[4] = {0.f, 0.f, 0.f, 0.f}, ps2[4] = {0.f, 0.f, 0.f, 0.f};   // per-thread sum du2 * r2, sum du2
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float* xc = X + (size_t)(g * 4 + j) * RP + row0;
 #pragma unroll
-        for (int r = 0; r < RT; ++r) xc[r] = (xc[r] > 0.f) ? acc[r][j] : 0.f;
+        for (int r = 0; r < RT; ++r) {
+            const float rv = xc[r];
+            const float du = (rv > 0.f) ? acc[r][j] : 0.f;
+            pr2[j] = fmaf(du, rv, pr2[j]);
+            ps2[j] += du;
+            xc[r] = du;
+        }
     }
     __syncthreads();
 
+    if (STAGE == 2 && a.du2_tiles) {
+        // ---- train mode: du2 tile -> global (coalesced, channel-major as in shared memory), BatchNorm sums
+        float* red = gp;                                   // [2][H] scratch (the dpooled tile is no longer needed)
+        for (int i = tid; i < 2 * H; i += NT) red[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&red[g * 4 + j], ps2[j]);
+            atomicAdd(&red[H + g * 4 + j], pr2[j]);
+        }
+        float* tile = a.du2_tiles + ((size_t)b * gridDim.x + blockIdx.x) * H * C::ROWS;
+        for (int i = tid; i < H * C::ROWS / 4; i += NT) {
+            const int c = i / (C::ROWS / 4), q = i % (C::ROWS / 4);
+            const int p = (q * 4) / K, k = (q * 4) % K;
+            reinterpret_cast<float4*>(tile)[i] = *reinterpret_cast<const float4*>(X + (size_t)c * RP + p * C::PSTRIDE + k);
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * H; i += NT) atomicAdd(a.sum_du2 + i, (double)red[i]);
+        return;
+    }
+
     if (STAGE == 1) {
-        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(X, RPE, RP, a.g1, kRpeRows, 11, tid);
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(X, RPE, RP, a.g1, kRpeRows, 11, tid);
         return;
     }
 
@@ -251,8 +283,8 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
         for (int ch = c_lo; ch < c_hi; ++ch) G[(size_t)ch * RP + off] = rpe_mlp1(Pw1, Pa1, Pb1, ch, rpe);
     }
     __syncthreads();
-    reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, float>(X, G, RP, a.g2m, H, H, tid);
-    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(X, RPE, RP, a.g2c, kRpeRows, 11, tid);
+    reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, double>(X, G, RP, a.g2m, H, H, tid);
+    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(X, RPE, RP, a.g2c, kRpeRows, 11, tid);
     {
         float acc2[RT][4];
 #pragma unroll
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
         }
     }
     __syncthreads();
-    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(G, RPE, RP, a.g1, kRpeRows, 11, tid);
+    reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(G, RPE, RP, a.g1, kRpeRows, 11, tid);
 }
 
 // ---------------------------------------------------------------------------------------- moments
@@ -285,7 +317,13 @@ struct LfaMomArgs {
     double* s_r1;       // (h,16): [:,10] += sum r1                                               MODE 1
     const float* gsym;  // (h,h) G + G^T, [c][j] (symmetric)                                      MODE 2 (backward)
     const float* gsum;  // (h)   d loss / d sum r1                                                MODE 2
-    float* g1;          // (h,16) += du1^T [rpe, 1]                                               MODE 2
+    double* g1;         // (h,16) += du1^T [rpe, 1]                                               MODE 2, 3
+    // MODE 3: two-pass BatchNorm backward of mlp_rpe2 (batch statistics)
+    const float* du2_tiles;   // [b][tile][h][PTS*K] from lfa_pool_bwd_kernel
+    const float* w_rpe2T;     // (h,h) [in][out]
+    const float* w_rpe2;      // (h,h) [out][in]
+    const float* bn2;         // (5,h): a2, mean2 (of W2 r1), rstd2, m1 = mean(du2), m2 = mean(du2 * zhat2)
+    double* dw2;              // (h,h) [out][in] += dz2^T r1
     int B, N;
 };
 
@@ -297,6 +335,11 @@ struct LfaMomSmem {
 };
 
 // MODE 0: rpe moments.  MODE 1: r1 moments.  MODE 2: backward of the r1 moments.
+// MODE 3: BatchNorm backward of mlp_rpe2 in the standard two-pass form: with the batch sums of pass 1 (m1, m2),
+//         z2 = W2 r1, dz2 = a2 (du2 - m1 - zhat2 m2), dW2 += dz2^T r1, dr1 = dz2 W2, du1 = dr1 * [r1 > 0],
+//         G1 += du1^T [rpe, 1].  Mean and variance terms are subtracted PER ROW before any row sum is taken: going
+//         through the moments instead (MODE 2) subtracts two row sums that cancel to ~1/sqrt(rows) of their size and
+//         lost 3-4 digits at 65 k rows.
 template <int D, int K, int NT, int MODE>
 __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
     using C = LfaBwdCfg<D, K, NT>;
@@ -316,7 +359,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * C::PTS;
-    if (MODE == 2 && tid == 0) {
+    if (MODE >= 2 && tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
@@ -356,6 +399,54 @@ __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
     } else if (MODE == 1) {
         reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, double>(R1, R1, RP, a.m_r1, H, H, tid);
         reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(R1, RPE, RP, a.s_r1, kRpeRows, 11, tid);
+    } else if (MODE == 3) {
+        const int rh = tid % C::RH;
+        const int g = (tid / C::RH) % C::CG;
+        const int p = tid / C::TPP;
+        const int row0 = p * C::PSTRIDE + rh * RT;
+        WPipe pipe{ring, bars, 0u, C::WSTAGE};
+        // du2 tile -> DU (padding floats of the shared-memory rows are never read)
+        const float* tile = a.du2_tiles + ((size_t)b * gridDim.x + blockIdx.x) * H * C::ROWS;
+        for (int i = tid; i < H * C::ROWS / 4; i += NT) {
+            const int c = i / (C::ROWS / 4), q = i % (C::ROWS / 4);
+            const int pp = (q * 4) / K, k = (q * 4) % K;
+            *reinterpret_cast<float4*>(DU + (size_t)c * RP + pp * C::PSTRIDE + k) = reinterpret_cast<const float4*>(tile)[i];
+        }
+        float acc2[RT][4];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
+        gemm_stream<1, NT, RT>(acc2, R1, RP, row0, H, a.w_rpe2T, H, 0, g, pipe, tid);   // z2 = W2 r1 (barrier inside)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = g * 4 + j;
+            const float a2 = a.bn2[col], mean2 = a.bn2[H + col], rstd2 = a.bn2[2 * H + col];
+            const float m1 = a.bn2[3 * H + col], m2 = a.bn2[4 * H + col];
+            float* dc = DU + (size_t)col * RP + row0;
+            const float* valid = RPE + 10 * RP + row0;      // the ones channel: 0 on padding points
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const float zh = (acc2[r][j] - mean2) * rstd2;
+                dc[r] = valid[r] * (a2 * (dc[r] - m1 - zh * m2));
+            }
+        }
+        __syncthreads();
+        reduce_gemm<H, H, NT, C::PTS, K, C::PSTRIDE, double>(DU, R1, RP, a.dw2, H, H, tid);
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[r][j] = 0.f;
+        gemm_stream<1, NT, RT>(acc2, DU, RP, row0, H, a.w_rpe2, H, 0, g, pipe, tid);    // dr1 = dz2 W2
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* rc = R1 + (size_t)(g * 4 + j) * RP + row0;
+            float* dc = DU + (size_t)(g * 4 + j) * RP + row0;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) dc[r] = (rc[r] > 0.f) ? acc2[r][j] : 0.f;
+        }
+        __syncthreads();
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(DU, RPE, RP, a.g1, kRpeRows, 11, tid);
     } else {
         const int rh = tid % C::RH;
         const int g = (tid / C::RH) % C::CG;
@@ -378,7 +469,7 @@ __global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
             for (int r = 0; r < RT; ++r) dc[r] = (rc[r] > 0.f) ? acc2[r][j] : 0.f;   // padding rows: r1 == 0
         }
         __syncthreads();
-        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, float>(DU, RPE, RP, a.g1, kRpeRows, 11, tid);
+        reduce_gemm<H, kRpeRows, NT, C::PTS, K, C::PSTRIDE, double>(DU, RPE, RP, a.g1, kRpeRows, 11, tid);
     }
 }
 
@@ -438,7 +529,7 @@ extern "C" int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstri
                                 const float* b_rpe1, const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2,
                                 const float* w_rpe2s, const float* w_scoreT, const float* w_score,
                                 const float* dpooled, float* dfeat, long long dfeat_bstride, float* dw_score,
-                                float* g1, float* g2m, float* g2c, int B, int N, int K, int d, r3d_stream_t stream) {
+                                double* g1, double* g2m, double* g2c, int B, int N, int K, int d, r3d_stream_t stream) {
     if (stage != 1 && stage != 2) return R3D_EINVAL;
     if (B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
     if (B == 0 || N == 0) return R3D_OK;
@@ -455,14 +546,68 @@ extern "C" int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstri
         (dfeat_bstride % 4) != 0)
         return R3D_EALIGN;
     LfaBwdArgs a{xyz, xyz_bstride, idx, feat, feat_bstride, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2,
-                 w_rpe2s, w_scoreT, w_score, dpooled, dfeat, dfeat_bstride, dw_score, g1, g2m, g2c, B, N};
+                 w_rpe2s, w_scoreT, w_score, dpooled, dfeat, dfeat_bstride, dw_score, g1, g2m, g2c, nullptr, nullptr,
+                 B, N};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return stage == 1 ? dispatch_bwd<1>(d, K, a, st) : dispatch_bwd<2>(d, K, a, st);
 }
 
+// points per CTA tile of the backward / moment kernels (layout of du2_tiles)
+template <int D, int K>
+static int tile_points() { return LfaBwdCfg<D, K, 128>::PTS; }
+
+extern "C" int r3d_lfa_tile_points(int K, int d) {
+#define R3D_CASE(DD, KK) \
+    if (d == DD && K == KK) return tile_points<DD, KK>();
+    R3D_CASE(16, 16) R3D_CASE(32, 16) R3D_CASE(64, 16) R3D_CASE(128, 16) R3D_CASE(256, 16)
+    R3D_CASE(16, 32) R3D_CASE(32, 32) R3D_CASE(64, 32) R3D_CASE(128, 32) R3D_CASE(256, 32)
+#undef R3D_CASE
+    return R3D_EUNSUPPORTED;
+}
+
+extern "C" int r3d_lfa_pool2_bwd_train(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                                       long long feat_bstride, const float* w_rpe1, const float* a_rpe1,
+                                       const float* b_rpe1, const float* w_rpe2T, const float* a_rpe2,
+                                       const float* b_rpe2, const float* w_scoreT, const float* w_score,
+                                       const float* dpooled, float* dfeat, long long dfeat_bstride, float* dw_score,
+                                       float* du2_tiles, double* sum_du2, int B, int N, int K, int d,
+                                       r3d_stream_t stream) {
+    if (B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
+    if (B == 0 || N == 0) return R3D_OK;
+    if (!xyz || !idx || !feat || !w_rpe1 || !a_rpe1 || !b_rpe1 || !w_rpe2T || !a_rpe2 || !b_rpe2 || !w_scoreT ||
+        !w_score || !dpooled || !dfeat || !dw_score || !du2_tiles || !sum_du2)
+        return R3D_EINVAL;
+    const int h = d / 2;
+    if (xyz_bstride == 0) xyz_bstride = (long long)N * 3;
+    if (feat_bstride == 0) feat_bstride = (long long)N * h;
+    if (dfeat_bstride == 0) dfeat_bstride = (long long)N * h;
+    if (!is_aligned(feat, 16) || !is_aligned(dfeat, 16) || !is_aligned(w_scoreT, 16) || !is_aligned(w_score, 16) ||
+        !is_aligned(w_rpe2T, 16) || !is_aligned(du2_tiles, 16) || (feat_bstride % 4) != 0 || (dfeat_bstride % 4) != 0)
+        return R3D_EALIGN;
+    LfaBwdArgs a{xyz, xyz_bstride, idx, feat, feat_bstride, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, nullptr,
+                 w_scoreT, w_score, dpooled, dfeat, dfeat_bstride, dw_score, nullptr, nullptr, nullptr, du2_tiles,
+                 sum_du2, B, N};
+    return dispatch_bwd<2>(d, K, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int r3d_lfa_bn2_bwd(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* w_rpe1,
+                               const float* a_rpe1, const float* b_rpe1, const float* du2_tiles, const float* w_rpe2T,
+                               const float* w_rpe2, const float* bn2, double* g1, double* dw2, int B, int N, int K,
+                               int d, r3d_stream_t stream) {
+    if (B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
+    if (B == 0 || N == 0) return R3D_OK;
+    if (!xyz || !idx || !w_rpe1 || !a_rpe1 || !b_rpe1 || !du2_tiles || !w_rpe2T || !w_rpe2 || !bn2 || !g1 || !dw2)
+        return R3D_EINVAL;
+    if (!is_aligned(du2_tiles, 16) || !is_aligned(w_rpe2T, 16) || !is_aligned(w_rpe2, 16)) return R3D_EALIGN;
+    if (xyz_bstride == 0) xyz_bstride = (long long)N * 3;
+    LfaMomArgs a{xyz, xyz_bstride, idx, w_rpe1, a_rpe1, b_rpe1, nullptr, nullptr, nullptr, nullptr, nullptr, g1,
+                 du2_tiles, w_rpe2T, w_rpe2, bn2, dw2, B, N};
+    return dispatch_mom<3>(d, K, a, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx,
                                const float* w_rpe1, const float* a_rpe1, const float* b_rpe1, double* m_rpe,
-                               double* m_r1, double* s_r1, const float* gsym, const float* gsum, float* g1, int B,
+                               double* m_r1, double* s_r1, const float* gsym, const float* gsum, double* g1, int B,
                                int N, int K, int d, r3d_stream_t stream) {
     if (mode < 0 || mode > 2 || B < 0 || N < 0 || K <= 0 || d <= 0) return R3D_EINVAL;
     if (B == 0 || N == 0) return R3D_OK;
@@ -472,7 +617,8 @@ extern "C" int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride
     if (mode == 1 && (!m_r1 || !s_r1)) return R3D_EINVAL;
     if (mode == 2 && (!gsym || !gsum || !g1 || !is_aligned(gsym, 16))) return R3D_EINVAL;
     if (xyz_bstride == 0) xyz_bstride = (long long)N * 3;
-    LfaMomArgs a{xyz, xyz_bstride, idx, w_rpe1, a_rpe1, b_rpe1, m_rpe, m_r1, s_r1, gsym, gsum, g1, B, N};
+    LfaMomArgs a{xyz, xyz_bstride, idx, w_rpe1, a_rpe1, b_rpe1, m_rpe, m_r1, s_r1, gsym, gsum, g1,
+                 nullptr, nullptr, nullptr, nullptr, nullptr, B, N};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == 0) return dispatch_mom<0>(d, K, a, st);
     if (mode == 1) return dispatch_mom<1>(d, K, a, st);

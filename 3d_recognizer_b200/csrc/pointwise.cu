@@ -19,47 +19,13 @@
 //                          transposed so both are read with LDS.128) for Cout >= 16;
 //   pw_small_kernel        one thread per row for Cout <= 16 (fc_start 3->8, last decoder stage,
 //                          class logits): HBM-bound streaming.
-#include "common.cuh"
+#include "pointwise_common.cuh"
+
+#include <atomic>
 
 namespace r3d {
 
-struct PwArgs {
-    const float* xa;
-    long long xa_bstride;
-    int ca;
-    const int32_t* gidx;       // nullable; row n of cloud b reads xa row gidx[b*gidx_bstride + n]
-    long long gidx_bstride;    // 0 => the same index vector for every cloud
-    const float* xb;           // nullable second source
-    long long xb_bstride;
-    int cb;
-    const float* wT;           // (ca+cb, cout)
-    const float* scale;        // nullable (cout)
-    const float* shift;        // nullable (cout)
-    int act;                   // 0 none, 1 relu, 2 leaky relu
-    float slope;
-    float* y;
-    long long y_bstride;
-    int y_ld;                  // floats between consecutive output rows (>= cout): lets a layer write a channel slice
-    int cout;
-    int B;
-    int n;                     // rows per cloud
-    int transpose_out;         // 1: write y as (B, cout, n) — the reference's logits layout (modules.py:611)
-    double* stats;             // nullable (2*cout): += per-channel sum and sum of squares of the written values
-    int w_out_in;              // 0: wT is (cin, cout);  1: the weight is stored (cout, cin) (conv / Linear layout)
-};
-
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-    if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : v * slope;
-    return v;
-}
-
-__device__ __forceinline__ const float* src_row(const PwArgs& a, int b, int n, bool second) {
-    if (second) return a.xb + (size_t)b * a.xb_bstride + (size_t)n * a.cb;
-    int r = n;
-    if (a.gidx) r = a.gidx[(size_t)b * a.gidx_bstride + n];
-    return a.xa + (size_t)b * a.xa_bstride + (size_t)r * a.ca;
-}
+static std::atomic<int> g_pw_tensor_cores{1};
 
 // ------------------------------------------------------------------------------------ GEMM kernel
 constexpr int kPwKC = 16;  // input channels per staged chunk
@@ -166,9 +132,11 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
     }
 
     // ---- epilogue
-    __shared__ float csum[2][TN];
+    // fp64 shared accumulators: the order of the atomics then only matters at 1e-16, so the batch statistics — and
+    // with them which side of a ReLU kink a borderline activation falls on — are reproducible from run to run
+    __shared__ double csum[2][TN];
     if (a.stats) {
-        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.f;
+        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.0;
         __syncthreads();
     }
 #pragma unroll
@@ -212,8 +180,8 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
         if (a.stats) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                atomicAdd(&csum[0][h * (TN / 2) + tc * 4 + j], s1[j]);
-                atomicAdd(&csum[1][h * (TN / 2) + tc * 4 + j], s2[j]);
+                atomicAdd(&csum[0][h * (TN / 2) + tc * 4 + j], (double)s1[j]);
+                atomicAdd(&csum[1][h * (TN / 2) + tc * 4 + j], (double)s2[j]);
             }
         }
     }
@@ -221,8 +189,8 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
         __syncthreads();
         for (int i = tid; i < TN; i += NT) {
             if (n0 + i < a.cout) {
-                atomicAdd(a.stats + n0 + i, (double)csum[0][i]);
-                atomicAdd(a.stats + a.cout + n0 + i, (double)csum[1][i]);
+                atomicAdd(a.stats + n0 + i, csum[0][i]);
+                atomicAdd(a.stats + a.cout + n0 + i, csum[1][i]);
             }
         }
     }
@@ -245,7 +213,7 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
     static_assert(A_PER >= 1 && W_PER >= 1 && (TM * (KC / 4)) % NT == 0 && (KC * TN / 4) % NT == 0, "tile/threads");
     __shared__ __align__(16) float As[2][KC][TMP];
     __shared__ __align__(16) float Ws[2][KC][TN];
-    __shared__ float csum[2][TN];
+    __shared__ double csum[2][TN];   // fp64: see pw_gemm_kernel
 
     const int tid = threadIdx.x;
     const int tr = tid / (TN / RT);
@@ -336,7 +304,7 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
         for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
 
     if (a.stats)
-        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.f;
+        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.0;
     load(0);
     store(0);
     __syncthreads();
@@ -414,8 +382,8 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
         if (a.stats) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                atomicAdd(&csum[0][lcol + j], s1[j]);
-                atomicAdd(&csum[1][lcol + j], s2[j]);
+                atomicAdd(&csum[0][lcol + j], (double)s1[j]);
+                atomicAdd(&csum[1][lcol + j], (double)s2[j]);
             }
         }
     }
@@ -423,8 +391,8 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
         __syncthreads();
         for (int i = tid; i < TN; i += NT) {
             if (n0 + i < a.cout) {
-                atomicAdd(a.stats + n0 + i, (double)csum[0][i]);
-                atomicAdd(a.stats + a.cout + n0 + i, (double)csum[1][i]);
+                atomicAdd(a.stats + n0 + i, csum[0][i]);
+                atomicAdd(a.stats + a.cout + n0 + i, csum[1][i]);
             }
         }
     }
@@ -437,8 +405,8 @@ constexpr int kPwSmallMaxW = 4096;  // floats of weights staged in smem (cin*cou
 
 __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
     __shared__ float Ws[kPwSmallMaxW];
-    __shared__ float cta_sum[2][kPwSmallMaxCout];
-    if (threadIdx.x < 2 * kPwSmallMaxCout) (&cta_sum[0][0])[threadIdx.x] = 0.f;
+    __shared__ double cta_sum[2][kPwSmallMaxCout];
+    if (threadIdx.x < 2 * kPwSmallMaxCout) (&cta_sum[0][0])[threadIdx.x] = 0.0;
     const int cin = a.ca + a.cb;
     for (int i = threadIdx.x; i < cin * a.cout; i += blockDim.x)
         Ws[i] = a.w_out_in ? a.wT[(size_t)(i % a.cout) * cin + i / a.cout] : a.wT[i];
@@ -515,16 +483,16 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
                 s2 += __shfl_xor_sync(0xffffffffu, s2, off);
             }
             if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&cta_sum[0][j], s1);
-                atomicAdd(&cta_sum[1][j], s2);
+                atomicAdd(&cta_sum[0][j], (double)s1);
+                atomicAdd(&cta_sum[1][j], (double)s2);
             }
         }
     }
     if (a.stats) {          // one global (fp64) atomic per channel and CTA, not per warp: the 2*cout addresses are hot
         __syncthreads();
         if (threadIdx.x < a.cout) {
-            atomicAdd(a.stats + threadIdx.x, (double)cta_sum[0][threadIdx.x]);
-            atomicAdd(a.stats + a.cout + threadIdx.x, (double)cta_sum[1][threadIdx.x]);
+            atomicAdd(a.stats + threadIdx.x, cta_sum[0][threadIdx.x]);
+            atomicAdd(a.stats + a.cout + threadIdx.x, cta_sum[1][threadIdx.x]);
         }
     }
     if (live && vec_out) {
@@ -581,6 +549,7 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
         return R3D_OK;
     }
     const bool aligned = (ca % 4 == 0) && (cb % 4 == 0);
+    if (g_pw_tensor_cores.load() && pw_tc_eligible(a)) return pw_tc_launch(a, st);
     if (!aligned) {
         dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
         pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
@@ -600,4 +569,11 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     }
     R3D_LAUNCH_CHECK("pw_gemm_kernel");
     return R3D_OK;
+}
+
+// 1 (default): wide layers (C_in >= 32, C_out a multiple of 32) run on the tcgen05 3xTF32 kernel; 0: FP32 CUDA-core
+// kernels everywhere.  Returns the previous value.
+extern "C" int r3d_pointwise_set_tensor_cores(int on) {
+    if (on != 0 && on != 1) return g_pw_tensor_cores.load();
+    return g_pw_tensor_cores.exchange(on);
 }

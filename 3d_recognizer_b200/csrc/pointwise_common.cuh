@@ -1,0 +1,50 @@
+// Argument block and row addressing shared by the per-point layer kernels (pointwise.cu: FP32 CUDA-core kernels,
+// pointwise_tc.cu: tcgen05 3xTF32 kernel).
+#pragma once
+#include "common.cuh"
+
+namespace r3d {
+
+struct PwArgs {
+    const float* xa;
+    long long xa_bstride;
+    int ca;
+    const int32_t* gidx;       // nullable; row n of cloud b reads xa row gidx[b*gidx_bstride + n]
+    long long gidx_bstride;    // 0 => the same index vector for every cloud
+    const float* xb;           // nullable second source
+    long long xb_bstride;
+    int cb;
+    const float* wT;           // (ca+cb, cout)
+    const float* scale;        // nullable (cout)
+    const float* shift;        // nullable (cout)
+    int act;                   // 0 none, 1 relu, 2 leaky relu
+    float slope;
+    float* y;
+    long long y_bstride;
+    int y_ld;                  // floats between consecutive output rows (>= cout): lets a layer write a channel slice
+    int cout;
+    int B;
+    int n;                     // rows per cloud
+    int transpose_out;         // 1: write y as (B, cout, n) — the reference's logits layout (modules.py:611)
+    double* stats;             // nullable (2*cout): += per-channel sum and sum of squares of the written values
+    int w_out_in;              // 0: wT is (cin, cout);  1: the weight is stored (cout, cin) (conv / Linear layout)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+
+__device__ __forceinline__ const float* src_row(const PwArgs& a, int b, int n, bool second) {
+    if (second) return a.xb + (size_t)b * a.xb_bstride + (size_t)n * a.cb;
+    int r = n;
+    if (a.gidx) r = a.gidx[(size_t)b * a.gidx_bstride + n];
+    return a.xa + (size_t)b * a.xa_bstride + (size_t)r * a.ca;
+}
+
+// pointwise_tc.cu: true if the tensor-core kernel can take this layer
+bool pw_tc_eligible(const PwArgs& a);
+int pw_tc_launch(const PwArgs& a, cudaStream_t st);
+
+}  // namespace r3d

@@ -40,18 +40,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
-    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+// Round-to-nearest TF32 (cvt.rna): hi = rn(x), lo = rn(x - hi).  Plain masking (truncation) leaves the tensor core to
+// truncate lo as well, and truncation errors all point towards zero: they add up linearly over K (measured 9e-6 at
+// K = 1024) instead of as a random walk.
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
-
-
+__device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
+    hi.x = rn_tf32(v.x);
+    hi.y = rn_tf32(v.y);
+    hi.z = rn_tf32(v.z);
+    hi.w = rn_tf32(v.w);
+    lo = make_float4(rn_tf32(v.x - hi.x), rn_tf32(v.y - hi.y), rn_tf32(v.z - hi.z), rn_tf32(v.w - hi.w));
+}
 __device__ __forceinline__ void split_tf32_1(float v, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    lo = v - hi;
+    hi = rn_tf32(v);
+    lo = rn_tf32(v - hi);
 }
 
 // one warp allocates `cols` (power of two >= 32) TMEM columns and publishes the base address in *slot (shared memory)

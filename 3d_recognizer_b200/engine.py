@@ -179,86 +179,126 @@ def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch
 # ------------------------------------------------------------- training path: fused LFA with autograd
 class _LfaPoolFn(torch.autograd.Function):
     """One fused LocSE + attentive-pooling launch (ops.lfa_pool) with its mirrored backward kernel
-    (ops.lfa_pool_bwd).  Differentiable inputs: feat, w1 (h,10), a1, c1 (h) [, w2 (h,h), a2, c2], ws (d,d);
-    a*/c* are the per-channel affine maps that BatchNorm (+ conv bias) reduces to."""
+    (ops.lfa_pool_bwd).  Differentiable inputs: feat, ws (d,d), and — as fp64 tensors — w1 (h,10), a1, c1 (h)
+    [, w2 (h,h), a2, c2]; a*/c* are the per-channel affine maps that BatchNorm (+ conv bias) reduces to.
+
+    Why fp64 edges.  The gradient of mlp_rpe1/2 is the sum of a direct term (a (.) sum du x^T, from here) and the
+    BatchNorm-statistics term (from _BnFromMomentsFn); with un-centred inputs (absolute coordinates) the two are
+    ~1e3 times larger than their sum.  Accumulating the sums in fp64 and letting autograd add the fp64 pieces keeps
+    the result at fp32 accuracy (measured at N=16384: 8e-4 relative in fp32, 3e-6 in fp64); the kernels themselves
+    run in fp32 on the float copies w1f, a1f, c1f [, w2f, a2f, c2f]."""
 
     @staticmethod
-    def forward(ctx, stage, xyz, idx32, feat, w1, a1, c1, w2, a2, c2, ws):
-        w1 = w1.contiguous()
-        w2T = w2.t().contiguous() if stage == 2 else None
+    def forward(ctx, stage, xyz, idx32, feat, ws, w1, a1, c1, w2, a2, c2, w1f, a1f, c1f, w2f, a2f, c2f):
+        w2T = w2f.t().contiguous() if stage == 2 else None
         wsT = ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
-            pooled = ops.lfa_pool_tc(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(),
-                                     w2.contiguous() if stage == 2 else None, a2.contiguous() if stage == 2 else None,
-                                     c2.contiguous() if stage == 2 else None, ws.contiguous())
+            pooled = ops.lfa_pool_tc(stage, xyz, idx32, feat, w1f, a1f, c1f, w2f if stage == 2 else None,
+                                     a2f if stage == 2 else None, c2f if stage == 2 else None, ws.contiguous())
         else:
-            pooled = ops.lfa_pool(stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
-                                  a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None,
-                                  wsT)
+            pooled = ops.lfa_pool(stage, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f if stage == 2 else None,
+                                  c2f if stage == 2 else None, wsT)
         ctx.stage = stage
-        ctx.save_for_backward(xyz, idx32, feat, w1, a1, c1, w2 if stage == 2 else None, a2 if stage == 2 else None,
-                              c2 if stage == 2 else None, ws, w2T, wsT)
+        ctx.save_for_backward(xyz, idx32, feat, ws, w1, a1, w2 if stage == 2 else None, a2 if stage == 2 else None,
+                              w1f, a1f, c1f, w2f if stage == 2 else None, a2f if stage == 2 else None,
+                              c2f if stage == 2 else None, w2T, wsT)
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
-        xyz, idx32, feat, w1, a1, c1, w2, a2, c2, ws, w2T, wsT = ctx.saved_tensors
+        xyz, idx32, feat, ws, w1, a1, w2, a2, w1f, a1f, c1f, w2f, a2f, c2f, w2T, wsT = ctx.saved_tensors
         stage = ctx.stage
-        w2s = (w2 * a2.unsqueeze(1)).contiguous() if stage == 2 else None
-        dfeat, dws, g1, g2m, g2c = ops.lfa_pool_bwd(
-            stage, xyz, idx32, feat, w1, a1.contiguous(), c1.contiguous(), w2T,
-            a2.contiguous() if stage == 2 else None, c2.contiguous() if stage == 2 else None, w2s, wsT,
-            ws.contiguous(), dpooled)
+        w2s = (w2f * a2f.unsqueeze(1)).contiguous() if stage == 2 else None
+        dfeat, dws, g1, g2m, g2c = ops.lfa_pool_bwd(stage, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, w2s, wsT,
+                                                    ws.contiguous(), dpooled)
         gm = g1[:, :10]
         dw1, da1, dc1 = a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
         dw2 = da2 = dc2 = None
         if stage == 2:
             dw2, da2, dc2 = a2.unsqueeze(1) * g2m, (w2 * g2m).sum(dim=1), g2c[:, 10]
-        return None, None, None, dfeat, dw1, da1, dc1, dw2, da2, dc2, dws
+        return (None, None, None, dfeat, dws, dw1, da1, dc1, dw2, da2, dc2) + (None,) * 6
+
+
+class _LfaPool2TrainFn(torch.autograd.Function):
+    """Stage 2 of an LFA block in TRAINING mode: r2 = relu(BN_batch(W2 r1)), PFA gather of p1, attentive pooling.
+    Forward = the same fused kernel as _LfaPoolFn; backward = the standard two BatchNorm passes
+    (ops.lfa_pool2_bwd_train: everything down to du2 and the batch sums; ops.lfa_bn2_bwd: dz2, dW2, dr1, du1, G1).
+    Differentiable inputs: feat (= p1), ws, gamma2, beta2, w2 (fp32 parameters) and the fp64 edges w1, a1, c1 of
+    mlp_rpe1 (see _LfaPoolFn).  a2f/c2f/mean2/rstd2 are this step's batch statistics (constants here: their
+    dependence on w2 and r1 IS the BatchNorm backward that pass 2 carries out)."""
+
+    @staticmethod
+    def forward(ctx, xyz, idx32, feat, ws, w2, gamma2, beta2, w1, a1, c1, w1f, a1f, c1f, a2f, c2f, mean2, rstd2):
+        w2f = w2.detach().contiguous()
+        w2T = w2f.t().contiguous()
+        wsT = ws.t().contiguous()
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+            pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f, a2f, c2f, ws.contiguous())
+        else:
+            pooled = ops.lfa_pool(2, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT)
+        ctx.save_for_backward(xyz, idx32, feat, ws, w1, a1, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, mean2, rstd2)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        xyz, idx32, feat, ws, w1, a1, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, mean2, rstd2 = ctx.saved_tensors
+        h = w1f.shape[0]
+        dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,
+                                                        ws.contiguous(), dpooled)
+        rows = float(idx32.numel())
+        s_du, s_dur = sums[0], sums[1]
+        a2, c2, mu2, rs2 = a2f.double(), c2f.double(), mean2.double(), rstd2.double()
+        # sum du2 * zhat2 with zhat2 = (z2 - mean2) rstd2 and z2 = (r2 - c2) / a2 wherever du2 != 0
+        safe_a2 = torch.where(a2 == 0, torch.ones_like(a2), a2)
+        s_duz = torch.where(a2 == 0, torch.zeros_like(a2), rs2 * ((s_dur - c2 * s_du) / safe_a2 - mu2 * s_du))
+        bn2 = torch.stack((a2, mu2, rs2, s_du / rows, s_duz / rows)).float().contiguous()
+        g1, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h)
+        gm = g1[:, :10]
+        dw1, da1, dc1 = a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
+        return (None, None, dfeat, dws, dw2.float(), s_duz.float(), s_du.float(), dw1, da1, dc1) + (None,) * 7
 
 
 class _R1MomentsFn(torch.autograd.Function):
     """(sum r1 (h), sum r1 r1^T (h,h)) in fp64 over all (point, neighbour) rows, r1 = relu(a1 (W1 rpe) + c1):
-    the statistics mlp_rpe2's train-mode BatchNorm needs."""
+    the statistics mlp_rpe2's train-mode BatchNorm needs.  w1, a1, c1: fp64 autograd edges, w1f.. their fp32 copies."""
 
     @staticmethod
-    def forward(ctx, xyz, idx32, w1, a1, c1):
-        w1, a1, c1 = w1.contiguous(), a1.contiguous(), c1.contiguous()
-        m_r1, s_r1 = ops.lfa_moments(1, xyz, idx32, 2 * w1.shape[0], w1, a1, c1)
-        ctx.save_for_backward(xyz, idx32, w1, a1, c1)
+    def forward(ctx, xyz, idx32, w1, a1, c1, w1f, a1f, c1f):
+        m_r1, s_r1 = ops.lfa_moments(1, xyz, idx32, 2 * w1f.shape[0], w1f, a1f, c1f)
+        ctx.save_for_backward(xyz, idx32, w1, a1, w1f, a1f, c1f)
         return s_r1[:, 10].clone(), m_r1
 
     @staticmethod
     def backward(ctx, g_sum, g_m):
-        xyz, idx32, w1, a1, c1 = ctx.saved_tensors
+        xyz, idx32, w1, a1, w1f, a1f, c1f = ctx.saved_tensors
         gsym = (g_m + g_m.t()).float().contiguous()
-        g1 = ops.lfa_moments(2, xyz, idx32, 2 * w1.shape[0], w1, a1, c1, gsym=gsym, gsum=g_sum.float().contiguous())
+        g1 = ops.lfa_moments(2, xyz, idx32, 2 * w1f.shape[0], w1f, a1f, c1f, gsym=gsym,
+                             gsum=g_sum.float().contiguous())
         gm = g1[:, :10]
-        return None, None, a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
+        return None, None, a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10], None, None, None
 
 
 class _BnFromMomentsFn(torch.autograd.Function):
     """Train-mode BatchNorm of y = W x + b expressed through the input moments (sums s, second-moment sums m over
     ``count`` rows, fp64): mean_y = W mu + b, var_y = diag(W Cov W^T) (biased, as BatchNorm normalises;
-    modules.py:86-90).  Returns the per-channel affine (a, c) with bn(y) = a (W x) + c and updates the running
-    statistics like BatchNorm2d (momentum 0.99, unbiased running variance).  One small kernel forward, one or
-    two backward (ops.bn_from_moments*)."""
+    modules.py:86-90).  Returns the per-channel affine (a, c) with bn(y) = a (W x) + c as fp64 tensors (see
+    _LfaPoolFn) and updates the running statistics like BatchNorm2d (momentum 0.99, unbiased running variance).
+    ``w`` is the fp64 autograd edge of the conv weight, ``wf`` its fp32 values.  One small kernel forward, one or two
+    backward (ops.bn_from_moments*)."""
 
     @staticmethod
-    def forward(ctx, w, bias, gamma, beta, s, m, bn, count):
-        w = w.contiguous()
-        a, c, save = ops.bn_from_moments(w, s, m, count, bn, bias)
+    def forward(ctx, w, wf, gamma, beta, s, m, bn, bias, count):
+        a, c, save = ops.bn_from_moments(wf, s, m, count, bn, bias)
         ctx.count = count
-        ctx.save_for_backward(w, gamma, s, m, save)
-        return a, c
+        ctx.save_for_backward(wf, gamma, s, m, save)
+        return a.double(), c.double()
 
     @staticmethod
     def backward(ctx, ga, gc):
-        w, gamma, s, m, save = ctx.saved_tensors
+        wf, gamma, s, m, save = ctx.saved_tensors
         need = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
-        dw, dgamma, dbeta, dm, ds = ops.bn_from_moments_bwd(w, s, m, ctx.count, gamma.contiguous(), save, ga, gc, need)
-        # the conv bias cancels against the batch mean: exactly zero gradient, reported as None
-        return dw, None, dgamma, dbeta, ds, dm, None, None
+        dw, dgamma, dbeta, dm, ds = ops.bn_from_moments_bwd(wf, s, m, ctx.count, gamma.contiguous(), save, ga, gc, need)
+        return dw, None, dgamma, dbeta, ds, dm, None, None, None
 
 
 def _eval_affine(smlp):
@@ -274,29 +314,39 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     K = lfa._n_neighbors
     idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
     f = shared_mlp(lfa.mlp1, feat)
-    w1 = lfa.mlp_rpe1.conv.weight.view(-1, 10)
-    w2 = lfa.mlp_rpe2.conv.weight.view(w1.shape[0], w1.shape[0])
-    d = 2 * w1.shape[0]
-    training = lfa.mlp_rpe1.batch_norm.training
+    r1m, r2m = lfa.mlp_rpe1, lfa.mlp_rpe2
+    w1f = r1m.conv.weight.detach().view(-1, 10)
+    h = w1f.shape[0]
+    w2f = r2m.conv.weight.detach().view(h, h)
+    w1 = r1m.conv.weight.view(h, 10).double()        # fp64 autograd edges (see _LfaPoolFn)
+    w2 = r2m.conv.weight.view(h, h).double()
+    d = 2 * h
+    training = r1m.batch_norm.training
     if training:
         m = ops.lfa_moments(0, xyz, idx, d)                      # (16,16) fp64, no parameters involved
         count = float(xyz.shape[0] * xyz.shape[1] * K)
-        r1m = lfa.mlp_rpe1
-        a1, c1 = _BnFromMomentsFn.apply(w1, r1m.conv.bias, r1m.batch_norm.weight, r1m.batch_norm.bias, m[10], m,
-                                        r1m.batch_norm, count)
+        a1, c1 = _BnFromMomentsFn.apply(w1, w1f, r1m.batch_norm.weight, r1m.batch_norm.bias, m[10], m,
+                                        r1m.batch_norm, r1m.conv.bias, count)
     else:
-        a1, c1 = _eval_affine(lfa.mlp_rpe1)
+        a1, c1 = (t.double() for t in _eval_affine(r1m))
+    a1f, c1f = a1.detach().float(), c1.detach().float()
     ws1, ws2 = lfa.pool1.score_fn[0].weight, lfa.pool2.score_fn[0].weight
-    pooled1 = _LfaPoolFn.apply(1, xyz, idx, f, w1, a1, c1, None, None, None, ws1)
+    pooled1 = _LfaPoolFn.apply(1, xyz, idx, f, ws1, w1, a1, c1, None, None, None, w1f, a1f, c1f, None, None, None)
     p1 = shared_mlp(lfa.pool1.mlp, pooled1)
     if training:
-        s_r1, m_r1 = _R1MomentsFn.apply(xyz, idx, w1, a1, c1)
-        r2m = lfa.mlp_rpe2
-        a2, c2 = _BnFromMomentsFn.apply(w2, r2m.conv.bias, r2m.batch_norm.weight, r2m.batch_norm.bias, s_r1, m_r1,
-                                        r2m.batch_norm, count)
+        # batch statistics of mlp_rpe2 from the moments of r1 (forward only; the backward is the explicit two-pass
+        # BatchNorm backward inside _LfaPool2TrainFn)
+        with torch.no_grad():
+            m_r1, s_r1 = ops.lfa_moments(1, xyz, idx, d, w1f, a1f, c1f)
+            a2f, c2f, save2 = ops.bn_from_moments(w2f.contiguous(), s_r1[:, 10].contiguous(), m_r1, count,
+                                                  r2m.batch_norm, r2m.conv.bias)
+        pooled2 = _LfaPool2TrainFn.apply(xyz, idx, p1, ws2, r2m.conv.weight.view(h, h), r2m.batch_norm.weight,
+                                         r2m.batch_norm.bias, w1, a1, c1, w1f, a1f, c1f, a2f, c2f,
+                                         save2[0].float(), save2[2].float())
     else:
-        a2, c2 = _eval_affine(lfa.mlp_rpe2)
-    pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, w1, a1, c1, w2, a2, c2, ws2)
+        a2, c2 = (t.double() for t in _eval_affine(r2m))
+        a2f, c2f = a2.detach().float(), c2.detach().float()
+        pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, ws2, w1, a1, c1, w2, a2, c2, w1f, a1f, c1f, w2f, a2f, c2f)
     p2 = shared_mlp(lfa.pool2.mlp, pooled2)
     return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
 

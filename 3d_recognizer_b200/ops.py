@@ -263,7 +263,7 @@ def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_rpe2s, w_scoreT,
                  w_score, dpooled):
     """Backward of ``lfa_pool`` (C ABI ``r3d_lfa_pool_bwd``).  Returns (dfeat (B,N,h), dw_score (d,d)
-    [out][in], g1 (h,16), g2m (h,h) | None, g2c (h,16) | None) — see include/r3d_b200.h."""
+    [out][in], g1 (h,16) fp64, g2m (h,h) fp64 | None, g2c (h,16) fp64 | None) — see include/r3d_b200.h."""
     xyz, xs = _cloud_view(xyz)
     feat, fs = _rows_view(feat.detach())
     B, N, K = idx32.shape
@@ -271,17 +271,18 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
     d = 2 * h
     dev = xyz.device
     dpooled = dpooled.contiguous()
-    # one zero-filled block for the feature gradient and all small accumulators
+    # one zero-filled fp32 block for the feature gradient and the score-weight gradient, one fp64 block for the
+    # encoding-MLP accumulators (they cancel against the BatchNorm moment terms and need the extra digits)
     n_df = B * N * h
-    acc = torch.zeros(n_df + d * d + h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float32, device=dev)
+    acc = torch.zeros(n_df + d * d, dtype=torch.float32, device=dev)
     dfeat = acc[:n_df].view(B, N, h)
-    dws = acc[n_df:n_df + d * d].view(d, d)
-    g1 = acc[n_df + d * d:n_df + d * d + h * 16].view(h, 16)
+    dws = acc[n_df:].view(d, d)
+    acc64 = torch.zeros(h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float64, device=dev)
+    g1 = acc64[:h * 16].view(h, 16)
     g2m = g2c = None
     if stage == 2:
-        o = n_df + d * d + h * 16
-        g2m = acc[o:o + h * h].view(h, h)
-        g2c = acc[o + h * h:].view(h, 16)
+        g2m = acc64[h * 16:h * 16 + h * h].view(h, h)
+        g2c = acc64[h * 16 + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -296,7 +297,7 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
 
 def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=None, gsym=None, gsum=None):
     """BatchNorm moments of the fused LocSE (C ABI ``r3d_lfa_moments``).
-    mode 0 -> m_rpe (16,16) float64; mode 1 -> (m_r1 (h,h), s_r1 (h,16)) float64; mode 2 -> g1 (h,16) float32."""
+    mode 0 -> m_rpe (16,16) float64; mode 1 -> (m_r1 (h,h), s_r1 (h,16)) float64; mode 2 -> g1 (h,16) float64."""
     xyz, xs = _cloud_view(xyz)
     B, N, K = idx32.shape
     h = d // 2
@@ -308,7 +309,7 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
         buf = torch.zeros(h * h + h * 16, dtype=torch.float64, device=dev)
         m_r1, s_r1 = buf[:h * h].view(h, h), buf[h * h:].view(h, 16)
     else:
-        g1 = torch.zeros((h, 16), dtype=torch.float32, device=dev)
+        g1 = torch.zeros((h, 16), dtype=torch.float64, device=dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -347,10 +348,10 @@ def bn_from_moments(w: torch.Tensor, s: torch.Tensor, m: torch.Tensor, count: fl
 
 
 def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments: bool):
-    """Backward of ``bn_from_moments``.  Returns (dW, dgamma, dbeta, dM | None, dS | None)."""
+    """Backward of ``bn_from_moments``: ga, gc fp64 -> (dW fp64, dgamma, dbeta, dM | None, dS | None)."""
     cout, cin = w.shape
     dev = w.device
-    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+    dw = torch.empty((cout, cin), dtype=torch.float64, device=dev)
     dgb = torch.empty((2, cout), dtype=torch.float32, device=dev)
     scal = torch.empty((2, cout), dtype=torch.float64, device=dev)
     dm = torch.empty((cin, cin), dtype=torch.float64, device=dev) if need_moments else None
@@ -359,7 +360,59 @@ def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments
                                                     bytes=8.0 * cin * cin):
         rc = _cabi.lib().r3d_bn_from_moments_bwd(
             _cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0), float(count),
-            _cabi.ptr(gamma), _cabi.ptr(save), _cabi.ptr(ga.contiguous()), _cabi.ptr(gc.contiguous()), _cabi.ptr(dw),
+            _cabi.ptr(gamma), _cabi.ptr(save), _cabi.ptr(ga.double().contiguous()), _cabi.ptr(gc.double().contiguous()),
+            _cabi.ptr(dw),
             _cabi.raw(dgb[0]), _cabi.raw(dgb[1]), _cabi.ptr(scal), _cabi.ptr(dm), _cabi.ptr(ds), _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_bn_from_moments_bwd")
     return dw, dgb[0], dgb[1], dm, ds
+
+
+def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT, w_score, dpooled):
+    """Pass 1 of the train-mode stage-2 backward (C ABI ``r3d_lfa_pool2_bwd_train``).
+    Returns (dfeat (B,N,h), dw_score (d,d), du2_tiles, sum_du2 (2,h) fp64)."""
+    xyz, xs = _cloud_view(xyz)
+    feat, fs = _rows_view(feat.detach())
+    B, N, K = idx32.shape
+    h = feat.shape[2]
+    d = 2 * h
+    dev = xyz.device
+    L = _cabi.lib()
+    pts = L.r3d_lfa_tile_points(K, d)
+    if pts <= 0:
+        raise ValueError(f"r3d_lfa_tile_points: unsupported shape d={d}, K={K}")
+    tiles = -(-N // pts)
+    dpooled = dpooled.contiguous()
+    n_df = B * N * h
+    acc = torch.zeros(n_df + d * d, dtype=torch.float32, device=dev)
+    dfeat, dws = acc[:n_df].view(B, N, h), acc[n_df:].view(d, d)
+    du2 = torch.empty(B * tiles * h * pts * K, dtype=torch.float32, device=dev)
+    sums = torch.zeros((2, h), dtype=torch.float64, device=dev)
+    flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + h * h))
+    nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 8 * K * h)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool2_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
+        rc = L.r3d_lfa_pool2_bwd_train(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1),
+                                       _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2T), _cabi.ptr(a_rpe2),
+                                       _cabi.ptr(b_rpe2), _cabi.ptr(w_scoreT), _cabi.ptr(w_score), _cabi.ptr(dpooled),
+                                       _cabi.raw(dfeat), 0, _cabi.raw(dws), _cabi.ptr(du2), _cabi.ptr(sums), B, N, K, d,
+                                       _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_pool2_bwd_train")
+    return dfeat, dws, du2, sums
+
+
+def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, bn2, h: int):
+    """Pass 2 (C ABI ``r3d_lfa_bn2_bwd``): -> (g1 (h,16) fp64, dw2 (h,h) fp64)."""
+    xyz, xs = _cloud_view(xyz)
+    B, N, K = idx32.shape
+    d = 2 * h
+    dev = xyz.device
+    buf = torch.zeros(h * 16 + h * h, dtype=torch.float64, device=dev)
+    g1, dw2 = buf[:h * 16].view(h, 16), buf[h * 16:].view(h, h)
+    flops = float(B) * N * K * 2 * (10 * h + 3 * h * h + 16 * h)
+    nbytes = float(B) * N * (12 + 4 * K + 4 * K * h)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_bn2_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_bn2_bwd(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
+                                         _cabi.ptr(b_rpe1), _cabi.ptr(du2_tiles), _cabi.ptr(w_rpe2T), _cabi.ptr(w_rpe2),
+                                         _cabi.ptr(bn2), _cabi.raw(g1), _cabi.raw(dw2), B, N, K, d,
+                                         _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_bn2_bwd")
+    return g1, dw2

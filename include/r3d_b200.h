@@ -125,6 +125,7 @@ int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstride, const in
  * Outputs, all ACCUMULATED into (the caller zero-fills them):
  *   dfeat    (B,N,h)  gradient w.r.t. `feat` (scatter-add over neighbour lists, fp32 atomics)
  *   dw_score (d,d)    [out][in]
+ * g1, g2m, g2c are fp64 (their sums cancel against the BatchNorm mean/variance terms of the moment path):
  *   g1       (h,16)   cols 0..9 = sum_rows du1 * rpe, col 10 = sum_rows du1, where du1 is the gradient at
  *                     the input of mlp_rpe1's ReLU; the host forms dW1 = a1 (.) g1[:, :10],
  *                     da1 = rowsum(W1 (.) g1[:, :10]), db1 = g1[:,10]
@@ -134,8 +135,28 @@ int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstride, const i
                      long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
                      const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_rpe2s,
                      const float* w_scoreT, const float* w_score, const float* dpooled, float* dfeat,
-                     long long dfeat_bstride, float* dw_score, float* g1, float* g2m, float* g2c, int B, int N,
+                     long long dfeat_bstride, float* dw_score, double* g1, double* g2m, double* g2c, int B, int N,
                      int K, int d, r3d_stream_t stream);
+
+/* Train-mode backward of a STAGE-2 launch, split in the standard two BatchNorm passes (batch statistics of mlp_rpe2):
+ *   r3d_lfa_pool2_bwd_train  pass 1: as r3d_lfa_pool_bwd(stage 2) up to du2 (gradient at mlp_rpe2's ReLU input),
+ *                            which is written per CTA tile to du2_tiles ([b][tile][h][P*K], P = r3d_lfa_tile_points)
+ *                            together with sum_du2 (2,h) fp64 += (sum du2, sum du2 * r2); dfeat, dw_score as before.
+ *   r3d_lfa_bn2_bwd          pass 2: with bn2 (5,h) = a2, mean2, rstd2, mean(du2), mean(du2*zhat2):
+ *                            dz2 = a2 (du2 - m1 - zhat2 m2), dw2 (h,h) fp64 += dz2^T r1, dr1 = dz2 W2,
+ *                            du1 = dr1 [r1 > 0], g1 (h,16) fp64 += du1^T [rpe, 1].
+ * Subtracting the mean/variance terms per row (not as row sums) keeps fp32 accuracy at any cloud size. */
+int r3d_lfa_tile_points(int K, int d);
+int r3d_lfa_pool2_bwd_train(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                            long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                            const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,
+                            const float* w_score, const float* dpooled, float* dfeat, long long dfeat_bstride,
+                            float* dw_score, float* du2_tiles, double* sum_du2, int B, int N, int K, int d,
+                            r3d_stream_t stream);
+int r3d_lfa_bn2_bwd(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* w_rpe1,
+                    const float* a_rpe1, const float* b_rpe1, const float* du2_tiles, const float* w_rpe2T,
+                    const float* w_rpe2, const float* bn2, double* g1, double* dw2, int B, int N, int K, int d,
+                    r3d_stream_t stream);
 
 /* Moments for the train-mode BatchNorm of mlp_rpe1 / mlp_rpe2 (modules.py:86-90 statistics over all
  * B*N*K positions), accumulated in fp64 into caller-zeroed buffers:
@@ -146,14 +167,14 @@ int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstride, const i
  *           g1 (h,16) += du1^T [rpe, 1] as in r3d_lfa_pool_bwd. */
 int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* w_rpe1,
                     const float* a_rpe1, const float* b_rpe1, double* m_rpe, double* m_r1, double* s_r1,
-                    const float* gsym, const float* gsum, float* g1, int B, int N, int K, int d,
+                    const float* gsym, const float* gsum, double* g1, int B, int N, int K, int d,
                     r3d_stream_t stream);
 
 /* Train-mode BatchNorm of y = W x (+bias) from the input moments S = sum x (stride s_stride), M = sum x x^T
  * (ldm), R rows (r3d_lfa_moments): a = gamma/sqrt(var+eps), c = beta - a (W mu) with mean = W mu,
  * var = diag(W Cov W^T).  W (cout,cin) [out][in], cin <= 128.  Updates running_mean/var/num_batches (nullable)
  * like BatchNorm2d; save (5,cout) fp64 is scratch for the backward.
- * Backward: ga, gc (cout) -> dW (cout,cin), dgamma, dbeta; scal (2,cout) fp64 scratch; when dM (cin,cin) and
+ * Backward: ga, gc (cout, fp64) -> dW (cout,cin, fp64), dgamma, dbeta; scal (2,cout) fp64 scratch; when dM (cin,cin) and
  * dS (cin) are given (fp64) they receive the gradient w.r.t. the moments (mlp_rpe2: r1's moments depend on
  * mlp_rpe1's parameters; they feed r3d_lfa_moments mode 2). */
 int r3d_bn_from_moments(const float* W, int cout, int cin, const double* S, int s_stride, const double* M, int ldm,
@@ -161,8 +182,8 @@ int r3d_bn_from_moments(const float* W, int cout, int cin, const double* S, int 
                         float momentum, float* running_mean, float* running_var, long long* num_batches,
                         float* a_out, float* c_out, double* save, r3d_stream_t stream);
 int r3d_bn_from_moments_bwd(const float* W, int cout, int cin, const double* S, int s_stride, const double* M,
-                            int ldm, double R, const float* gamma, const double* save, const float* ga,
-                            const float* gc, float* dW, float* dgamma, float* dbeta, double* scal, double* dM,
+                            int ldm, double R, const float* gamma, const double* save, const double* ga,
+                            const double* gc, double* dW, float* dgamma, float* dbeta, double* scal, double* dM,
                             double* dS, r3d_stream_t stream);
 
 /* ----------------------------------------------------------------------------- per-point MLP layer
@@ -189,6 +210,11 @@ int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int
                         const float* xb, long long xb_bstride, int cb, const float* wT, const float* scale,
                         const float* shift, int act, float slope, float* y, long long y_bstride, int y_ld, int cout,
                         int B, int n, int transpose_out, double* stats, int w_out_in, r3d_stream_t stream);
+
+/* Wide layers (C_in >= 32, C_out a multiple of 32, channel counts multiples of 4) run on the tcgen05 tensor cores
+ * with the 3xTF32 split (csrc/pointwise_tc.cu, fp32-level accuracy); everything else on the FP32 CUDA-core kernels.
+ * on = 0 forces the CUDA-core kernels everywhere, 1 (default) enables the tensor-core path.  Returns the previous value. */
+int r3d_pointwise_set_tensor_cores(int on);
 
 /* ------------------------------------------------------------- train-mode BatchNorm of a per-point layer
  * Forward tail of SharedMLP in training mode (modules.py:92-104): z (M,C) = conv output WITHOUT bias, stats from

@@ -102,7 +102,7 @@ def synth_state_dict(settings: dict, seed: int = 0) -> "Dict[str, torch.Tensor]"
 def knn(xyz: torch.Tensor, xyz_query: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """KNN.forward: indices int64 (B,N,K) and NON-squared distances (sqrt at modules.py:149)."""
     idx, d2 = knn_exact(xyz.detach().cpu().numpy(), xyz_query.detach().cpu().numpy(), k)
-    return torch.from_numpy(idx), torch.sqrt(torch.from_numpy(d2))
+    return torch.from_numpy(idx), torch.sqrt(torch.from_numpy(d2)).to(xyz.dtype)
 
 
 # --------------------------------------------------------------------------- SharedMLP (modules.py:60-104)
@@ -202,7 +202,7 @@ def forward(sd: "Dict[str, torch.Tensor]", settings: dict, inp: torch.Tensor,
     assert N >= min_n_points(s), f"Input point cloud should have at least {min_n_points(s)} points!"
     dec, k, L = s["decimation"], s["n_neighbors"], len(s["layer_sizes"])
 
-    xyz = inp[..., :3].float()
+    xyz = inp[..., :3] if inp.dtype == torch.float64 else inp[..., :3].float()   # fp64 runs are the arbiter in tests
     feat = F.linear(inp, sd["fc_start.weight"], sd["fc_start.bias"]).transpose(-2, -1).unsqueeze(-1)
     feat = F.leaky_relu(_bn(sd, "bn_start.0", feat, training), 0.2)
     if training:
@@ -319,6 +319,36 @@ def grad_parity(got: "Dict[str, torch.Tensor]", ref: "Dict[str, torch.Tensor]", 
         if r > worst:
             worst, worst_name = r, name
     return worst, worst_name
+
+
+def grad_parity_l2(got: "Dict[str, torch.Tensor]", ref: "Dict[str, torch.Tensor]"):
+    """Worst per-tensor relative L2 error ||got - ref|| / ||ref|| (dead conv biases excluded).  Used for clouds
+    beyond the golden sizes, where one flipped ReLU branch (see grad_parity) moves a whole channel row of the small
+    encoding-MLP gradients — more than 1 % of their entries — while the tensor as a whole stays within ~1e-4..1e-3."""
+    worst, worst_name = 0.0, ""
+    for name, g in ref.items():
+        dead = name == "fc_start.bias" or (
+            name.endswith(".conv.bias") and (name[:-len("conv.bias")] + "batch_norm.weight") in ref)
+        if dead or got[name] is None:
+            continue
+        r = float((got[name].detach().cpu().double() - g.double()).norm() / max(float(g.double().norm()), 1e-30))
+        if r > worst:
+            worst, worst_name = r, name
+    return worst, worst_name
+
+
+def grad_parity_fraction(got: "Dict[str, torch.Tensor]", ref: "Dict[str, torch.Tensor]", tol: float = 1e-4) -> float:
+    """Fraction of all gradient entries (dead conv biases excluded) within ``tol`` * max|ref tensor| of the reference."""
+    ok = total = 0
+    for name, g in ref.items():
+        dead = name == "fc_start.bias" or (
+            name.endswith(".conv.bias") and (name[:-len("conv.bias")] + "batch_norm.weight") in ref)
+        if dead or got[name] is None:
+            continue
+        d = (got[name].detach().cpu().double() - g.double()).abs()
+        ok += int((d <= tol * max(float(g.abs().max()), 1e-30)).sum())
+        total += d.numel()
+    return ok / max(total, 1)
 
 
 def grad_fixture_view(g: torch.Tensor, limit: int = 1024) -> torch.Tensor:

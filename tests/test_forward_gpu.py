@@ -46,6 +46,9 @@ def mods():
     (2, 999, 128, 0, 64, "relu", None, False), (4, 39, 512, 0, 512, "relu", None, False),
     (2, 333, 8, 0, 64, "relu", "shared", False), (1, 77, 64, 0, 32, "relu", None, False),
     (2, 100, 5, 0, 8, "lrelu", "shared", False),
+    # >= 4096 rows: wide layers take the tcgen05 path
+    (2, 2560, 512, 512, 256, "relu", "per_cloud", False), (4, 1100, 128, 0, 512, "relu", None, False),
+    (1, 5000, 64, 32, 128, "lrelu", "shared", False), (2, 4096, 32, 0, 64, None, None, False),
 ])
 def test_pointwise_vs_torch(mods, B, n, ca, cb, cout, act, gather, tr):
     _, _, ops = mods
@@ -73,7 +76,17 @@ def test_pointwise_vs_torch(mods, B, n, ca, cb, cout, act, gather, tr):
     if tr:
         ref = ref.transpose(1, 2)
     assert got.shape == ref.shape
-    assert rel_err(got.double(), ref) < 2e-6
+    # wide layers run on tcgen05 with the 3xTF32 split (error up to ~1e-5 at C_in = 1024), the rest in plain fp32
+    assert rel_err(got.double(), ref) < 2e-5
+    # and the two back-ends agree with each other
+    L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+    prev = L.r3d_pointwise_set_tensor_cores(0)
+    try:
+        got_cc = ops.pointwise(xa, wT, sc, sh, act, 0.2, gidx=gidx, xb=xb, transpose_out=tr)
+    finally:
+        L.r3d_pointwise_set_tensor_cores(prev)
+    assert rel_err(got_cc.double(), ref) < 2e-6
+    assert rel_err(got, got_cc) < 2e-5
 
 
 @pytest.mark.parametrize("d,K", [(16, 16), (64, 16), (128, 16), (256, 16), (16, 32), (32, 32), (64, 32), (128, 32),

@@ -133,7 +133,8 @@ def test_lfa_block_fused_vs_autograd(mods, n_in, d, K, N, train):
 
 
 @pytest.mark.parametrize("M,cin,cout,act", [(5000, 8, 8, "lrelu"), (1237, 3, 8, "lrelu"), (2048, 64, 32, "relu"),
-                                            (700, 512, 512, "relu"), (333, 1024, 256, "relu"), (40000, 16, 32, None)])
+                                            (700, 512, 512, "relu"), (333, 1024, 256, "relu"), (40000, 16, 32, None),
+                                            (8192, 512, 512, "relu"), (5000, 96, 128, "relu"), (16384, 64, 32, "lrelu")])
 def test_shared_mlp_train_kernels_vs_torch(mods, M, cin, cout, act):
     """Train-mode SharedMLP (GEMM + batch-stat BatchNorm + activation) forward, dx, dW, dgamma, dbeta and the
     running statistics: sm_100a per-point kernels vs fp64 tensor ops."""
@@ -166,7 +167,7 @@ def test_shared_mlp_train_kernels_vs_torch(mods, M, cin, cout, act):
         assert rel_err(pa.grad, pc.grad) < TOL, k
     for (k, va), (_, vc) in zip(la.state_dict().items(), lc.state_dict().items()):
         if "running" in k:
-            assert torch.allclose(va.double(), vc, rtol=1e-5, atol=1e-6), k
+            assert torch.allclose(va.double(), vc, rtol=1e-4, atol=1e-5), k
         if "num_batches" in k:
             assert int(va) == int(vc) == 1
 
