@@ -58,7 +58,7 @@ struct LfaFwdSmem {
 };
 
 template <int D, int K, int STAGE>
-__global__ void __launch_bounds__(kLfaThreads, 2) lfa_pool_kernel(LfaArgs a) {
+__global__ void __launch_bounds__(kLfaThreads, (D <= 16 ? 5 : (D <= 64 ? 3 : 2))) lfa_pool_kernel(LfaArgs a) {
     using C = LfaCfg<D, K, kLfaThreads, kLfaFwdStage, lfa_rows_per_thread(D)>;
     constexpr int H = C::H;
     constexpr int RT = C::RT;

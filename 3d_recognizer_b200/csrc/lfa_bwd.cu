@@ -66,7 +66,7 @@ struct LfaBwdSmem {
 };
 
 template <int D, int K, int NT, int STAGE>
-__global__ void __launch_bounds__(NT, 1) lfa_pool_bwd_kernel(LfaBwdArgs a) {
+__global__ void __launch_bounds__(NT, (D <= 16 ? 3 : (D <= 64 ? 2 : 1))) lfa_pool_bwd_kernel(LfaBwdArgs a) {
     using C = LfaBwdCfg<D, K, NT>;
     constexpr int H = C::H;
     constexpr int RT = C::RT;
@@ -341,7 +341,7 @@ struct LfaMomSmem {
 //         through the moments instead (MODE 2) subtracts two row sums that cancel to ~1/sqrt(rows) of their size and
 //         lost 3-4 digits at 65 k rows.
 template <int D, int K, int NT, int MODE>
-__global__ void __launch_bounds__(NT, 1) lfa_moments_kernel(LfaMomArgs a) {
+__global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : 1))) lfa_moments_kernel(LfaMomArgs a) {
     using C = LfaBwdCfg<D, K, NT>;
     constexpr int H = C::H;
     constexpr int RT = C::RT;
