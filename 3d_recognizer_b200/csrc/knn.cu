@@ -41,6 +41,7 @@ static std::atomic<int> g_knn_algorithm{0};  // 0 auto, 1 tiled brute force, 2 u
 
 // knn_grid.cu
 size_t knn_grid_workspace_bytes(int B, int Ns, int Nq);
+void knn_grid_set_density(float v);
 int knn_grid_run(const float* support, long long s_stride, const float* query, long long q_stride, int B, int Ns,
                  int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq, void* workspace,
                  cudaStream_t st);
@@ -370,6 +371,12 @@ extern "C" size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K) {
 extern "C" int r3d_knn_set_variant(int variant) {
     if (variant < 0 || variant > 2) return g_knn_variant.load();
     return g_knn_variant.exchange(variant);
+}
+
+// tuning hook for tools/knn_bench.py: average support points per grid cell (0 = built-in default)
+extern "C" int r3d_knn_set_grid_density(float points_per_cell) {
+    knn_grid_set_density(points_per_cell);
+    return R3D_OK;
 }
 
 extern "C" int r3d_knn_set_algorithm(int algorithm) {

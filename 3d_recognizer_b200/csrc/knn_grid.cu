@@ -40,6 +40,7 @@ struct GridHdr {
 static_assert(sizeof(GridHdr) == 48, "GridHdr layout");
 
 constexpr int kGridMaxAxis = 1024;
+static float g_pts_per_cell = 0.f;   // tuning hook (r3d_knn_set_grid_density); 0 = default
 
 __device__ __forceinline__ float d2_contract_g(float qx, float qy, float qz, float sx, float sy, float sz) {
     const float dx = __fsub_rn(qx, sx), dy = __fsub_rn(qy, sy), dz = __fsub_rn(qz, sz);
@@ -450,7 +451,7 @@ int knn_grid_run(const float* support, long long s_stride, const float* query, l
     R3D_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(p.off_cellof - p.off_counts), st));
     grid_bbox_kernel<<<B, 1024, 0, st>>>(support, s_stride, Ns, bbox);
     R3D_LAUNCH_CHECK("grid_bbox_kernel");
-    grid_setup_kernel<<<ceil_div(B, 128), 128, 0, st>>>(bbox, hdr, B, Ns, budget, K >= 24 ? 4.f : 2.f);
+    grid_setup_kernel<<<ceil_div(B, 128), 128, 0, st>>>(bbox, hdr, B, Ns, budget, g_pts_per_cell > 0.f ? g_pts_per_cell : (K >= 24 ? 4.f : 2.f));
     R3D_LAUNCH_CHECK("grid_setup_kernel");
     {
         dim3 grid(ceil_div(Ns, 256), B);
@@ -494,5 +495,8 @@ int knn_grid_run(const float* support, long long s_stride, const float* query, l
     R3D_LAUNCH_CHECK("knn_grid_kernel");
     return R3D_OK;
 }
+
+
+void knn_grid_set_density(float v) { g_pts_per_cell = v; }
 
 }  // namespace r3d

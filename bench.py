@@ -489,6 +489,12 @@ def main():
 
     # per-kernel shares are relative to the EAGER instrumented step (event records are not capturable)
     for kname in tab:
+        kv = tab[kname]
+        # per-kernel roofline fractions (algorithmic work / measured launch time / peak of the binding resource)
+        kv["tflops"] = kv["flops"] / kv["ms_avg"] * 1e-9 if kv["ms_avg"] > 0 else 0.0
+        kv["frac_fp32_peak"] = kv["tflops"] / fp32_peak["ffma"]
+        kv["gbs"] = kv["bytes"] / kv["ms_avg"] * 1e-6 if kv["ms_avg"] > 0 else 0.0
+        kv["frac_hbm_peak"] = kv["gbs"] / peaks["hbm_gbs"]
         tab[kname]["ms_per_step"] = tab[kname]["ms_total"] / n_eager
         tab[kname]["share_of_eager_step"] = tab[kname]["ms_per_step"] / eager_ms_per_step
         tab[kname]["launches"] //= n_eager

@@ -84,6 +84,8 @@ int r3d_knn_set_variant(int variant);
 /* search algorithm: 0 auto (uniform-grid search for Ns >= 2048, tiled brute force below), 1 tiled brute
  * force, 2 uniform grid.  Both return identical results.  Returns the previous value. */
 int r3d_knn_set_algorithm(int algorithm);
+/* tuning hook: average number of support points per grid cell of the uniform-grid search (0 = built-in default) */
+int r3d_knn_set_grid_density(float points_per_cell);
 
 /* ------------------------------------------------------- fused LocSE + attentive pooling (one LFA half)
  * Replaces, for one half of LocalFeatureAggregation.forward (modules.py:316-319 = stage 1, :321-323 =
