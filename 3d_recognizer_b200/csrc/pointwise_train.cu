@@ -277,6 +277,81 @@ __global__ void __launch_bounds__(256) rowreduce_gemm_fast_kernel(const float* _
         }
 }
 
+// Large-tile variant for wide layers (both channel counts >= 128): 128 x 128 outputs per CTA, 8 x 8 per thread, 16-row
+// chunks double-buffered with register prefetch — four times the FMA : LDS ratio of the 64 x 64 kernel.
+constexpr int kRrBig = 128;
+constexpr int kRrBigKC = 16;
+
+__global__ void __launch_bounds__(256) rowreduce_gemm_big_kernel(const float* __restrict__ A, int Ca,
+                                                                 const float* __restrict__ Bm, int Cb, long long M,
+                                                                 long long rows_per_cta, float* __restrict__ out,
+                                                                 int ld_out) {
+    __shared__ __align__(16) float As[2][kRrBigKC][kRrBig];
+    __shared__ __align__(16) float Bs[2][kRrBigKC][kRrBig];
+    const int tid = threadIdx.x;
+    const int a0 = blockIdx.x * kRrBig, b0 = blockIdx.y * kRrBig;
+    const long long r_lo = (long long)blockIdx.z * rows_per_cta;
+    const long long r_hi = min(M, r_lo + rows_per_cta);
+    const int ta = tid / 16, tb = tid % 16;   // rows ta*4.. and 64 + ta*4.., cols tb*4.. and 64 + tb*4..
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 ra[2], rb[2];
+    auto load = [&](long long r0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * 256;                 // 16 rows x 32 quads
+            const int row = i / 32, c = (i % 32) * 4;
+            const long long r = r0 + row;
+            ra[k] = (r < r_hi && a0 + c < Ca) ? *reinterpret_cast<const float4*>(A + r * Ca + a0 + c)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[k] = (r < r_hi && b0 + c < Cb) ? *reinterpret_cast<const float4*>(Bm + r * Cb + b0 + c)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * 256;
+            *reinterpret_cast<float4*>(&As[buf][i / 32][(i % 32) * 4]) = ra[k];
+            *reinterpret_cast<float4*>(&Bs[buf][i / 32][(i % 32) * 4]) = rb[k];
+        }
+    };
+    load(r_lo);
+    store(0);
+    __syncthreads();
+    int buf = 0;
+    for (long long r0 = r_lo; r0 < r_hi; r0 += kRrBigKC, buf ^= 1) {
+        const bool more = r0 + kRrBigKC < r_hi;
+        if (more) load(r0 + kRrBigKC);
+#pragma unroll
+        for (int k = 0; k < kRrBigKC; ++k) {
+            const float4 a0v = *reinterpret_cast<const float4*>(&As[buf][k][ta * 4]);
+            const float4 a1v = *reinterpret_cast<const float4*>(&As[buf][k][64 + ta * 4]);
+            const float4 b0v = *reinterpret_cast<const float4*>(&Bs[buf][k][tb * 4]);
+            const float4 b1v = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tb * 4]);
+            const float a_[8] = {a0v.x, a0v.y, a0v.z, a0v.w, a1v.x, a1v.y, a1v.z, a1v.w};
+            const float b_[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+        }
+        if (more) store(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ca = a0 + (i < 4 ? ta * 4 + i : 64 + ta * 4 + (i - 4));
+            const int cb = b0 + (j < 4 ? tb * 4 + j : 64 + tb * 4 + (j - 4));
+            if (ca < Ca && cb < Cb) atomicAdd(out + (size_t)ca * ld_out + cb, acc[i][j]);
+        }
+}
+
 }  // namespace r3d
 
 using namespace r3d;
@@ -337,9 +412,12 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
     if (M == 0) return R3D_OK;
     if (!A || !Bm || !out) return R3D_EINVAL;
     if (ld_out == 0) ld_out = Cb;
-    const int ga = ceil_div(Ca, kRrTile), gb = ceil_div(Cb, kRrTile);
-    // enough row chunks to fill the machine, at least 256 rows each
-    long long chunks = ((long long)kNumSMs * 4 + ga * gb - 1) / (ga * gb);
+    const bool vec = (Ca % 4) == 0 && (Cb % 4) == 0 && is_aligned(A, 16) && is_aligned(Bm, 16);
+    const bool big = vec && Ca >= 128 && Cb >= 128;
+    const int tile = big ? kRrBig : kRrTile;
+    const int ga = ceil_div(Ca, tile), gb = ceil_div(Cb, tile);
+    // enough row chunks to fill the machine, at least 128 rows each
+    long long chunks = ((long long)kNumSMs * (big ? 2 : 4) + ga * gb - 1) / (ga * gb);
     const long long max_chunks = (M + 127) / 128;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -348,12 +426,13 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
     rows_per_cta = (rows_per_cta + kRrKC2 - 1) / kRrKC2 * kRrKC2;
     chunks = (M + rows_per_cta - 1) / rows_per_cta;
     dim3 grid(ga, gb, (unsigned)chunks);
-    if ((Ca % 4) == 0 && (Cb % 4) == 0 && is_aligned(A, 16) && is_aligned(Bm, 16))
-        rowreduce_gemm_fast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, rows_per_cta,
-                                                                                        out, ld_out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (big)
+        rowreduce_gemm_big_kernel<<<grid, 256, 0, st>>>(A, Ca, Bm, Cb, M, rows_per_cta, out, ld_out);
+    else if (vec)
+        rowreduce_gemm_fast_kernel<<<grid, 256, 0, st>>>(A, Ca, Bm, Cb, M, rows_per_cta, out, ld_out);
     else
-        rowreduce_gemm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, rows_per_cta, out,
-                                                                                   ld_out);
+        rowreduce_gemm_kernel<<<grid, 256, 0, st>>>(A, Ca, Bm, Cb, M, rows_per_cta, out, ld_out);
     R3D_LAUNCH_CHECK("rowreduce_gemm_kernel");
     return R3D_OK;
 }
