@@ -352,6 +352,43 @@ __global__ void __launch_bounds__(256) rowreduce_gemm_big_kernel(const float* __
         }
 }
 
+// Thin variant (one side <= 8 channels, the other <= 32: fc_start's 8x3, the class logits' 2x32): HBM-streaming.
+// A lane owns one channel of the wide side, loops over the narrow side; rows are strided over all warps of the grid;
+// one shared-memory reduction per CTA, then one atomic per element and CTA.
+__global__ void __launch_bounds__(256) rowreduce_gemm_thin_kernel(const float* __restrict__ A, int Ca,
+                                                                  const float* __restrict__ Bm, int Cb, long long M,
+                                                                  float* __restrict__ out, int ld_out) {
+    // W = wide operand (lanes), Nw = its channels; S = narrow operand, Ns <= 8
+    const bool a_wide = Ca >= Cb;
+    const float* Wd = a_wide ? A : Bm;
+    const float* Sd = a_wide ? Bm : A;
+    const int Nw = a_wide ? Ca : Cb, Ns = a_wide ? Cb : Ca;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long r = gw; r < M; r += nw) {
+        const float w = lane < Nw ? Wd[r * Nw + lane] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < Ns) acc[j] = fmaf(w, Sd[r * Ns + j], acc[j]);
+    }
+    __shared__ float red[8][32];
+    for (int i = threadIdx.x; i < 256; i += 256) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < Ns) atomicAdd(&red[j][lane], acc[j]);
+    __syncthreads();
+    const int i = threadIdx.x;            // 256 = 8 x 32 elements
+    const int j = i / 32, l = i % 32;
+    if (j < Ns && l < Nw) {
+        const int ca = a_wide ? l : j, cb = a_wide ? j : l;
+        atomicAdd(out + (size_t)ca * ld_out + cb, red[j][l]);
+    }
+}
+
 }  // namespace r3d
 
 using namespace r3d;
@@ -412,6 +449,15 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
     if (M == 0) return R3D_OK;
     if (!A || !Bm || !out) return R3D_EINVAL;
     if (ld_out == 0) ld_out = Cb;
+    if ((Ca <= 8 && Cb <= 32) || (Cb <= 8 && Ca <= 32)) {
+        long long blocks = (M + 8 * 64 - 1) / (8 * 64);           // >= 64 rows per warp
+        if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+        if (blocks < 1) blocks = 1;
+        rowreduce_gemm_thin_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, out,
+                                                                                                  ld_out);
+        R3D_LAUNCH_CHECK("rowreduce_gemm_thin_kernel");
+        return R3D_OK;
+    }
     const bool vec = (Ca % 4) == 0 && (Cb % 4) == 0 && is_aligned(A, 16) && is_aligned(Bm, 16);
     const bool big = vec && Ca >= 128 && Cb >= 128;
     const int tile = big ? kRrBig : kRrTile;
