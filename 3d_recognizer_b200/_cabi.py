@@ -31,6 +31,7 @@ SIGNATURES = {
     "r3d_knn_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "r3d_knn_set_variant": (c_int, [c_int]),
     "r3d_knn_set_algorithm": (c_int, [c_int]),
+    "r3d_knn_plan": (c_int, [c_int, c_int, c_int, c_int]),
     "r3d_knn_set_grid_density": (c_int, [ctypes.c_float]),
     "r3d_lfa_pool": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -66,7 +67,7 @@ SIGNATURES = {
     "r3d_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int,
                                   ctypes.c_float, c_void_p, c_void_p]),
     "r3d_bn_bwd_dz": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, ctypes.c_float,
-                              c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_rowreduce_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p]),
     "r3d_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_fp32_probe_floats": (c_size_t, []),

@@ -42,6 +42,7 @@ static std::atomic<int> g_knn_algorithm{0};  // 0 auto, 1 tiled brute force, 2 u
 // knn_grid.cu
 size_t knn_grid_workspace_bytes(int B, int Ns, int Nq);
 void knn_grid_set_density(float v);
+void knn_grid_set_walk(int thread_per_query);
 int knn_grid_run(const float* support, long long s_stride, const float* query, long long q_stride, int B, int Ns,
                  int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq, void* workspace,
                  cudaStream_t st);
@@ -307,6 +308,105 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_kernel(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------- small clouds (Ns < 2048)
+// The down-sampled levels and the decoder of a 2 500-point cloud search 39..625 support points for a few thousand
+// queries: one thread per query leaves most SMs idle and every thread walks the whole support with a dependent
+// insertion chain (96 us per launch in the training step's launch list).  Here a WARP owns a query: lane l computes
+// the contract d2 of support points l, l+32, l+64, .. once and keeps them in registers as 64-bit keys
+// (d2 bits << 32 | index; d2 >= 0, so the unsigned order of the keys IS the (d2, index) order of the contract), and
+// the K nearest are extracted by K rounds of "smallest key above the last one": a branch-free scan of the lane's
+// registers and two warp redux.min.u32 (d2 bits, then index among the lanes that hold that d2).  No insertion,
+// no divergence, results bit-identical to the other back-ends.
+constexpr int kSmallThreads = 256;
+constexpr int kSmallMaxNs = 2047;
+
+template <int C>
+__global__ void __launch_bounds__(kSmallThreads) knn_small_kernel(const float* __restrict__ support, long long s_stride,
+                                                                  const float* __restrict__ query, long long q_stride,
+                                                                  int Ns, int Nq, int K, int qpw,
+                                                                  int64_t* __restrict__ idx64, int32_t* __restrict__ idx32,
+                                                                  float* __restrict__ dist, float* __restrict__ dist_sq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sx = reinterpret_cast<float*>(smem_raw);            // [3][C*32]
+    constexpr int NP = C * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
+    const float* sup = support + (size_t)b * s_stride;
+    for (int i = tid; i < Ns; i += kSmallThreads) {
+        sx[i] = sup[(size_t)i * 3 + 0];
+        sx[NP + i] = sup[(size_t)i * 3 + 1];
+        sx[2 * NP + i] = sup[(size_t)i * 3 + 2];
+    }
+    __syncthreads();
+    const int q0 = (blockIdx.x * (kSmallThreads / 32) + warp) * qpw;
+    for (int qi = q0; qi < min(q0 + qpw, Nq); ++qi) {
+        const float* qp = query + (size_t)b * q_stride + (size_t)qi * 3;
+        const float qx = qp[0], qy = qp[1], qz = qp[2];
+        unsigned long long key[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = c * 32 + lane;
+            const float d = d2_contract(qx, qy, qz, sx[j], sx[NP + j], sx[2 * NP + j]);
+            key[c] = j < Ns ? ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j : ~0ull;
+        }
+        unsigned long long lo = 0, mine = 0;
+        const size_t o = ((size_t)b * Nq + qi) * K;
+        for (int k = 0; k < K; ++k) {
+            unsigned long long best = ~0ull;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (key[c] >= lo && key[c] < best) best = key[c];
+            const unsigned hi = (unsigned)(best >> 32);
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)best : 0xffffffffu);
+            const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+            lo = m + 1;
+            if ((k & 31) == lane) mine = m;
+            if ((k & 31) == 31 || k == K - 1) {       // coalesced store of up to 32 results
+                const int kk = (k & ~31) + lane;
+                if (kk <= k) {
+                    const float d = __uint_as_float((unsigned)(mine >> 32));
+                    const int id = (int)(unsigned)mine;
+                    if (idx64) idx64[o + kk] = id;
+                    if (idx32) idx32[o + kk] = id;
+                    if (dist) dist[o + kk] = __fsqrt_rn(d);
+                    if (dist_sq) dist_sq[o + kk] = d;
+                }
+            }
+        }
+    }
+}
+
+template <int C>
+static int launch_knn_small_c(const float* support, long long s_stride, const float* query, long long q_stride, int B,
+                              int Ns, int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
+                              cudaStream_t st) {
+    const size_t smem = (size_t)3 * C * 32 * sizeof(float);
+    // queries per warp: enough CTAs for ~4 per SM, at most 8 queries behind one staging of the cloud per warp
+    long long qpw = ((long long)B * Nq) / (8LL * 148 * 4);
+    qpw = qpw < 1 ? 1 : (qpw > 8 ? 8 : qpw);
+    dim3 grid(ceil_div(Nq, (kSmallThreads / 32) * (int)qpw), B);
+    knn_small_kernel<C><<<grid, kSmallThreads, smem, st>>>(support, s_stride, query, q_stride, Ns, Nq, K, (int)qpw, idx64,
+                                                           idx32, dist, dist_sq);
+    R3D_LAUNCH_CHECK("knn_small_kernel");
+    return R3D_OK;
+}
+
+static int launch_knn_small(const float* support, long long s_stride, const float* query, long long q_stride, int B,
+                            int Ns, int Nq, int K, int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
+                            cudaStream_t st) {
+#define R3D_SMALL(CC)                                                                                                   \
+    if (Ns <= CC * 32)                                                                                                  \
+        return launch_knn_small_c<CC>(support, s_stride, query, q_stride, B, Ns, Nq, K, idx64, idx32, dist, dist_sq, st);
+    R3D_SMALL(2)
+    R3D_SMALL(5)
+    R3D_SMALL(10)
+    R3D_SMALL(20)
+    R3D_SMALL(32)
+    R3D_SMALL(64)
+#undef R3D_SMALL
+    return R3D_EUNSUPPORTED;
+}
+
 static size_t knn_smem_bytes(int K, int Q, bool k1) {
     return 2 * 3 * kTile * sizeof(float) + 16 + (k1 ? 0 : (size_t)K * Q * kKnnThreads * 8);
 }
@@ -380,8 +480,23 @@ extern "C" int r3d_knn_set_grid_density(float points_per_cell) {
 }
 
 extern "C" int r3d_knn_set_algorithm(int algorithm) {
-    if (algorithm < 0 || algorithm > 2) return g_knn_algorithm.load();
+    if (algorithm < 0 || algorithm > 4 || algorithm == 3) return g_knn_algorithm.load();
+    knn_grid_set_walk(algorithm == 4 ? 1 : (algorithm == 2 ? 0 : -1));
     return g_knn_algorithm.exchange(algorithm);
+}
+
+// Which back-end r3d_knn runs for a shape under the current algorithm setting: 1 tiled brute force, 2 uniform grid,
+// 3 warp-per-query register scan.  Auto: the grid from 2048 support points up; below, the register scan while its
+// O(Nq Ns K / 32) work stays under the grid search's fixed cost (measured: 15 ps per query x candidate-per-lane x K
+// against ~25 us for the grid build and walk, profiles/r01_knn_small.txt).
+extern "C" int r3d_knn_plan(int B, int Ns, int Nq, int K) {
+    const int algo = g_knn_algorithm.load();
+    if (algo == 1 || algo == 2) return algo;
+    if (algo == 4) return 2;
+    if (Ns >= kGridMinSupport) return 2;
+    const long long c = (Ns + 31) / 32;
+    if (c <= 10 || K == 1 || (long long)B * Nq * c * K <= 1500000LL) return 3;
+    return 2;
 }
 
 extern "C" int r3d_knn(const float* support, long long support_batch_stride, const float* query,
@@ -399,10 +514,13 @@ extern "C" int r3d_knn(const float* support, long long support_batch_stride, con
     if (query_batch_stride == 0) query_batch_stride = (long long)Nq * 3;
     if (support_batch_stride < (long long)Ns * 3 || query_batch_stride < (long long)Nq * 3) return R3D_EINVAL;
 
-    const int algo = g_knn_algorithm.load();
-    if (algo == 2 || (algo == 0 && Ns >= kGridMinSupport))
+    const int plan = r3d_knn_plan(B, Ns, Nq, K);
+    if (plan == 2)
         return knn_grid_run(support, support_batch_stride, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
                             dist_sq, workspace, st);
+    if (plan == 3)
+        return launch_knn_small(support, support_batch_stride, query, query_batch_stride, B, Ns, Nq, K, idx64, idx32, dist,
+                                dist_sq, st);
 
     const int Nsp = (Ns + 3) & ~3;
     float* soa = static_cast<float*>(workspace);

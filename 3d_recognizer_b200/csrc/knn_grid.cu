@@ -41,6 +41,7 @@ static_assert(sizeof(GridHdr) == 48, "GridHdr layout");
 
 constexpr int kGridMaxAxis = 1024;
 static float g_pts_per_cell = 0.f;   // tuning hook (r3d_knn_set_grid_density); 0 = default
+static int g_grid_walk = -1;         // -1 by batch size, 0 one warp per query, 1 one thread per query (r3d_knn_set_algorithm)
 
 __device__ __forceinline__ float d2_contract_g(float qx, float qy, float qz, float sx, float sy, float sz) {
     const float dx = __fsub_rn(qx, sx), dy = __fsub_rn(qy, sy), dz = __fsub_rn(qz, sz);
@@ -390,6 +391,198 @@ __global__ void __launch_bounds__(kGridThreads) knn_grid_kernel(
     }
 }
 
+// ------------------------------------------------------------------------ query, one warp per query
+// The thread-per-query walk above is latency-bound: every candidate goes through a dependent shared-memory insertion
+// and a batch of 20 000 queries (8 clouds of 2 500 points) fills half the SMs with four warps each (230 us in the
+// training step's launch list).  Here a WARP walks the rings of one query: the lanes fetch 32 candidates at a time
+// (the block's cell rows are contiguous runs of the cell-sorted support; a shuffle binary search over the runs'
+// prefix sums maps lane -> point), candidates are 64-bit keys (d2 bits << 32 | index: d2 >= 0, so unsigned key order
+// is the contract's (d2, index) order), and the running K-best is a sorted list DISTRIBUTED over the lanes (entry p
+// lives in lane p % 32): inserting a key is one ballot (how many entries are smaller) and one shuffle-up.  Same rings,
+// same stop test, same results as the walk above.
+constexpr int kGridWarpThreads = 256;
+
+template <int KS>
+__global__ void __launch_bounds__(kGridWarpThreads) knn_grid_warp_kernel(
+    const float4* __restrict__ pts, const int* __restrict__ starts, int cells_alloc, const GridHdr* __restrict__ hdr,
+    const float* __restrict__ query, long long q_stride, const int* __restrict__ qorder /* nullable: self search */,
+    int Ns, int Nq, int K, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ dist,
+    float* __restrict__ dist_sq) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned long long NONE = ~0ull;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * (kGridWarpThreads / 32) + (threadIdx.x >> 5);
+    if (t >= Nq) return;                                   // warp-uniform
+    const GridHdr h = hdr[b];
+    const float4* P = pts + (size_t)b * Ns;
+    const int* S = starts + (size_t)b * cells_alloc;
+
+    int qi;
+    float qx, qy, qz;
+    if (qorder) {
+        qi = qorder[(size_t)b * Nq + t];
+        const float* q = query + (size_t)b * q_stride + (size_t)qi * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
+    } else {
+        const float4 q = P[t];
+        qx = q.x; qy = q.y; qz = q.z;
+        qi = __float_as_int(q.w);
+    }
+    const int gx = h.g[0], gy = h.g[1], gz = h.g[2];
+    const int cx = cell_coord(qx, h.lo[0], h.inv_s, gx);
+    const int cy = cell_coord(qy, h.lo[1], h.inv_s, gy);
+    const int cz = cell_coord(qz, h.lo[2], h.inv_s, gz);
+
+    unsigned long long lst[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) lst[s] = NONE;
+    unsigned long long kth = NONE;                          // key of entry K-1 (NONE until the list is full)
+    bool fresh = true;                                      // nothing inserted yet
+    const int kslot = (K - 1) >> 5, klane = (K - 1) & 31;
+
+    const int rmax = max(max(gx, gy), gz);
+    for (int r = 1; r <= rmax + 1; ++r) {
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, gz - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, gy - 1);
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, gx - 1);
+        const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+        const bool block = (r == 1);                        // the first pass takes the whole 3x3x3 block, later ones a shell
+        const int rows_per_batch = block ? 32 : 16;
+        for (int rb = 0; rb < nrows; rb += rows_per_batch) {
+            // ---- this lane's run of the cell-sorted support
+            int beg = 0, len = 0;
+            const int i = rb + (block ? lane : (lane >> 1));
+            if (i < nrows) {
+                const int z = z0 + i / ny, y = y0 + i % ny;
+                const int row = (z * gy + y) * gx;
+                if (block || z == cz - r || z == cz + r || y == cy - r || y == cy + r) {
+                    if (block || !(lane & 1)) {
+                        beg = S[row + x0];
+                        len = S[row + x1 + 1] - beg;
+                    }
+                } else {
+                    const int xx = (lane & 1) ? cx + r : cx - r;
+                    if (xx >= 0 && xx < gx) {
+                        beg = S[row + xx];
+                        len = S[row + xx + 1] - beg;
+                    }
+                }
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int shift = beg - (incl - len);           // point index = candidate number + shift, within this run
+            for (int cb = 0; cb < total; cb += 32) {
+                const int tt = cb + lane;
+                int sgm = 0;                                // first run whose inclusive prefix exceeds tt
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, (sgm + step - 1) & 31);
+                    if (tt >= v) sgm += step;
+                }
+                const int sh = __shfl_sync(FULL, shift, sgm & 31);
+                unsigned long long key = NONE;
+                if (tt < total) {
+                    const float4 p = __ldg(&P[tt + sh]);
+                    const float d = d2_contract_g(qx, qy, qz, p.x, p.y, p.z);
+                    key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                }
+                unsigned mask = __ballot_sync(FULL, key < kth);
+                if (KS == 1 && (fresh || __popc(mask) >= 8)) {
+                    // many admissible candidates (always true for the first chunk of a query): sort the chunk across
+                    // the lanes (15-stage bitonic network) and merge it with the list -- the element-wise minimum of
+                    // the list and the reversed chunk is a bitonic sequence holding the 32 smallest keys of both,
+                    // which five more stages sort.  ~200 instructions instead of ~25 per insertion.
+                    if (!(key < kth)) key = NONE;
+#pragma unroll
+                    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(FULL, key, j);
+                            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+                            key = ((other < key) == keep_min) ? other : key;
+                        }
+                    }
+                    if (fresh) {
+                        lst[0] = key;
+                    } else {
+                        const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
+                        unsigned long long m = rev < lst[0] ? rev : lst[0];
+#pragma unroll
+                        for (int j = 16; j > 0; j >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(FULL, m, j);
+                            const bool keep_min = (lane & j) == 0;
+                            m = ((other < m) == keep_min) ? other : m;
+                        }
+                        lst[0] = m;
+                    }
+                    fresh = false;
+                    kth = __shfl_sync(FULL, lst[0], klane);
+                    continue;
+                }
+                fresh = false;
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long x = __shfl_sync(FULL, key, src);
+                    if (x < kth) {                          // kth shrinks while the chunk is inserted
+                        int pos = 0;
+#pragma unroll
+                        for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(FULL, lst[s] < x));
+#pragma unroll
+                        for (int s = KS - 1; s >= 0; --s) {
+                            unsigned long long up = __shfl_up_sync(FULL, lst[s], 1);
+                            if (s > 0) {
+                                const unsigned long long carry = __shfl_sync(FULL, lst[s - 1], 31);
+                                if (lane == 0) up = carry;
+                            }
+                            const int gp = s * 32 + lane;
+                            if (gp > pos) lst[s] = up;
+                            else if (gp == pos) lst[s] = x;
+                        }
+                        unsigned long long tail = lst[0];
+#pragma unroll
+                        for (int s = 1; s < KS; ++s)
+                            if (kslot == s) tail = lst[s];
+                        kth = __shfl_sync(FULL, tail, klane);
+                    }
+                }
+            }
+        }
+        // ---- stop test: distance from the query to the nearest block face with cells behind it
+        float bound = CUDART_INF_F;
+        if (cx - r > 0) bound = fminf(bound, qx - (h.lo[0] + (float)(cx - r) * h.s));
+        if (cx + r < gx - 1) bound = fminf(bound, (h.lo[0] + (float)(cx + r + 1) * h.s) - qx);
+        if (cy - r > 0) bound = fminf(bound, qy - (h.lo[1] + (float)(cy - r) * h.s));
+        if (cy + r < gy - 1) bound = fminf(bound, (h.lo[1] + (float)(cy + r + 1) * h.s) - qy);
+        if (cz - r > 0) bound = fminf(bound, qz - (h.lo[2] + (float)(cz - r) * h.s));
+        if (cz + r < gz - 1) bound = fminf(bound, (h.lo[2] + (float)(cz + r + 1) * h.s) - qz);
+        if (bound == CUDART_INF_F) break;  // the block covers the whole grid
+        bound = (bound - h.margin) * 0.99999f;
+        const float kd = kth == NONE ? CUDART_INF_F : __uint_as_float((unsigned)(kth >> 32));
+        if (bound > 0.f && kd < bound * bound) break;
+    }
+
+    const size_t o = ((size_t)b * Nq + qi) * K;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        const int k = s * 32 + lane;
+        if (k < K) {
+            const float d = __uint_as_float((unsigned)(lst[s] >> 32));
+            const int id = (int)(unsigned)lst[s];
+            if (idx64) idx64[o + k] = id;
+            if (idx32) idx32[o + k] = id;
+            if (dist) dist[o + k] = __fsqrt_rn(d);
+            if (dist_sq) dist_sq[o + k] = d;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------- host side
 struct GridPlan {
     int cells_alloc;    // ints per cloud in a count/start array (cell budget + 1, rounded up)
@@ -479,6 +672,23 @@ int knn_grid_run(const float* support, long long s_stride, const float* query, l
                                                   nullptr, qorder);
         R3D_LAUNCH_CHECK("grid_scatter_kernel(q)");
     }
+    // One warp per query wins while the batch is too small to fill the SMs with independent query threads; beyond,
+    // the thread-per-query walk has the higher throughput (measured, profiles/r01_knn_small.txt: 8 x 2500 K=16
+    // 42 vs 144 us, 64 x 40960 3.8 vs 3.1 ms; from K=24 up the warp wins at every size: 1M x 1M K=32 3.0 vs 4.4 ms;
+    // K=1 has no list to share: thread walk).
+    const long long nq_total = (long long)B * Nq;
+    const bool warp_walk = g_grid_walk >= 0 ? g_grid_walk == 0 : (K > 1 && (K >= 24 || nq_total <= 160000LL));
+    if (warp_walk) {
+        dim3 wgrid(ceil_div(Nq, kGridWarpThreads / 32), B);
+        if (K <= 32)
+            knn_grid_warp_kernel<1><<<wgrid, kGridWarpThreads, 0, st>>>(pts, counts, p.cells_alloc, hdr, query, q_stride,
+                                                                        qorder, Ns, Nq, K, idx64, idx32, dist, dist_sq);
+        else
+            knn_grid_warp_kernel<2><<<wgrid, kGridWarpThreads, 0, st>>>(pts, counts, p.cells_alloc, hdr, query, q_stride,
+                                                                        qorder, Ns, Nq, K, idx64, idx32, dist, dist_sq);
+        R3D_LAUNCH_CHECK("knn_grid_warp_kernel");
+        return R3D_OK;
+    }
     dim3 grid(ceil_div(Nq, kGridThreads), B);
     if (K == 1) {
         knn_grid_kernel<true><<<grid, kGridThreads, 0, st>>>(pts, counts, p.cells_alloc, hdr, query, q_stride, qorder,
@@ -498,5 +708,6 @@ int knn_grid_run(const float* support, long long s_stride, const float* query, l
 
 
 void knn_grid_set_density(float v) { g_pts_per_cell = v; }
+void knn_grid_set_walk(int thread_per_query) { g_grid_walk = thread_per_query; }
 
 }  // namespace r3d

@@ -106,7 +106,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     __shared__ float red[2][kBnMaxC];
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i < C ? i : kBnMaxC + (i - C)] = 0.f;
     __syncthreads();
-    if (active) {
+    // narrow layers: the lanes of a warp that hold the same column quad (lane % c4n) combine by shuffles first --
+    // with C = 8 all 256 threads would otherwise queue on 16 shared-memory addresses
+    bool writer = active;
+    if (c4n <= 16 && (c4n & (c4n - 1)) == 0) {
+        for (int o = 16; o >= c4n; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
+        }
+        writer = (threadIdx.x & 31) < c4n;
+    }
+    if (writer) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             atomicAdd(&red[0][q * 4 + j], s1[j]);
@@ -124,8 +137,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                         long long M, int C, const float* __restrict__ save,
                                                         const float* __restrict__ beta, int act, float slope,
-                                                        const double* __restrict__ stats2, float* __restrict__ dz) {
+                                                        const double* __restrict__ stats2, float* __restrict__ dz,
+                                                        float* __restrict__ dgb) {
     __shared__ float sa[kBnMaxC], sm[kBnMaxC], sr[kBnMaxC], sc[kBnMaxC], m1[kBnMaxC], m2[kBnMaxC];
+    if (dgb && blockIdx.x == 0)
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) dgb[c] = (float)stats2[c];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         sa[c] = save[c];
         sm[c] = save[C + c];
@@ -424,21 +440,21 @@ extern "C" int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, i
     if (!dy || !z || !save || !beta || !stats2) return R3D_EINVAL;
     if (!is_aligned(dy, 16) || !is_aligned(z, 16)) return R3D_EALIGN;
     const int rows_per_pass = 256 / (C / 4);
-    bn_bwd_reduce_kernel<<<grid_for(M, rows_per_pass * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_bwd_reduce_kernel<<<grid_for(M, rows_per_pass * 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dy, z, M, C, save, beta, act, slope, stats2);
     R3D_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     return R3D_OK;
 }
 
 extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
-                             int act, float slope, const double* stats2, float* dz, r3d_stream_t stream) {
+                             int act, float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
     if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
     if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
     if (M == 0) return R3D_OK;
     if (!dy || !z || !save || !beta || !stats2 || !dz) return R3D_EINVAL;
     if (!is_aligned(dy, 16) || !is_aligned(z, 16) || !is_aligned(dz, 16)) return R3D_EALIGN;
     bn_bwd_dz_kernel<<<grid_for(M * C / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, z, M, C, save, beta, act,
-                                                                                             slope, stats2, dz);
+                                                                                             slope, stats2, dz, dgb);
     R3D_LAUNCH_CHECK("bn_bwd_dz_kernel");
     return R3D_OK;
 }

@@ -63,7 +63,7 @@ class _SharedMLPTrainFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, gamma, beta, bn, act, slope):
         x = x.contiguous()
         cout = w.shape[0]
-        scratch = torch.zeros(4 * cout, dtype=torch.float64, device=x.device)   # forward stats | backward stats
+        scratch = ops.zeros(4 * cout, torch.float64, x.device)   # forward stats | backward stats
         stats = scratch[:2 * cout]
         z = ops.pointwise(x.unsqueeze(0), w.contiguous(), stats=stats, w_out_in=True).squeeze(0)
         y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
@@ -370,6 +370,8 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     dec, L = s.decimation, len(s.layer_sizes)
     B, N, _ = inp.shape
     perm = _device_permutation(permutation, inp.device)
+    if inp.is_cuda:
+        ops.ZEROS.begin()          # one zero-filled scratch block for this forward/backward (ops._ZeroPool)
 
     inp = inp.float()
     bn0 = net.bn_start[0]

@@ -10,6 +10,50 @@ import torch
 from . import _cabi
 
 
+
+class _ZeroPool:
+    """Zero-filled scratch (accumulators of the atomics-based reductions) carved from one block per step.
+
+    A 2 500-point training step needs ~160 small zero-filled buffers (BatchNorm statistics, weight-gradient
+    accumulators, moment matrices); one fill kernel each was 5 % of the step (profiles/r01_launches_train2500.txt).
+    Slices are handed out once and never reused, so a buffer stays valid for as long as anything references it; a
+    block is sized from what the previous step took (``begin`` marks the step boundary)."""
+    MAX_BYTES = 4 << 20          # larger requests get their own fill: nothing to win by batching them
+
+    def __init__(self):
+        self.block, self.off, self.need, self.hint, self.captured = None, 0, 0, 1 << 20, False
+
+    def begin(self):
+        self.hint = max(1 << 20, self.need)
+        self.block, self.off, self.need = None, 0, 0
+
+    def take(self, shape, dtype, device):
+        numel = 1
+        for v in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            numel *= int(v)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        if nbytes > self.MAX_BYTES or nbytes == 0:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        aligned = (nbytes + 255) & ~255
+        self.need += aligned
+        # a block filled outside a CUDA-graph capture must not feed a captured step: its fill would not be replayed
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (self.block is None or self.block.device != torch.device(device) or capturing != self.captured
+                or self.off + aligned > self.block.numel()):
+            self.block = torch.zeros(max(self.hint, aligned), dtype=torch.uint8, device=device)
+            self.off, self.captured = 0, capturing
+        out = self.block[self.off:self.off + nbytes].view(dtype).view(shape)
+        self.off += aligned
+        return out
+
+
+ZEROS = _ZeroPool()
+
+
+def zeros(shape, dtype, device):
+    """Zero-filled scratch tensor from the per-step pool (see ``_ZeroPool``)."""
+    return ZEROS.take(shape, dtype, device)
+
 def _cloud_view(x: torch.Tensor):
     """(tensor, batch stride in elements) for a (B,N,C) fp32 tensor whose clouds are dense row-major;
     prefix views x[:, :n] of a contiguous tensor pass through without a copy."""
@@ -60,9 +104,9 @@ def knn(support: torch.Tensor, query: torch.Tensor, k: int, *, idx64: bool = Tru
         ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
         # the uniform-grid back-end does O(N K) work: crediting it with the 8 Nq Ns flop of the exhaustive scan would
         # put it far above any roofline, so only the brute-force kernel carries algorithmic flops
-        algo = L.r3d_knn_set_algorithm(-1)
-        grid = algo == 2 or (algo == 0 and Ns >= 2048)
-        with _cabi.kernel_timer(f"knn_{'grid' if grid else 'brute'}_k{k}[Ns={Ns}]",
+        plan = L.r3d_knn_plan(B, Ns, Nq, k)
+        grid = plan == 2
+        with _cabi.kernel_timer(f"knn_{ {1: 'brute', 2: 'grid', 3: 'small'}[plan]}_k{k}[Ns={Ns}]",
                                 flops=0.0 if grid else 8.0 * B * Ns * Nq,
                                 bytes=4.0 * B * (3 * Ns + 3 * Nq + Nq * k * (len(out) + ("idx64" in out)))):
             rc = L.r3d_knn(ctypes.c_void_p(support.data_ptr()), s_stride, ctypes.c_void_p(query.data_ptr()),
@@ -232,17 +276,17 @@ def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: tor
     M, C = z.shape
     dy = dy.contiguous()
     if stats2 is None:
-        stats2 = torch.zeros(2 * C, dtype=torch.float64, device=z.device)
+        stats2 = zeros(2 * C, torch.float64, z.device)
     dz = torch.empty_like(z)
+    s2 = torch.empty(2 * C, dtype=torch.float32, device=z.device)
     L = _cabi.lib()
     with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_backward[M={M},C={C}]", flops=12.0 * M * C, bytes=20.0 * M * C):
         rc = L.r3d_bn_bwd_reduce(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
                                  float(slope), _cabi.ptr(stats2), _cabi.stream_ptr(z.device))
         _cabi.check(rc, "r3d_bn_bwd_reduce")
         rc = L.r3d_bn_bwd_dz(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
-                             float(slope), _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.stream_ptr(z.device))
+                             float(slope), _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.ptr(s2), _cabi.stream_ptr(z.device))
     _cabi.check(rc, "r3d_bn_bwd_dz")
-    s2 = stats2.float()
     return dz, s2[C:], s2[:C]
 
 
@@ -251,7 +295,7 @@ def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     a, b = a.contiguous(), b.contiguous()
     M, Ca = a.shape
     Cb = b.shape[1]
-    out = torch.zeros((Ca, Cb), dtype=torch.float32, device=a.device)
+    out = zeros((Ca, Cb), torch.float32, a.device)
     with torch.cuda.device(a.device), _cabi.kernel_timer(f"rowreduce_gemm[M={M},{Ca}x{Cb}]" if _cabi.TIMER_SHAPES else "rowreduce_gemm", flops=2.0 * M * Ca * Cb,
                                                          bytes=4.0 * M * (Ca + Cb)):
         rc = _cabi.lib().r3d_rowreduce_gemm(_cabi.ptr(a), Ca, _cabi.ptr(b), Cb, M, _cabi.ptr(out), Cb,
@@ -274,10 +318,10 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
     # one zero-filled fp32 block for the feature gradient and the score-weight gradient, one fp64 block for the
     # encoding-MLP accumulators (they cancel against the BatchNorm moment terms and need the extra digits)
     n_df = B * N * h
-    acc = torch.zeros(n_df + d * d, dtype=torch.float32, device=dev)
+    acc = zeros(n_df + d * d, torch.float32, dev)
     dfeat = acc[:n_df].view(B, N, h)
     dws = acc[n_df:].view(d, d)
-    acc64 = torch.zeros(h * 16 + (h * h + h * 16 if stage == 2 else 0), dtype=torch.float64, device=dev)
+    acc64 = zeros(h * 16 + (h * h + h * 16 if stage == 2 else 0), torch.float64, dev)
     g1 = acc64[:h * 16].view(h, 16)
     g2m = g2c = None
     if stage == 2:
@@ -304,12 +348,12 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
     dev = xyz.device
     m_rpe = m_r1 = s_r1 = g1 = None
     if mode == 0:
-        m_rpe = torch.zeros((16, 16), dtype=torch.float64, device=dev)
+        m_rpe = zeros((16, 16), torch.float64, dev)
     elif mode == 1:
-        buf = torch.zeros(h * h + h * 16, dtype=torch.float64, device=dev)
+        buf = zeros(h * h + h * 16, torch.float64, dev)
         m_r1, s_r1 = buf[:h * h].view(h, h), buf[h * h:].view(h, 16)
     else:
-        g1 = torch.zeros((h, 16), dtype=torch.float64, device=dev)
+        g1 = zeros((h, 16), torch.float64, dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -383,10 +427,10 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     tiles = -(-N // pts)
     dpooled = dpooled.contiguous()
     n_df = B * N * h
-    acc = torch.zeros(n_df + d * d, dtype=torch.float32, device=dev)
+    acc = zeros(n_df + d * d, torch.float32, dev)
     dfeat, dws = acc[:n_df].view(B, N, h), acc[n_df:].view(d, d)
     du2 = torch.empty(B * tiles * h * pts * K, dtype=torch.float32, device=dev)
-    sums = torch.zeros((2, h), dtype=torch.float64, device=dev)
+    sums = zeros((2, h), torch.float64, dev)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + h * h))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 8 * K * h)
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool2_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -405,7 +449,7 @@ def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, 
     B, N, K = idx32.shape
     d = 2 * h
     dev = xyz.device
-    buf = torch.zeros(h * 16 + h * h, dtype=torch.float64, device=dev)
+    buf = zeros(h * 16 + h * h, torch.float64, dev)
     g1, dw2 = buf[:h * 16].view(h, 16), buf[h * 16:].view(h, h)
     flops = float(B) * N * K * 2 * (10 * h + 3 * h * h + 16 * h)
     nbytes = float(B) * N * (12 + 4 * K + 4 * K * h)

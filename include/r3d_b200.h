@@ -81,9 +81,13 @@ int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq
 /* tuning hook for benchmarks/tests: 0 exact scalar, 1 FMA-prefilter scalar, 2 FMA-prefilter
  * packed f32x2 (default).  All variants return identical results.  Returns the previous value. */
 int r3d_knn_set_variant(int variant);
-/* search algorithm: 0 auto (uniform-grid search for Ns >= 2048, tiled brute force below), 1 tiled brute
- * force, 2 uniform grid.  Both return identical results.  Returns the previous value. */
+/* search algorithm: 0 auto (see r3d_knn_plan), 1 tiled brute force, 2 uniform grid (one warp walks the rings of a
+ * query), 4 uniform grid with the one-thread-per-query walk.  All back-ends return identical results.  Returns the
+ * previous value. */
 int r3d_knn_set_algorithm(int algorithm);
+/* the back-end r3d_knn runs for this shape under the current setting: 1 tiled brute force, 2 uniform grid,
+ * 3 warp-per-query register scan (auto mode only: small supports, Ns < 2048) */
+int r3d_knn_plan(int B, int Ns, int Nq, int K);
 /* tuning hook: average number of support points per grid cell of the uniform-grid search (0 = built-in default) */
 int r3d_knn_set_grid_density(float points_per_cell);
 
@@ -227,11 +231,11 @@ int r3d_bn_apply(const float* z, const double* stats, long long M, int C, const 
                  const float* bias, float eps, float momentum, float* running_mean, float* running_var,
                  long long* num_batches, int act, float slope, float* y, float* save, r3d_stream_t stream);
 /* Backward: du = dy * act'(a z + c); stats2[2C] (fp64, caller-zeroed) += (sum du, sum du*zhat) = (dbeta, dgamma);
- * then dz = a (du - mean(du) - zhat * mean(du*zhat)). */
+ * then dz = a (du - mean(du) - zhat * mean(du*zhat)); dgb (2C fp32, nullable) receives (dbeta, dgamma) rounded. */
 int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
                       int act, float slope, double* stats2, r3d_stream_t stream);
 int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
-                  float slope, const double* stats2, float* dz, r3d_stream_t stream);
+                  float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream);
 /* Weight gradient of a per-point layer: out (Ca,Cb; ld_out, caller-zeroed) += A^T B for A (M,Ca), B (M,Cb). */
 int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
                        r3d_stream_t stream);

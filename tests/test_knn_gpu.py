@@ -12,7 +12,8 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 # (algorithm, variant): tiled brute force in its three arithmetic variants, and the uniform-grid search
-VARIANTS = [(1, 0), (1, 1), (1, 2), (2, 2)]
+# (2 = one warp per query, 4 = one thread per query), and (0, 2) = the library's own choice (r3d_knn_plan)
+VARIANTS = [(1, 0), (1, 1), (1, 2), (2, 2), (4, 2), (0, 2)]
 
 
 class _mode:
@@ -78,6 +79,22 @@ def test_knn_vs_oracle_seeded(ops, oracle_built, variant, B, Ns, Nq, K):
         assert np.array_equal(out["idx64"], oi)
         if same:
             assert (out["dist_sq"][..., 0] == 0).all(), "self distance must be exactly 0"
+
+
+@pytest.mark.parametrize("B,Ns,Nq,K", [(8, 625, 625, 16), (8, 156, 156, 16), (8, 39, 39, 16), (8, 156, 625, 1),
+                                       (3, 2048, 501, 32), (1, 2000, 2000, 64), (2, 33, 1000, 33), (5, 1, 7, 1)])
+def test_knn_small_clouds(ops, oracle_built, B, Ns, Nq, K):
+    """The lane-group kernel the down-sampled levels and the decoder of a 2 500-point cloud run on (Ns <= 2048)."""
+    rng = np.random.RandomState(Ns + K)
+    s = rng.rand(B, Ns, 3).astype(np.float32)
+    s[::2] = np.round(s[::2] * 16) / 16          # heavy ties and duplicates
+    same = Ns == Nq
+    q = s if same else rng.rand(B, Nq, 3).astype(np.float32)
+    out = _run(ops, s, q, K, same=same)
+    oi, od = oracle_built.knn_exact(s, q, K)
+    assert np.array_equal(out["dist_sq"], od)
+    assert np.array_equal(out["idx64"], oi)
+    assert np.array_equal(out["idx32"], oi.astype(np.int32))
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
