@@ -108,6 +108,57 @@ __global__ void __launch_bounds__(kBnmThreads) bnm_bwd_moments_kernel(const floa
     if (k == 0) dS[i] = s / R;
 }
 
+// Parameter gradients of mlp_rpe1 (train mode) in one launch: G (cout, ldg) fp64 holds, per output channel, the sums
+// over all (point, neighbour) rows of du (x) x in columns 0..cin-1 and of du in column cin (accumulated by the fused
+// LocSE backward kernels of BOTH halves of the block, u = a (W x) + c).  With ga = sum_i W_i G_i (gradient at a),
+// gc = G[cin] (gradient at c) this is bnm_bwd_kernel plus the direct term a G:  dW = a G + (BatchNorm terms).
+__global__ void __launch_bounds__(kBnmThreads) bnm_rpe1_grads_kernel(
+    const float* __restrict__ W, int cin, const double* __restrict__ S, int s_stride, const double* __restrict__ M,
+    int ldm, double R, const float* __restrict__ gamma, const double* __restrict__ save, const double* __restrict__ G,
+    int ldg, float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta, int cout) {
+    __shared__ double red[kBnmThreads / 32];
+    const int j = blockIdx.x, i = threadIdx.x;
+    const float* w = W + (size_t)j * cin;
+    const double* g = G + (size_t)j * ldg;
+    const double ga = block_sum(i < cin ? (double)w[i] * g[i] : 0.0, red);
+    const double wmu = save[j], rstd = save[2 * cout + j], a = save[3 * cout + j];
+    const double gc_j = g[cin];
+    const double ga1 = ga - gc_j * wmu;
+    const double gvar = ga1 * (double)gamma[j] * (-0.5) * rstd * rstd * rstd;
+    const double gq = gvar / R;
+    const double gwmu = -gc_j * a - 2.0 * wmu * gvar;
+    if (i < cin) {
+        double t = 0.0;
+        for (int k = 0; k < cin; ++k) t += (M[(size_t)i * ldm + k] + M[(size_t)k * ldm + i]) * (double)w[k];
+        dW[(size_t)j * cin + i] = (float)(a * g[i] + gq * t + gwmu * S[(size_t)i * s_stride] / R);
+    }
+    if (i == 0) {
+        dgamma[j] = (float)(ga1 * rstd);
+        dbeta[j] = (float)gc_j;
+    }
+}
+
+// Coefficients of the second BatchNorm-backward pass of mlp_rpe2 (r3d_lfa_bn2_bwd) from the batch sums of pass 1:
+// sums (2,h) fp64 = (sum du2, sum du2 r2), r2 = relu(a2 z2 + c2) the forward's activations, save (5,h) the forward's
+// statistics (bnm_fwd_kernel).  sum du2 zhat2 = rstd ((sum du2 r2 - c2 sum du2) / a2 - mean sum du2)  (du2 != 0 only
+// where r2 = a2 z2 + c2).  bn2 (5,h) fp32 = a2, mean, rstd, mean du2, mean du2 zhat2;  dgamma = sum du2 zhat2, dbeta = sum du2.
+__global__ void bn2_coeffs_kernel(const double* __restrict__ sums, const float* __restrict__ a2, const float* __restrict__ c2,
+                                  const double* __restrict__ save, double rows, int h, float* __restrict__ bn2,
+                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    const double a = (double)a2[i], c = (double)c2[i], mu = save[i], rs = save[2 * h + i];
+    const double s_du = sums[i], s_dur = sums[h + i];
+    const double s_duz = a == 0.0 ? 0.0 : rs * ((s_dur - c * s_du) / a - mu * s_du);
+    bn2[i] = (float)a;
+    bn2[h + i] = (float)mu;
+    bn2[2 * h + i] = (float)rs;
+    bn2[3 * h + i] = (float)(s_du / rows);
+    bn2[4 * h + i] = (float)(s_duz / rows);
+    dgamma[i] = (float)s_duz;
+    dbeta[i] = (float)s_du;
+}
+
 }  // namespace r3d
 
 using namespace r3d;
@@ -142,5 +193,27 @@ extern "C" int r3d_bn_from_moments_bwd(const float* W, int cout, int cin, const 
         bnm_bwd_moments_kernel<<<cin, kBnmThreads, 0, st>>>(W, cin, cout, R, scal, dM, dS);
         R3D_LAUNCH_CHECK("bnm_bwd_moments_kernel");
     }
+    return R3D_OK;
+}
+
+extern "C" int r3d_lfa_rpe1_grads(const float* W, int cout, int cin, const double* S, int s_stride, const double* M,
+                                  int ldm, double R, const float* gamma, const double* save, const double* G, int ldg,
+                                  float* dW, float* dgamma, float* dbeta, r3d_stream_t stream) {
+    if (cout <= 0 || cin <= 0 || ldg <= cin || !(R > 0.0)) return R3D_EINVAL;
+    if (cin > kBnmMaxCin) return R3D_EUNSUPPORTED;
+    if (!W || !S || !M || !gamma || !save || !G || !dW || !dgamma || !dbeta) return R3D_EINVAL;
+    bnm_rpe1_grads_kernel<<<cout, kBnmThreads, 0, static_cast<cudaStream_t>(stream)>>>(W, cin, S, s_stride, M, ldm, R, gamma,
+                                                                                      save, G, ldg, dW, dgamma, dbeta, cout);
+    R3D_LAUNCH_CHECK("bnm_rpe1_grads_kernel");
+    return R3D_OK;
+}
+
+extern "C" int r3d_lfa_bn2_coeffs(const double* sums, const float* a2, const float* c2, const double* save, double rows,
+                                  int h, float* bn2, float* dgamma, float* dbeta, r3d_stream_t stream) {
+    if (h <= 0 || !(rows > 0.0)) return R3D_EINVAL;
+    if (!sums || !a2 || !c2 || !save || !bn2 || !dgamma || !dbeta) return R3D_EINVAL;
+    bn2_coeffs_kernel<<<ceil_div(h, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, a2, c2, save, rows, h, bn2,
+                                                                                      dgamma, dbeta);
+    R3D_LAUNCH_CHECK("bn2_coeffs_kernel");
     return R3D_OK;
 }

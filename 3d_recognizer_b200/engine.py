@@ -219,43 +219,70 @@ class _LfaPoolFn(torch.autograd.Function):
         return (None, None, None, dfeat, dws, dw1, da1, dc1, dw2, da2, dc2) + (None,) * 6
 
 
+class _LfaPool1TrainFn(torch.autograd.Function):
+    """Stage 1 of an LFA block in TRAINING mode: rpe -> r1 = relu(BN_batch(W1 rpe)) -> PFA gather of f -> attentive
+    pooling, with mlp_rpe1's BatchNorm expressed through the moments of the encoding (ops.bn_from_moments).
+    Differentiable inputs: feat, ws, and mlp_rpe1's parameters w1 (conv weight), gamma1, beta1.  The gradient of
+    mlp_rpe1 collects contributions from BOTH halves of the block (r1 also feeds mlp_rpe2): the kernels of both
+    accumulate du1 (x) [rpe, 1] into the shared fp64 buffer ``g1`` (stage 2's backward always runs first: its
+    input p1 is computed from this function's output), and this backward turns the total into (dW1, dgamma1,
+    dbeta1) with one kernel (ops.lfa_rpe1_grads).  The fp64 accumulation matters: the direct term and the
+    BatchNorm-statistics term are ~1e3 times larger than their sum with un-centred inputs (measured at N=16384:
+    8e-4 relative in fp32, 3e-6 in fp64)."""
+
+    @staticmethod
+    def forward(ctx, xyz, idx32, feat, ws, w1, gamma1, beta1, w1f, a1f, c1f, m, save1, g1, count):
+        wsT = ws.t().contiguous()
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+            pooled = ops.lfa_pool_tc(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, ws.contiguous())
+        else:
+            pooled = ops.lfa_pool(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, wsT)
+        ctx.count = count
+        ctx.w1_shape = w1.shape
+        ctx.save_for_backward(xyz, idx32, feat, ws, wsT, gamma1, w1f, a1f, c1f, m, save1, g1)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        xyz, idx32, feat, ws, wsT, gamma1, w1f, a1f, c1f, m, save1, g1 = ctx.saved_tensors
+        dfeat, dws, _, _, _ = ops.lfa_pool_bwd(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, None, wsT,
+                                               ws.contiguous(), dpooled, g1_acc=g1)
+        dw1, dgamma1, dbeta1 = ops.lfa_rpe1_grads(w1f, m[10], m, ctx.count, gamma1.detach().contiguous(), save1, g1)
+        return (None, None, dfeat, dws, dw1.view(ctx.w1_shape), dgamma1, dbeta1) + (None,) * 7
+
+
 class _LfaPool2TrainFn(torch.autograd.Function):
     """Stage 2 of an LFA block in TRAINING mode: r2 = relu(BN_batch(W2 r1)), PFA gather of p1, attentive pooling.
     Forward = the same fused kernel as _LfaPoolFn; backward = the standard two BatchNorm passes
-    (ops.lfa_pool2_bwd_train: everything down to du2 and the batch sums; ops.lfa_bn2_bwd: dz2, dW2, dr1, du1, G1).
-    Differentiable inputs: feat (= p1), ws, gamma2, beta2, w2 (fp32 parameters) and the fp64 edges w1, a1, c1 of
-    mlp_rpe1 (see _LfaPoolFn).  a2f/c2f/mean2/rstd2 are this step's batch statistics (constants here: their
-    dependence on w2 and r1 IS the BatchNorm backward that pass 2 carries out)."""
+    (ops.lfa_pool2_bwd_train: everything down to du2 and the batch sums; ops.lfa_bn2_coeffs: the per-channel
+    coefficients; ops.lfa_bn2_bwd: dz2, dW2, dr1, du1, and du1 (x) [rpe, 1] added to the block's shared ``g1``
+    accumulator, see _LfaPool1TrainFn).  Differentiable inputs: feat (= p1), ws, w2 (conv weight), gamma2, beta2.
+    a2f/c2f/save2 are this step's batch statistics (constants here: their dependence on w2 and r1 IS the BatchNorm
+    backward that pass 2 carries out)."""
 
     @staticmethod
-    def forward(ctx, xyz, idx32, feat, ws, w2, gamma2, beta2, w1, a1, c1, w1f, a1f, c1f, a2f, c2f, mean2, rstd2):
-        w2f = w2.detach().contiguous()
+    def forward(ctx, xyz, idx32, feat, ws, w2, gamma2, beta2, w1f, a1f, c1f, a2f, c2f, save2, g1):
+        h = w1f.shape[0]
+        w2f = w2.detach().view(h, h)
         w2T = w2f.t().contiguous()
         wsT = ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
             pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f, a2f, c2f, ws.contiguous())
         else:
             pooled = ops.lfa_pool(2, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT)
-        ctx.save_for_backward(xyz, idx32, feat, ws, w1, a1, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, mean2, rstd2)
+        ctx.w2_shape = w2.shape
+        ctx.save_for_backward(xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1)
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
-        xyz, idx32, feat, ws, w1, a1, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, mean2, rstd2 = ctx.saved_tensors
+        xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1 = ctx.saved_tensors
         h = w1f.shape[0]
         dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,
                                                         ws.contiguous(), dpooled)
-        rows = float(idx32.numel())
-        s_du, s_dur = sums[0], sums[1]
-        a2, c2, mu2, rs2 = a2f.double(), c2f.double(), mean2.double(), rstd2.double()
-        # sum du2 * zhat2 with zhat2 = (z2 - mean2) rstd2 and z2 = (r2 - c2) / a2 wherever du2 != 0
-        safe_a2 = torch.where(a2 == 0, torch.ones_like(a2), a2)
-        s_duz = torch.where(a2 == 0, torch.zeros_like(a2), rs2 * ((s_dur - c2 * s_du) / safe_a2 - mu2 * s_du))
-        bn2 = torch.stack((a2, mu2, rs2, s_du / rows, s_duz / rows)).float().contiguous()
-        g1, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h)
-        gm = g1[:, :10]
-        dw1, da1, dc1 = a1.unsqueeze(1) * gm, (w1 * gm).sum(dim=1), g1[:, 10]
-        return (None, None, dfeat, dws, dw2.float(), s_duz.float(), s_du.float(), dw1, da1, dc1) + (None,) * 7
+        bn2, dgamma2, dbeta2 = ops.lfa_bn2_coeffs(sums, a2f, c2f, save2, float(idx32.numel()))
+        _, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h, g1_acc=g1)
+        return (None, None, dfeat, dws, dw2.float().view(ctx.w2_shape), dgamma2, dbeta2) + (None,) * 7
 
 
 class _R1MomentsFn(torch.autograd.Function):
@@ -318,32 +345,32 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     w1f = r1m.conv.weight.detach().view(-1, 10)
     h = w1f.shape[0]
     w2f = r2m.conv.weight.detach().view(h, h)
-    w1 = r1m.conv.weight.view(h, 10).double()        # fp64 autograd edges (see _LfaPoolFn)
-    w2 = r2m.conv.weight.view(h, h).double()
     d = 2 * h
-    training = r1m.batch_norm.training
-    if training:
-        m = ops.lfa_moments(0, xyz, idx, d)                      # (16,16) fp64, no parameters involved
-        count = float(xyz.shape[0] * xyz.shape[1] * K)
-        a1, c1 = _BnFromMomentsFn.apply(w1, w1f, r1m.batch_norm.weight, r1m.batch_norm.bias, m[10], m,
-                                        r1m.batch_norm, r1m.conv.bias, count)
-    else:
-        a1, c1 = (t.double() for t in _eval_affine(r1m))
-    a1f, c1f = a1.detach().float(), c1.detach().float()
     ws1, ws2 = lfa.pool1.score_fn[0].weight, lfa.pool2.score_fn[0].weight
-    pooled1 = _LfaPoolFn.apply(1, xyz, idx, f, ws1, w1, a1, c1, None, None, None, w1f, a1f, c1f, None, None, None)
-    p1 = shared_mlp(lfa.pool1.mlp, pooled1)
-    if training:
-        # batch statistics of mlp_rpe2 from the moments of r1 (forward only; the backward is the explicit two-pass
-        # BatchNorm backward inside _LfaPool2TrainFn)
+    if r1m.batch_norm.training:
+        # batch statistics of mlp_rpe1 / mlp_rpe2 from the moments of their inputs (no (B,N,K,h) tensor is ever
+        # materialised); everything between the parameters and the pooled features is inside the two functions
+        bn1, bn2 = r1m.batch_norm, r2m.batch_norm
+        count = float(xyz.shape[0] * xyz.shape[1] * K)
+        g1 = ops.zeros((h, 16), torch.float64, xyz.device)       # mlp_rpe1's gradient accumulator, both halves
+        with torch.no_grad():
+            m = ops.lfa_moments(0, xyz, idx, d)                   # (16,16) fp64, no parameters involved
+            a1f, c1f, save1 = ops.bn_from_moments(w1f, m[10], m, count, bn1, r1m.conv.bias)
+        pooled1 = _LfaPool1TrainFn.apply(xyz, idx, f, ws1, r1m.conv.weight, bn1.weight, bn1.bias, w1f, a1f, c1f, m,
+                                         save1, g1, count)
+        p1 = shared_mlp(lfa.pool1.mlp, pooled1)
         with torch.no_grad():
             m_r1, s_r1 = ops.lfa_moments(1, xyz, idx, d, w1f, a1f, c1f)
-            a2f, c2f, save2 = ops.bn_from_moments(w2f.contiguous(), s_r1[:, 10].contiguous(), m_r1, count,
-                                                  r2m.batch_norm, r2m.conv.bias)
-        pooled2 = _LfaPool2TrainFn.apply(xyz, idx, p1, ws2, r2m.conv.weight.view(h, h), r2m.batch_norm.weight,
-                                         r2m.batch_norm.bias, w1, a1, c1, w1f, a1f, c1f, a2f, c2f,
-                                         save2[0].float(), save2[2].float())
+            a2f, c2f, save2 = ops.bn_from_moments(w2f, s_r1[:, 10], m_r1, count, bn2, r2m.conv.bias)
+        pooled2 = _LfaPool2TrainFn.apply(xyz, idx, p1, ws2, r2m.conv.weight, bn2.weight, bn2.bias, w1f, a1f, c1f,
+                                         a2f, c2f, save2, g1)
     else:
+        w1 = r1m.conv.weight.view(h, 10).double()        # fp64 autograd edges (see _LfaPoolFn)
+        w2 = r2m.conv.weight.view(h, h).double()
+        a1, c1 = (t.double() for t in _eval_affine(r1m))
+        a1f, c1f = a1.detach().float(), c1.detach().float()
+        pooled1 = _LfaPoolFn.apply(1, xyz, idx, f, ws1, w1, a1, c1, None, None, None, w1f, a1f, c1f, None, None, None)
+        p1 = shared_mlp(lfa.pool1.mlp, pooled1)
         a2, c2 = (t.double() for t in _eval_affine(r2m))
         a2f, c2f = a2.detach().float(), c2.detach().float()
         pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, ws2, w1, a1, c1, w2, a2, c2, w1f, a1f, c1f, w2f, a2f, c2f)

@@ -305,9 +305,10 @@ def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_rpe2s, w_scoreT,
-                 w_score, dpooled):
+                 w_score, dpooled, g1_acc=None):
     """Backward of ``lfa_pool`` (C ABI ``r3d_lfa_pool_bwd``).  Returns (dfeat (B,N,h), dw_score (d,d)
-    [out][in], g1 (h,16) fp64, g2m (h,h) fp64 | None, g2c (h,16) fp64 | None) — see include/r3d_b200.h."""
+    [out][in], g1 (h,16) fp64, g2m (h,h) fp64 | None, g2c (h,16) fp64 | None) — see include/r3d_b200.h.
+    ``g1_acc``: an (h,16) fp64 buffer to accumulate g1 INTO (the block's two halves share one)."""
     xyz, xs = _cloud_view(xyz)
     feat, fs = _rows_view(feat.detach())
     B, N, K = idx32.shape
@@ -322,7 +323,7 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
     dfeat = acc[:n_df].view(B, N, h)
     dws = acc[n_df:].view(d, d)
     acc64 = zeros(h * 16 + (h * h + h * 16 if stage == 2 else 0), torch.float64, dev)
-    g1 = acc64[:h * 16].view(h, 16)
+    g1 = acc64[:h * 16].view(h, 16) if g1_acc is None else g1_acc
     g2m = g2c = None
     if stage == 2:
         g2m = acc64[h * 16:h * 16 + h * h].view(h, h)
@@ -443,14 +444,15 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     return dfeat, dws, du2, sums
 
 
-def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, bn2, h: int):
-    """Pass 2 (C ABI ``r3d_lfa_bn2_bwd``): -> (g1 (h,16) fp64, dw2 (h,h) fp64)."""
+def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, bn2, h: int, g1_acc=None):
+    """Pass 2 (C ABI ``r3d_lfa_bn2_bwd``): -> (g1 (h,16) fp64, dw2 (h,h) fp64).  ``g1_acc``: accumulate g1 into this
+    (h,16) fp64 buffer instead of a fresh one."""
     xyz, xs = _cloud_view(xyz)
     B, N, K = idx32.shape
     d = 2 * h
     dev = xyz.device
     buf = zeros(h * 16 + h * h, torch.float64, dev)
-    g1, dw2 = buf[:h * 16].view(h, 16), buf[h * 16:].view(h, h)
+    g1, dw2 = (buf[:h * 16].view(h, 16) if g1_acc is None else g1_acc), buf[h * 16:].view(h, h)
     flops = float(B) * N * K * 2 * (10 * h + 3 * h * h + 16 * h)
     nbytes = float(B) * N * (12 + 4 * K + 4 * K * h)
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_bn2_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -460,3 +462,34 @@ def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, 
                                          _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_lfa_bn2_bwd")
     return g1, dw2
+
+
+def lfa_rpe1_grads(w, s, m, count: float, gamma, save, g1):
+    """mlp_rpe1's parameter gradients from the block's g1 accumulator (C ABI ``r3d_lfa_rpe1_grads``):
+    w (h,cin) fp32, s / m the moments given to ``bn_from_moments``, save its scratch, g1 (h,16) fp64.
+    Returns (dW (h,cin), dgamma (h), dbeta (h)) fp32."""
+    cout, cin = w.shape
+    dev = w.device
+    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+    dgb = torch.empty((2, cout), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_rpe1_grads[{cout}x{cin}]", flops=4.0 * cout * cin * cin,
+                                                    bytes=8.0 * cin * cin):
+        rc = _cabi.lib().r3d_lfa_rpe1_grads(_cabi.ptr(w), cout, cin, _cabi.raw(s), s.stride(0), _cabi.raw(m), m.stride(0),
+                                            float(count), _cabi.ptr(gamma), _cabi.ptr(save), _cabi.ptr(g1), g1.stride(0),
+                                            _cabi.ptr(dw), _cabi.raw(dgb[0]), _cabi.raw(dgb[1]), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_rpe1_grads")
+    return dw, dgb[0], dgb[1]
+
+
+def lfa_bn2_coeffs(sums, a2, c2, save, rows: float):
+    """Coefficients of ``lfa_bn2_bwd`` and mlp_rpe2's (dgamma, dbeta) from pass 1's sums (C ABI ``r3d_lfa_bn2_coeffs``).
+    Returns (bn2 (5,h) fp32, dgamma (h), dbeta (h))."""
+    h = a2.shape[0]
+    dev = a2.device
+    bn2 = torch.empty((5, h), dtype=torch.float32, device=dev)
+    dgb = torch.empty((2, h), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_bn2_coeffs[{h}]", flops=16.0 * h, bytes=64.0 * h):
+        rc = _cabi.lib().r3d_lfa_bn2_coeffs(_cabi.ptr(sums), _cabi.ptr(a2), _cabi.ptr(c2), _cabi.ptr(save), float(rows), h,
+                                            _cabi.ptr(bn2), _cabi.raw(dgb[0]), _cabi.raw(dgb[1]), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_bn2_coeffs")
+    return bn2, dgb[0], dgb[1]

@@ -336,6 +336,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="training step eager instead of CUDA-graph replay")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="run only P eager steps between cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
+                         "prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     name = args.workload
@@ -438,6 +441,19 @@ def main():
                 torch.cuda.synchronize()
 
             h2d, d2h = batch * n * 12, batch * n * 2 * 4
+
+    if args.profile_steps:
+        step = eager_step or dev_step
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(args.profile_steps):
+            step(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_steps": args.profile_steps, "workload": name}))
+        return
 
     # ---- eager instrumented pass: per-kernel CUDA events (C-ABI wrappers) and launch counting
     eager = eager_step or dev_step

@@ -192,6 +192,20 @@ int r3d_bn_from_moments_bwd(const float* W, int cout, int cin, const double* S, 
                             const double* gc, double* dW, float* dgamma, float* dbeta, double* scal, double* dM,
                             double* dS, r3d_stream_t stream);
 
+/* mlp_rpe1's parameter gradients in one launch (train mode): G (cout, ldg > cin) fp64 = per output channel the sums
+ * over all (point, neighbour) rows of du (x) x (columns 0..cin-1) and of du (column cin), as accumulated by
+ * r3d_lfa_pool_bwd / r3d_lfa_bn2_bwd of BOTH halves of a block into one g1 buffer; S, M, R, gamma, save as in
+ * r3d_bn_from_moments.  dW (cout,cin) = a G + BatchNorm terms, dgamma, dbeta: fp32.  Replaces the tensor-op
+ * composition of modules.py:60-104 backward for mlp_rpe1 (autograd of Conv2d + BatchNorm2d over B*N*K rows). */
+int r3d_lfa_rpe1_grads(const float* W, int cout, int cin, const double* S, int s_stride, const double* M, int ldm,
+                       double R, const float* gamma, const double* save, const double* G, int ldg, float* dW,
+                       float* dgamma, float* dbeta, r3d_stream_t stream);
+/* Coefficients of r3d_lfa_bn2_bwd from pass 1's batch sums: sums (2,h) fp64 (r3d_lfa_pool2_bwd_train), a2, c2 the
+ * forward's fp32 affine, save (5,h) fp64 the forward's statistics (r3d_bn_from_moments), rows = B*N*K.
+ * bn2 (5,h) fp32 = a2, mean, rstd, mean du2, mean du2*zhat2;  dgamma = sum du2*zhat2, dbeta = sum du2 (mlp_rpe2's). */
+int r3d_lfa_bn2_coeffs(const double* sums, const float* a2, const float* c2, const double* save, double rows, int h,
+                       float* bn2, float* dgamma, float* dbeta, r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,
