@@ -203,10 +203,9 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
 // list of the small-cloud training step showed the unpipelined kernel at 61 us per launch (24 % of the step):
 // 16..64 chunks of load -> barrier -> 16 k-steps -> barrier on a handful of CTAs.
 // RT = register tile edge (8: 8x8 per thread; 4: 4x4 per thread, more threads/CTAs for small row counts).
-template <int TM, int TN, int RT>
+template <int TM, int TN, int RT, int KC = kPwKC>
 __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwArgs a) {
     constexpr int NT = (TM / RT) * (TN / RT);
-    constexpr int KC = kPwKC;
     constexpr int TMP = TM + 4;
     constexpr int A_PER = TM * (KC / 4) / NT;
     constexpr int W_PER = KC * TN / 4 / NT;
@@ -553,6 +552,18 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     if (!aligned) {
         dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
         pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
+    } else if (M <= 2048 && ca + cb >= 128) {
+        // a few hundred rows of a wide layer (the bottom of the encoder / decoder of a small cloud): the kernel is a
+        // chain of load -> barrier -> FMA steps on a handful of CTAs, each step exposed to the full L2 latency.
+        // 32-channel steps halve the chain, 32-row tiles put 2-4x more CTAs on the machine.
+        const long long tiles32 = ((M + 31) / 32) * ((cout + 31) / 32);
+        if (tiles32 <= 2 * kNumSMs) {
+            dim3 grid((unsigned)((M + 31) / 32), (cout + 31) / 32);
+            pw_gemm_fast_kernel<32, 32, 4, 32><<<grid, 64, 0, st>>>(a);
+        } else {
+            dim3 grid((unsigned)((M + 31) / 32), (cout + 63) / 64);
+            pw_gemm_fast_kernel<32, 64, 4, 32><<<grid, 128, 0, st>>>(a);
+        }
     } else if (M <= 64 * 4 * kNumSMs / ((cout + 63) / 64)) {
         // few rows: 64x64 tiles of 256 threads (4x4 per thread) put more CTAs and warps on the machine
         dim3 grid((unsigned)((M + 63) / 64), (cout + 63) / 64);

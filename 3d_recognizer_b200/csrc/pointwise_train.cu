@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(256) rowreduce_gemm_thin_kernel(const float* _
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
     for (long long r = gw; r < M; r += nw) {
         const float w = lane < Nw ? Wd[r * Nw + lane] : 0.f;
 #pragma unroll
@@ -466,7 +467,7 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
     if (!A || !Bm || !out) return R3D_EINVAL;
     if (ld_out == 0) ld_out = Cb;
     if ((Ca <= 8 && Cb <= 32) || (Cb <= 8 && Ca <= 32)) {
-        long long blocks = (M + 8 * 64 - 1) / (8 * 64);           // >= 64 rows per warp
+        long long blocks = (M + 8 * 8 - 1) / (8 * 8);             // >= 8 rows per warp: the row loop is latency-bound
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
         if (blocks < 1) blocks = 1;
         rowreduce_gemm_thin_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, out,
@@ -480,7 +481,7 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
     const int ga = ceil_div(Ca, tile), gb = ceil_div(Cb, tile);
     // enough row chunks to fill the machine, at least 128 rows each
     long long chunks = ((long long)kNumSMs * (big ? 2 : 4) + ga * gb - 1) / (ga * gb);
-    const long long max_chunks = (M + 127) / 128;
+    const long long max_chunks = (M + 2 * kRrKC2 - 1) / (2 * kRrKC2);   // at least 64 rows per CTA
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     if (chunks > 65535) chunks = 65535;
