@@ -548,7 +548,7 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
         return R3D_OK;
     }
     const bool aligned = (ca % 4 == 0) && (cb % 4 == 0);
-    if (g_pw_tensor_cores.load() && pw_tc_eligible(a)) return pw_tc_launch(a, st);
+    if (g_pw_tensor_cores.load() && pw_tc_eligible(a, g_pw_tensor_cores.load() == 2)) return pw_tc_launch(a, st);
     if (!aligned) {
         dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
         pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
@@ -582,9 +582,10 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     return R3D_OK;
 }
 
-// 1 (default): wide layers (C_in >= 32, C_out a multiple of 32) run on the tcgen05 3xTF32 kernel; 0: FP32 CUDA-core
-// kernels everywhere.  Returns the previous value.
+// 1 (default): the layers the tcgen05 3xTF32 kernel is measured to win on (pw_tc_eligible) run there; 0: FP32
+// CUDA-core kernels everywhere; 2: every layer the tensor-core kernel supports (C_in >= 32, C_out a multiple of 32,
+// >= 4096 rows) -- benchmarks and tests.  Returns the previous value.
 extern "C" int r3d_pointwise_set_tensor_cores(int on) {
-    if (on != 0 && on != 1) return g_pw_tensor_cores.load();
+    if (on < 0 || on > 2) return g_pw_tensor_cores.load();
     return g_pw_tensor_cores.exchange(on);
 }

@@ -44,7 +44,7 @@ __device__ __forceinline__ const float* src_row(const PwArgs& a, int b, int n, b
 }
 
 // pointwise_tc.cu: true if the tensor-core kernel can take this layer
-bool pw_tc_eligible(const PwArgs& a);
+bool pw_tc_eligible(const PwArgs& a, bool force);
 int pw_tc_launch(const PwArgs& a, cudaStream_t st);
 
 }  // namespace r3d

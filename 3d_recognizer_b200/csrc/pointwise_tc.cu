@@ -188,14 +188,20 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(PwArgs a, int tmem_cols) {
     if (warp == 0) tmem_dealloc_warp(tmem, (uint32_t)tmem_cols);
 }
 
-// Layers with few rows stay on the FP32 kernels: they are latency-bound (nothing for the tensor core to win), and a
-// train-mode BatchNorm over a handful of rows (eps 1e-6) amplifies the ~2e-6 error of the tensor-core accumulation
-// a thousandfold on near-constant channels (measured: 5e-3 on the bottleneck's dgamma at 20 rows).
-constexpr long long kPwTcMinRows = 4096;
+// Where the tensor-core kernel wins (tools/pointwise_bench.py, profiles/r01_pointwise_tc_vs_fp32.txt): every CTA
+// re-splits its W block into TF32 hi/lo and runs a two-stage load -> split -> MMA chain, so it needs (a) enough rows
+// to fill the machine several times over and (b) either a long contraction (C_in >= 256: 59 vs 39 TFLOP/s at
+// 512 -> 256) or a narrow output (C_out <= 32, where the FP32 kernel is HBM/latency-bound); mid-size layers
+// (64 -> 128, 128 -> 256) stay on the FP32 kernels, which are 15-25 % faster there.  Few-row layers stay on FP32 in
+// any case: they are latency-bound, and a train-mode BatchNorm over a handful of rows (eps 1e-6) amplifies the
+// ~2e-6 error of the tensor-core accumulation a thousandfold on near-constant channels (measured: 5e-3 on the
+// bottleneck's dgamma at 20 rows).
+constexpr long long kPwTcMinRows = 32768;
 
-bool pw_tc_eligible(const PwArgs& a) {
+bool pw_tc_eligible(const PwArgs& a, bool force) {
     const int Kc = a.ca + a.cb;
-    if ((long long)a.B * a.n < kPwTcMinRows) return false;
+    if ((long long)a.B * a.n < (force ? 4096 : kPwTcMinRows)) return false;
+    if (!force && !(Kc >= 256 || a.cout <= 32)) return false;
     return (a.ca % 4 == 0) && (a.cb % 4 == 0) && Kc >= 32 && a.cout >= 32 && (a.cout % 32) == 0 && !a.transpose_out &&
            (a.y_ld % 4) == 0 && (a.y_bstride % 4) == 0;
 }

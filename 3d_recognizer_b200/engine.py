@@ -14,6 +14,7 @@ Two execution paths share this file:
 
 Neither path runs on the CPU; ``ops`` raises if a tensor is not on a CUDA device.
 """
+import os
 from typing import List, Tuple
 
 import numpy as np
@@ -55,6 +56,39 @@ def batch_norm_lastdim(bn: torch.nn.BatchNorm2d, y: torch.Tensor) -> torch.Tenso
     return out.view_as(y)
 
 
+_SIDE_STREAMS = {}
+OVERLAP_WEIGHT_GRADS = os.environ.get("R3D_NO_OVERLAP") is None
+
+
+class _fork:
+    """Runs the enclosed launches on a side stream of the current device, ordered after everything queued on the
+    current stream so far; ``join()`` makes the current stream wait for them.  The per-point layers of a small cloud
+    are latency-bound kernels on a handful of SMs each: the weight-gradient row reduction and the input-gradient
+    GEMM of a layer are independent and overlap almost perfectly (also inside a CUDA-graph capture, where the fork
+    and join become graph edges)."""
+
+    def __init__(self, device):
+        self.cur = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+        self.side = _SIDE_STREAMS[key]
+        self.ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        self.cur.wait_stream(self.side)
+
+
 class _SharedMLPTrainFn(torch.autograd.Function):
     """SharedMLP with train-mode BatchNorm on dense rows x (M,Cin): the sm_100a per-point kernels forward
     (GEMM + batch statistics, normalise + activation) and backward (BatchNorm backward, dx GEMM, dW row-reduction)."""
@@ -76,8 +110,14 @@ class _SharedMLPTrainFn(torch.autograd.Function):
         x, w, z, save, beta, scratch = ctx.saved_tensors
         cout = w.shape[0]
         dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope, stats2=scratch[2 * cout:])
-        dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
-        dw = ops.rowreduce_gemm(dz, x)
+        if OVERLAP_WEIGHT_GRADS and ctx.needs_input_grad[0]:
+            with _fork(dz.device) as f:
+                dw = ops.rowreduce_gemm(dz, x)
+            dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0)
+            f.join()
+        else:
+            dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
+            dw = ops.rowreduce_gemm(dz, x)
         # the conv bias cancels against the batch mean: its gradient is exactly zero and is reported as None (the
         # optimiser then leaves the parameter alone, which is what a zero gradient does)
         return dx, dw, None, dgamma, dbeta, None, None, None

@@ -46,9 +46,11 @@ def mods():
     (2, 999, 128, 0, 64, "relu", None, False), (4, 39, 512, 0, 512, "relu", None, False),
     (2, 333, 8, 0, 64, "relu", "shared", False), (1, 77, 64, 0, 32, "relu", None, False),
     (2, 100, 5, 0, 8, "lrelu", "shared", False),
-    # >= 4096 rows: wide layers take the tcgen05 path
     (2, 2560, 512, 512, 256, "relu", "per_cloud", False), (4, 1100, 128, 0, 512, "relu", None, False),
     (1, 5000, 64, 32, 128, "lrelu", "shared", False), (2, 4096, 32, 0, 64, None, None, False),
+    # >= 32768 rows with a long contraction or a narrow output: the tcgen05 path (pw_tc_eligible)
+    (2, 16384, 512, 512, 256, "relu", "per_cloud", False), (4, 8200, 256, 0, 32, "relu", None, False),
+    (1, 33000, 64, 32, 32, "lrelu", "shared", False), (3, 11000, 128, 128, 512, None, None, False),
 ])
 def test_pointwise_vs_torch(mods, B, n, ca, cb, cout, act, gather, tr):
     _, _, ops = mods
