@@ -67,9 +67,11 @@ class _fork:
     GEMM of a layer are independent and overlap almost perfectly (also inside a CUDA-graph capture, where the fork
     and join become graph edges)."""
 
-    def __init__(self, device):
+    def __init__(self, device, lane: int = 0):
         self.cur = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device())
+        # lane 0: short forks joined within the same function; lane 1: forks that stay open across several launches
+        # of the main stream (a shared stream would serialise the short forks behind the long one)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), lane)
         if key not in _SIDE_STREAMS:
             _SIDE_STREAMS[key] = torch.cuda.Stream(device)
         self.side = _SIDE_STREAMS[key]
@@ -271,7 +273,8 @@ class _LfaPool1TrainFn(torch.autograd.Function):
     8e-4 relative in fp32, 3e-6 in fp64)."""
 
     @staticmethod
-    def forward(ctx, xyz, idx32, feat, ws, w1, gamma1, beta1, w1f, a1f, c1f, m, save1, g1, count):
+    def forward(ctx, xyz, idx32, feat, ws, w1, gamma1, beta1, w2, gamma2, beta2, w1f, a1f, c1f, m, save1, g1, count,
+                shared):
         wsT = ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
             pooled = ops.lfa_pool_tc(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, ws.contiguous())
@@ -279,6 +282,7 @@ class _LfaPool1TrainFn(torch.autograd.Function):
             pooled = ops.lfa_pool(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, wsT)
         ctx.count = count
         ctx.w1_shape = w1.shape
+        ctx.shared = shared
         ctx.save_for_backward(xyz, idx32, feat, ws, wsT, gamma1, w1f, a1f, c1f, m, save1, g1)
         return pooled
 
@@ -287,8 +291,12 @@ class _LfaPool1TrainFn(torch.autograd.Function):
         xyz, idx32, feat, ws, wsT, gamma1, w1f, a1f, c1f, m, save1, g1 = ctx.saved_tensors
         dfeat, dws, _, _, _ = ops.lfa_pool_bwd(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, None, wsT,
                                                ws.contiguous(), dpooled, g1_acc=g1)
+        # stage 2's second BatchNorm pass (side stream, see _LfaPool2TrainFn.backward) has been adding to g1 too
+        dw2, dgamma2, dbeta2, fork = ctx.shared.pop("stage2", (None, None, None, None))
+        if fork is not None:
+            fork.join()
         dw1, dgamma1, dbeta1 = ops.lfa_rpe1_grads(w1f, m[10], m, ctx.count, gamma1.detach().contiguous(), save1, g1)
-        return (None, None, dfeat, dws, dw1.view(ctx.w1_shape), dgamma1, dbeta1) + (None,) * 7
+        return (None, None, dfeat, dws, dw1.view(ctx.w1_shape), dgamma1, dbeta1, dw2, dgamma2, dbeta2) + (None,) * 8
 
 
 class _LfaPool2TrainFn(torch.autograd.Function):
@@ -301,7 +309,7 @@ class _LfaPool2TrainFn(torch.autograd.Function):
     backward that pass 2 carries out)."""
 
     @staticmethod
-    def forward(ctx, xyz, idx32, feat, ws, w2, gamma2, beta2, w1f, a1f, c1f, a2f, c2f, save2, g1):
+    def forward(ctx, xyz, idx32, feat, ws, w2, w1f, a1f, c1f, a2f, c2f, save2, g1, shared):
         h = w1f.shape[0]
         w2f = w2.detach().view(h, h)
         w2T = w2f.t().contiguous()
@@ -311,6 +319,7 @@ class _LfaPool2TrainFn(torch.autograd.Function):
         else:
             pooled = ops.lfa_pool(2, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT)
         ctx.w2_shape = w2.shape
+        ctx.shared = shared
         ctx.save_for_backward(xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1)
         return pooled
 
@@ -320,9 +329,15 @@ class _LfaPool2TrainFn(torch.autograd.Function):
         h = w1f.shape[0]
         dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,
                                                         ws.contiguous(), dpooled)
-        bn2, dgamma2, dbeta2 = ops.lfa_bn2_coeffs(sums, a2f, c2f, save2, float(idx32.numel()))
-        _, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h, g1_acc=g1)
-        return (None, None, dfeat, dws, dw2.float().view(ctx.w2_shape), dgamma2, dbeta2) + (None,) * 7
+        # The second pass only produces parameter gradients (dW2, and mlp_rpe1's through g1): it runs on the side
+        # stream, overlapping pool1.mlp's and stage 1's backward, and is joined in _LfaPool1TrainFn.backward, which
+        # also hands (dW2, dgamma2, dbeta2) to autograd (w2 is a pass-through input there).
+        with _fork(dfeat.device, lane=1) as fork:
+            bn2, dgamma2, dbeta2 = ops.lfa_bn2_coeffs(sums, a2f, c2f, save2, float(idx32.numel()))
+            _, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h, g1_acc=g1)
+            dw2 = dw2.float().view(ctx.w2_shape)
+        ctx.shared["stage2"] = (dw2, dgamma2, dbeta2, fork)
+        return (None, None, dfeat, dws) + (None,) * 9
 
 
 class _R1MomentsFn(torch.autograd.Function):
@@ -393,17 +408,21 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
         bn1, bn2 = r1m.batch_norm, r2m.batch_norm
         count = float(xyz.shape[0] * xyz.shape[1] * K)
         g1 = ops.zeros((h, 16), torch.float64, xyz.device)       # mlp_rpe1's gradient accumulator, both halves
+        shared = {}
+        # the statistics kernels of stage 2 depend on the encoding only, not on pooled1: they run on the side stream
+        # next to stage 1's pooling kernel and pool1.mlp (every kernel here fills a fraction of the SMs at this size)
         with torch.no_grad():
             m = ops.lfa_moments(0, xyz, idx, d)                   # (16,16) fp64, no parameters involved
             a1f, c1f, save1 = ops.bn_from_moments(w1f, m[10], m, count, bn1, r1m.conv.bias)
-        pooled1 = _LfaPool1TrainFn.apply(xyz, idx, f, ws1, r1m.conv.weight, bn1.weight, bn1.bias, w1f, a1f, c1f, m,
-                                         save1, g1, count)
+            with _fork(xyz.device, lane=1) as fork:
+                m_r1, s_r1 = ops.lfa_moments(1, xyz, idx, d, w1f, a1f, c1f)
+                a2f, c2f, save2 = ops.bn_from_moments(w2f, s_r1[:, 10], m_r1, count, bn2, r2m.conv.bias)
+        pooled1 = _LfaPool1TrainFn.apply(xyz, idx, f, ws1, r1m.conv.weight, bn1.weight, bn1.bias, r2m.conv.weight,
+                                         bn2.weight, bn2.bias, w1f, a1f, c1f, m, save1, g1, count, shared)
         p1 = shared_mlp(lfa.pool1.mlp, pooled1)
-        with torch.no_grad():
-            m_r1, s_r1 = ops.lfa_moments(1, xyz, idx, d, w1f, a1f, c1f)
-            a2f, c2f, save2 = ops.bn_from_moments(w2f, s_r1[:, 10], m_r1, count, bn2, r2m.conv.bias)
-        pooled2 = _LfaPool2TrainFn.apply(xyz, idx, p1, ws2, r2m.conv.weight, bn2.weight, bn2.bias, w1f, a1f, c1f,
-                                         a2f, c2f, save2, g1)
+        fork.join()
+        pooled2 = _LfaPool2TrainFn.apply(xyz, idx, p1, ws2, r2m.conv.weight, w1f, a1f, c1f, a2f, c2f, save2, g1,
+                                         shared)
     else:
         w1 = r1m.conv.weight.view(h, 10).double()        # fp64 autograd edges (see _LfaPoolFn)
         w2 = r2m.conv.weight.view(h, h).double()
