@@ -204,10 +204,13 @@ def lfa_block(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
 
 
-def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch.Tensor) -> torch.Tensor:
-    """UpSampler (modules.py:343-456) on point-major features: feat (B,N1,F) -> (B,N2,F)."""
+def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch.Tensor,
+             idx: torch.Tensor = None) -> torch.Tensor:
+    """UpSampler (modules.py:343-456) on point-major features: feat (B,N1,F) -> (B,N2,F).  ``idx``: the 1-NN indices
+    (B,N2,1) int64 when the caller has searched already."""
     if approach == "nni":
-        idx = ops.knn(xyz, xyz_up, 1, idx64=True, dist=False)["idx64"]
+        if idx is None:
+            idx = ops.knn(xyz, xyz_up, 1, idx64=True, dist=False)["idx64"]
         return gather_points(feat, idx).squeeze(2)
     # "nna" reaches the inverse-distance branch too (default argument, modules.py:372 / :435)
     power = 2.0 if approach == "isdw" else 1.0
@@ -389,12 +392,19 @@ def _eval_affine(smlp):
     return a, bn.bias + (smlp.conv.bias - bn.running_mean) * a
 
 
-def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None) -> torch.Tensor:
     """LocalFeatureAggregation (modules.py:298-325) with gradients: KNN and the two fused LocSE + pooling
     halves run on the sm_100a kernels (forward AND backward); the per-point layers around them are
     differentiable tensor ops.  Works in train mode (batch statistics) and eval mode (running statistics)."""
     K = lfa._n_neighbors
-    idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
+    # the residual branch depends on the block input only: it runs on a side stream next to the whole main chain
+    # (autograd replays it on that stream too, so its backward overlaps mlp2's)
+    sc_fork = None
+    if OVERLAP_WEIGHT_GRADS and feat.is_cuda:
+        with _fork(feat.device, lane=2) as sc_fork:
+            sc = shared_mlp(lfa.shortcut, feat)
+    if idx is None:
+        idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
     f = shared_mlp(lfa.mlp1, feat)
     r1m, r2m = lfa.mlp_rpe1, lfa.mlp_rpe2
     w1f = r1m.conv.weight.detach().view(-1, 10)
@@ -434,7 +444,11 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
         a2f, c2f = a2.detach().float(), c2.detach().float()
         pooled2 = _LfaPoolFn.apply(2, xyz, idx, p1, ws2, w1, a1, c1, w2, a2, c2, w1f, a1f, c1f, w2f, a2f, c2f)
     p2 = shared_mlp(lfa.pool2.mlp, pooled2)
-    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
+    if sc_fork is not None:
+        sc_fork.join()
+    else:
+        sc = shared_mlp(lfa.shortcut, feat)
+    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + sc, 0.01)
 
 
 # LFA implementation used by forward_autograd: the fused kernels, or (tests / debugging) the plain
@@ -470,18 +484,37 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     xyz = inp[..., :3].index_select(1, perm).contiguous()
     feat = feat.index_select(1, perm)
 
+    # Every neighbour search depends on the coordinates only.  With the fused kernels the searches of the
+    # down-sampled levels and of the decoder's 1-NN up-sampling run on a side stream while level 0 is processed
+    # (each is a few-microsecond kernel on a fraction of the SMs; ~75 us of a 3 ms step on the main chain otherwise).
+    pre_fork, enc_idx, dec_idx = None, {}, {}
+    if LFA_IMPL is lfa_block_fused and OVERLAP_WEIGHT_GRADS and xyz.is_cuda and L > 1:
+        with torch.no_grad(), _fork(xyz.device, lane=3) as pre_fork:
+            sizes = [N]
+            for lvl in range(L):
+                sizes.append(sizes[-1] // dec)       # points kept after level lvl (floor, modules.py:583)
+            for lvl in range(1, L):
+                n_k = sizes[lvl]
+                K = net.encoder[lvl]._n_neighbors
+                enc_idx[lvl] = ops.knn(xyz[:, :n_k], xyz[:, :n_k], K, idx64=False, idx32=True, dist=False)["idx32"]
+            for lvl in range(L):                     # decoder stage lvl: sizes[L - lvl] -> sizes[L - lvl - 1] points
+                dec_idx[lvl] = ops.knn(xyz[:, :sizes[L - lvl]], xyz[:, :sizes[L - lvl - 1]], 1, idx64=True,
+                                       dist=False)["idx64"]
+
     skips: List[torch.Tensor] = []
     n_l = N
     cur = feat
-    for lfa in net.encoder:
-        out = LFA_IMPL(lfa, xyz[:, :n_l], cur)
+    for lvl, lfa in enumerate(net.encoder):
+        if lvl == 1 and pre_fork is not None:
+            pre_fork.join()
+        out = LFA_IMPL(lfa, xyz[:, :n_l], cur, enc_idx[lvl]) if lvl in enc_idx else LFA_IMPL(lfa, xyz[:, :n_l], cur)
         skips.append(out)
         n_l //= dec
         cur = out[:, :n_l]
     cur = shared_mlp(net.mlp, cur)
-    for stage in net.decoder:
+    for lvl, stage in enumerate(net.decoder):
         n_up = skips[-1].shape[1]          # N // dec^(l-1): the encoder level this stage returns to
-        up = upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up])
+        up = upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up], dec_idx.get(lvl))
         cur = shared_mlp(stage, torch.cat((up, skips.pop()), dim=-1))
         n_l = n_up
     inv = torch.empty_like(perm)                  # inverse permutation by scatter (argsort is a 30 us radix sort)
