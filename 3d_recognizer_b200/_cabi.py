@@ -54,6 +54,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_bn_from_moments_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double] +
                                 [c_void_p] * 10 + [c_void_p]),
+    "r3d_pointwise_plan": (c_int, [c_int, c_int, c_int, ctypes.c_longlong, c_int]),
     "r3d_lfa_rpe1_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_lfa_bn2_coeffs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_int, c_void_p, c_void_p,

@@ -22,6 +22,7 @@
 #include "pointwise_common.cuh"
 
 #include <atomic>
+#include <cooperative_groups.h>
 
 namespace r3d {
 
@@ -203,7 +204,11 @@ __global__ void __launch_bounds__((TM / 8) * (TN / 8)) pw_gemm_kernel(PwArgs a) 
 // list of the small-cloud training step showed the unpipelined kernel at 61 us per launch (24 % of the step):
 // 16..64 chunks of load -> barrier -> 16 k-steps -> barrier on a handful of CTAs.
 // RT = register tile edge (8: 8x8 per thread; 4: 4x4 per thread, more threads/CTAs for small row counts).
-template <int TM, int TN, int RT, int KC = kPwKC>
+// SPLITK > 1: a thread-block cluster of SPLITK CTAs (gridDim.z) shares one output tile, each CTA contracting 1/SPLITK
+// of the input channels; the partial tiles are summed through distributed shared memory by the cluster's rank-0 CTA,
+// which then runs the epilogue.  For few-row wide layers the chain of dependent load -> FMA steps is the whole cost
+// of the kernel: a cluster of 4 cuts it 4x and puts 4x more SMs to work.
+template <int TM, int TN, int RT, int KC = kPwKC, int SPLITK = 1>
 __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwArgs a) {
     constexpr int NT = (TM / RT) * (TN / RT);
     constexpr int TMP = TM + 4;
@@ -304,13 +309,21 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
 
     if (a.stats)
         for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.0;
-    load(0);
-    store(0);
+    // this CTA's share of the contraction (whole chunks)
+    const int chunks_all = (cin + KC - 1) / KC;
+    const int chunks_per = (chunks_all + SPLITK - 1) / SPLITK;
+    const int ch_begin = (SPLITK > 1 ? (int)blockIdx.z : 0) * chunks_per;
+    const int ch_end = ch_begin + chunks_per < chunks_all ? ch_begin + chunks_per : chunks_all;
+    const int nchunks = ch_end > ch_begin ? ch_end - ch_begin : 0;
+    const int cbase = ch_begin * KC;
+    if (nchunks > 0) {
+        load(cbase);
+        store(0);
+    }
     __syncthreads();
-    const int nchunks = (cin + KC - 1) / KC;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int buf = ch & 1;
-        if (ch + 1 < nchunks) load((ch + 1) * KC);
+        if (ch + 1 < nchunks) load(cbase + (ch + 1) * KC);
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
             float av[RT], wv[RT];
@@ -336,6 +349,33 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
         }
         if (ch + 1 < nchunks) store(buf ^ 1);
         __syncthreads();
+    }
+
+    if (SPLITK > 1) {
+        // partial tiles -> rank 0 through distributed shared memory (the staging buffers are free now)
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        static_assert(SPLITK == 1 || RT * RT * NT <= 2 * KC * TN, "partial tile must fit the W staging buffer");
+        float* part = &Ws[0][0][0];
+        const unsigned rank = cluster.block_rank();
+        if (rank != 0) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+#pragma unroll
+                for (int j = 0; j < RT; ++j) part[(i * RT + j) * NT + tid] = acc[i][j];
+        }
+        cluster.sync();
+        if (rank == 0) {
+            for (unsigned r = 1; r < (unsigned)SPLITK; ++r) {
+                const float* remote = cluster.map_shared_rank(part, r);
+#pragma unroll
+                for (int i = 0; i < RT; ++i)
+#pragma unroll
+                    for (int j = 0; j < RT; ++j) acc[i][j] += remote[(i * RT + j) * NT + tid];
+            }
+        }
+        cluster.sync();          // the partial tiles stay mapped until rank 0 has read them
+        if (rank != 0) return;
     }
 
     // ---- epilogue
@@ -557,7 +597,22 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
         // chain of load -> barrier -> FMA steps on a handful of CTAs, each step exposed to the full L2 latency.
         // 32-channel steps halve the chain, 32-row tiles put 2-4x more CTAs on the machine.
         const long long tiles32 = ((M + 31) / 32) * ((cout + 31) / 32);
-        if (tiles32 <= 2 * kNumSMs) {
+        if (tiles32 <= 2 * kNumSMs && ca + cb >= 256) {
+            // long contraction on few tiles: clusters of 4 CTAs split the input channels (see SPLITK above)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((M + 31) / 32), (cout + 31) / 32, 4);
+            cfg.blockDim = dim3(64);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 4;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, pw_gemm_fast_kernel<32, 32, 4, 32, 4>, a));
+        } else if (tiles32 <= 2 * kNumSMs) {
             dim3 grid((unsigned)((M + 31) / 32), (cout + 31) / 32);
             pw_gemm_fast_kernel<32, 32, 4, 32><<<grid, 64, 0, st>>>(a);
         } else {
@@ -580,6 +635,24 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     }
     R3D_LAUNCH_CHECK("pw_gemm_kernel");
     return R3D_OK;
+}
+
+// Which kernel r3d_pointwise runs for a layer under the current settings: 0 pw_small_kernel (thin layers, weights in
+// shared memory), 1 pw_gemm_kernel (channel counts not multiples of 4), 2 pw_gemm_fast_kernel (pipelined FP32 GEMM,
+// any tile shape), 3 pw_tc_kernel (tcgen05 3xTF32).  Dense layout assumed (y_ld = cout).
+extern "C" int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int transpose_out) {
+    if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) return 0;
+    PwArgs a{};
+    a.ca = ca;
+    a.cb = cb;
+    a.cout = cout;
+    a.B = 1;
+    a.n = (int)(rows > 0x7fffffffLL ? 0x7fffffffLL : rows);
+    a.transpose_out = transpose_out;
+    a.y_ld = cout;
+    a.y_bstride = 0;
+    if (g_pw_tensor_cores.load() && pw_tc_eligible(a, g_pw_tensor_cores.load() == 2)) return 3;
+    return ((ca % 4 == 0) && (cb % 4 == 0)) ? 2 : 1;
 }
 
 // 1 (default): the layers the tcgen05 3xTF32 kernel is measured to win on (pw_tc_eligible) run there; 0: FP32

@@ -237,7 +237,13 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
         gs = 0 if gidx.dim() == 1 else gidx.stride(0)
     flops = 2.0 * B * n * (ca + cb) * cout
     nbytes = 4.0 * B * n * (ca + cb + cout)
-    with torch.cuda.device(dev), _cabi.kernel_timer(f"pointwise[M={B * n},{ca + cb}->{cout}]" if _cabi.TIMER_SHAPES else "pointwise", flops=flops, bytes=nbytes):
+    tname = "pointwise"
+    if _cabi.KERNEL_TIMERS is not None:
+        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc")[
+            _cabi.lib().r3d_pointwise_plan(ca, cb, cout, B * n, 1 if transpose_out else 0)]
+        if _cabi.TIMER_SHAPES:
+            tname += f"[M={B * n},{ca + cb}->{cout}]"
+    with torch.cuda.device(dev), _cabi.kernel_timer(tname, flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_pointwise_stats(_cabi.raw(xa), xas, ca, _cabi.ptr(gidx), gs, _cabi.raw(xb), xbs, cb,
                                              _cabi.ptr(wT), _cabi.ptr(scale), _cabi.ptr(shift), _ACT[act],
                                              float(slope), _cabi.ptr(out), 0, 0, cout, B, n,

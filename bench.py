@@ -202,37 +202,74 @@ def measure_fp32_peak(cabi):
     return res
 
 
-def kernel_table(timers):
+def event_pair_overhead_ms(n=64):
+    """What a CUDA-event pair measures around nothing at all, with the GPU busy before and after (median of n): the
+    fixed cost every per-kernel sample below carries, subtracted in kernel_table."""
+    torch.cuda._sleep(int(2e6))
+    pairs = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sorted(a.elapsed_time(b) for a, b in pairs)[n // 2]
+
+
+def kernel_table(timers, overhead_ms=0.0):
     """name -> dict(launches, ms_total, ms_avg, flops, bytes) from the C-ABI wrappers' event pairs."""
     tab = {}
     for name, lst in timers.items():
-        ms = [a.elapsed_time(b) for a, b, _ in lst]
+        ms = [max(a.elapsed_time(b) - overhead_ms, 1e-4) for a, b, _ in lst]
         tab[name] = dict(launches=len(lst), ms_total=sum(ms), ms_avg=sum(ms) / len(ms),
                          flops=sum(w.get("flops", 0.0) for _, _, w in lst) / len(lst),
                          bytes=sum(w.get("bytes", 0.0) for _, _, w in lst) / len(lst))
     return tab
 
 
+def kernel_family(name):
+    """Timer name -> CUDA kernel behind it: shapes dropped, the two halves of an LFA block share one kernel template
+    (lfa_pool_kernel<D,K,STAGE> / lfa_pool_bwd_kernel<D,K,NT,STAGE>)."""
+    base = name.split("[")[0]
+    for a, b in (("lfa_pool1_bwd", "lfa_pool_bwd"), ("lfa_pool2_bwd", "lfa_pool_bwd"), ("lfa_pool1", "lfa_pool"),
+                 ("lfa_pool2", "lfa_pool")):
+        if base == a:
+            return b
+    return base
+
+
 def roofline_of(tab, peaks, fp32_peak):
-    """Roofline entry of the dominant kernel (largest share of the timed region)."""
+    """Roofline entry of the dominant kernel: the kernel (all its launches of the step, whatever their shapes) with
+    the largest share of the timed region.  achieved = algorithmic work of those launches / their summed duration,
+    i.e. the launch-time-weighted mean over the shapes the step runs the kernel on."""
     if not tab:
         return None
-    name = max(tab, key=lambda n: tab[n]["ms_total"])
-    k = tab[name]
-    t_s = k["ms_avg"] * 1e-3
-    t_hbm = k["bytes"] / (peaks["hbm_gbs"] * 1e9)
-    t_fp32 = k["flops"] / (fp32_peak["ffma"] * 1e12)
+    fam = {}
+    for name, k in tab.items():
+        f = fam.setdefault(kernel_family(name), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, shapes=[]))
+        n = k["launches"]
+        f["ms"] += k["ms_avg"] * n
+        f["flops"] += k["flops"] * n
+        f["bytes"] += k["bytes"] * n
+        f["launches"] += n
+        f["shapes"].append(name)
+    name = max(fam, key=lambda n: fam[n]["ms"])
+    f = fam[name]
+    t_s = f["ms"] * 1e-3
+    n = max(f["launches"], 1)
+    t_hbm = f["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    t_fp32 = f["flops"] / (fp32_peak["ffma"] * 1e12)
+    common = dict(kernel=name, launches=f["launches"], ms_avg=f["ms"] / n, traffic=None, shapes=sorted(f["shapes"]),
+                  algorithmic_flops_per_launch=f["flops"] / n, algorithmic_bytes_per_launch=f["bytes"] / n)
     if t_fp32 >= t_hbm:
-        ach = k["flops"] / t_s * 1e-12
-        return dict(kernel=name, bound="fp32", achieved=ach, peak=fp32_peak["ffma"], unit="TFLOP/s",
-                    frac=ach / fp32_peak["ffma"], traffic=None, launches=k["launches"], ms_avg=k["ms_avg"],
+        ach = f["flops"] / t_s * 1e-12
+        return dict(common, bound="fp32", achieved=ach, peak=fp32_peak["ffma"], unit="TFLOP/s",
+                    frac=ach / fp32_peak["ffma"],
                     peak_source="FFMA probe kernel measured in this run (r3d_fp32_probe); FFMA2 packed: %.1f"
-                                % fp32_peak["ffma2"],
-                    algorithmic_flops_per_launch=k["flops"], algorithmic_bytes_per_launch=k["bytes"])
-    ach = k["bytes"] / t_s * 1e-9
-    return dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                traffic=None, launches=k["launches"], ms_avg=k["ms_avg"], peak_source=peaks["source"],
-                algorithmic_flops_per_launch=k["flops"], algorithmic_bytes_per_launch=k["bytes"])
+                                % fp32_peak["ffma2"])
+    ach = f["bytes"] / t_s * 1e-9
+    return dict(common, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                peak_source=peaks["source"])
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -477,8 +514,10 @@ def main():
 
     cabi.KERNEL_TIMERS = {}
     timed_steps(instrumented, n_eager, 0, world, flush)
-    tab = kernel_table(cabi.KERNEL_TIMERS)
+    timer_overhead_ms = event_pair_overhead_ms()
+    tab = kernel_table(cabi.KERNEL_TIMERS, timer_overhead_ms)
     cabi.KERNEL_TIMERS = None
+    extras["kernel_timer_overhead_us"] = round(timer_overhead_ms * 1e3, 2)
     if wl["kind"] == "knn":
         # The default search for clouds this large is the uniform-grid back-end, whose work is O(N K), not the
         # 8 N^2 flop of the exhaustive scan, so it has no FP32 roofline to speak of.  The roofline entry is taken
@@ -493,6 +532,7 @@ def main():
         L.r3d_knn_set_algorithm(prev)
         for kn, kv in brute.items():
             kv["ms_total"] = kv["ms_avg"] * n_eager * 1.0      # comparable with the per-step table below
+            kv["launches"] = n_eager                           # one launch per step
             tab["forced_" + kn] = kv
         grid_name = next(kn for kn in tab if kn.startswith("knn_grid"))
         extras["default_search"] = "uniform grid (r3d_knn algorithm 0/2)"

@@ -233,8 +233,13 @@ int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int
 
 /* Wide layers (C_in >= 32, C_out a multiple of 32, channel counts multiples of 4) run on the tcgen05 tensor cores
  * with the 3xTF32 split (csrc/pointwise_tc.cu, fp32-level accuracy); everything else on the FP32 CUDA-core kernels.
- * on = 0 forces the CUDA-core kernels everywhere, 1 (default) enables the tensor-core path.  Returns the previous value. */
+ * on = 0 forces the CUDA-core kernels everywhere, 1 (default) uses the tensor-core kernel where it is measured to win
+ * (>= 32768 rows and C_in >= 256 or C_out <= 32; profiles/r01_pointwise_tc_vs_fp32.txt), 2 wherever it is supported
+ * (>= 4096 rows; tests, benchmarks).  Returns the previous value. */
 int r3d_pointwise_set_tensor_cores(int on);
+/* the kernel r3d_pointwise runs for a dense layer under the current settings: 0 pw_small_kernel, 1 pw_gemm_kernel,
+ * 2 pw_gemm_fast_kernel, 3 pw_tc_kernel (tcgen05) */
+int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int transpose_out);
 
 /* ------------------------------------------------------------- train-mode BatchNorm of a per-point layer
  * Forward tail of SharedMLP in training mode (modules.py:92-104): z (M,C) = conv output WITHOUT bias, stats from

@@ -48,6 +48,9 @@ def mods():
     (2, 100, 5, 0, 8, "lrelu", "shared", False),
     (2, 2560, 512, 512, 256, "relu", "per_cloud", False), (4, 1100, 128, 0, 512, "relu", None, False),
     (1, 5000, 64, 32, 128, "lrelu", "shared", False), (2, 4096, 32, 0, 64, None, None, False),
+    # few rows, long contraction: clusters of 4 CTAs split the input channels (distributed shared memory reduction)
+    (1, 312, 256, 0, 512, "relu", None, False), (2, 36, 520, 0, 64, None, None, False),
+    (1, 72, 512, 512, 256, "lrelu", "per_cloud", False), (3, 100, 256, 0, 36, "relu", None, True),
     # >= 32768 rows with a long contraction or a narrow output: the tcgen05 path (pw_tc_eligible)
     (2, 16384, 512, 512, 256, "relu", "per_cloud", False), (4, 8200, 256, 0, 32, "relu", None, False),
     (1, 33000, 64, 32, 32, "lrelu", "shared", False), (3, 11000, 128, 128, 512, None, None, False),
