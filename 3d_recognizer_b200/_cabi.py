@@ -43,6 +43,7 @@ SIGNATURES = {
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
                          [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_tile_points": (c_int, [c_int, c_int]),
+    "r3d_lfa_tile_points_for": (c_int, [c_int, c_int, c_int, c_int]),
     "r3d_lfa_pool2_bwd_train": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                                 [c_void_p] * 9 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 3 +
                                 [c_int, c_int, c_int, c_int, c_void_p]),

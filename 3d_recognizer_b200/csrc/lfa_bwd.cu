@@ -54,20 +54,24 @@ struct LfaBwdArgs {
     int B, N;
 };
 
-template <int D, int K, int NT>
-using LfaBwdCfg = LfaCfg<D, K, NT, (D <= 64 ? 2048 : 4096), lfa_rows_per_thread(D)>;
+// FINE = 1: half the rows per thread, i.e. twice the threads per point and half the points per CTA.  For the wide
+// levels of a SMALL batch (8 clouds x 39..156 points) the default tiles give 80..160 CTAs of 4 warps -- one CTA per SM,
+// one or two waves, every warp carrying a 16-row register tile; the fine tiles double the CTAs, halve each warp's
+// work and fit two CTAs per SM.
+template <int D, int K, int NT, int FINE = 0>
+using LfaBwdCfg = LfaCfg<D, K, NT, (D <= 64 ? 2048 : 4096), (FINE ? lfa_rows_per_thread(D) / 2 : lfa_rows_per_thread(D))>;
 
-template <int D, int K, int NT>
+template <int D, int K, int NT, int FINE = 0>
 struct LfaBwdSmem {
-    using C = LfaBwdCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT, FINE>;
     static constexpr int FLOATS = 2 * C::X_FLOATS + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 16 + C::ROWS +
                                   C::PTS * D;
     static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
 };
 
-template <int D, int K, int NT, int STAGE>
-__global__ void __launch_bounds__(NT, (D <= 16 ? 3 : (D <= 64 ? 2 : 1))) lfa_pool_bwd_kernel(LfaBwdArgs a) {
-    using C = LfaBwdCfg<D, K, NT>;
+template <int D, int K, int NT, int STAGE, int FINE = 0>
+__global__ void __launch_bounds__(NT, (D <= 16 ? 3 : (D <= 64 ? 2 : (FINE ? 2 : 1)))) lfa_pool_bwd_kernel(LfaBwdArgs a) {
+    using C = LfaBwdCfg<D, K, NT, FINE>;
     constexpr int H = C::H;
     constexpr int RT = C::RT;
     constexpr int RP = C::ROWS_PAD;
@@ -327,9 +331,9 @@ struct LfaMomArgs {
     int B, N;
 };
 
-template <int D, int K, int NT>
+template <int D, int K, int NT, int FINE = 0>
 struct LfaMomSmem {
-    using C = LfaBwdCfg<D, K, NT>;
+    using C = LfaBwdCfg<D, K, NT, FINE>;
     static constexpr int FLOATS = 2 * C::H * C::ROWS_PAD + kRpeRows * C::ROWS_PAD + 2 * C::WSTAGE + C::H * 14 + 4;
     static constexpr size_t BYTES = (size_t)FLOATS * sizeof(float) + 16;
 };
@@ -340,9 +344,9 @@ struct LfaMomSmem {
 //         G1 += du1^T [rpe, 1].  Mean and variance terms are subtracted PER ROW before any row sum is taken: going
 //         through the moments instead (MODE 2) subtracts two row sums that cancel to ~1/sqrt(rows) of their size and
 //         lost 3-4 digits at 65 k rows.
-template <int D, int K, int NT, int MODE>
-__global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : 1))) lfa_moments_kernel(LfaMomArgs a) {
-    using C = LfaBwdCfg<D, K, NT>;
+template <int D, int K, int NT, int MODE, int FINE = 0>
+__global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : (FINE ? 2 : 1)))) lfa_moments_kernel(LfaMomArgs a) {
+    using C = LfaBwdCfg<D, K, NT, FINE>;
     constexpr int H = C::H;
     constexpr int RT = C::RT;
     constexpr int RP = C::ROWS_PAD;
@@ -474,11 +478,11 @@ __global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : 1))) lfa_mom
 }
 
 // ------------------------------------------------------------------------------------- launchers
-template <int D, int K, int NT, int STAGE>
+template <int D, int K, int NT, int STAGE, int FINE = 0>
 static int launch_bwd(const LfaBwdArgs& a, cudaStream_t st) {
-    using C = LfaBwdCfg<D, K, NT>;
-    auto kern = lfa_pool_bwd_kernel<D, K, NT, STAGE>;
-    constexpr size_t smem = LfaBwdSmem<D, K, NT>::BYTES;
+    using C = LfaBwdCfg<D, K, NT, FINE>;
+    auto kern = lfa_pool_bwd_kernel<D, K, NT, STAGE, FINE>;
+    constexpr size_t smem = LfaBwdSmem<D, K, NT, FINE>::BYTES;
     static_assert(smem <= 232448, "backward tile does not fit shared memory");
     R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(a.N, C::PTS), a.B);
@@ -487,8 +491,28 @@ static int launch_bwd(const LfaBwdArgs& a, cudaStream_t st) {
     return R3D_OK;
 }
 
+// Fine tiles (see LfaBwdCfg) when the default grid would not even fill two waves of the wide-level kernels.
+template <int D, int K>
+static int tile_points() { return LfaBwdCfg<D, K, 128>::PTS; }
+static int default_tile_points(int K, int d);
+
+static bool lfa_fine_tiles(int d, int K, int B, int N) {
+    // measured on the 8 x 2 500-point step: d = 128 (8 x 156 points) 130 -> 107 us; d = 256 (8 x 39) 117 -> 130 us (every
+    // CTA streams the whole 3 x 256 KB of weights: halving the tile doubles that), so only d = 128 takes the fine tiles
+    if (d != 128) return false;
+    const int pts = default_tile_points(K, d);
+    if (pts < 2) return false;
+    return (long long)ceil_div(N, pts) * B <= 2LL * kNumSMs;
+}
+
 template <int STAGE>
 static int dispatch_bwd(int d, int K, const LfaBwdArgs& a, cudaStream_t st) {
+    if (lfa_fine_tiles(d, K, a.B, a.N)) {
+#define R3D_FINE(DD, KK) \
+    if (d == DD && K == KK) return launch_bwd<DD, KK, 128, STAGE, 1>(a, st);
+        R3D_FINE(128, 16) R3D_FINE(128, 32)
+#undef R3D_FINE
+    }
 #define R3D_CASE(DD, KK, NT) \
     if (d == DD && K == KK) return launch_bwd<DD, KK, NT, STAGE>(a, st);
     R3D_CASE(16, 16, 128) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
@@ -497,11 +521,11 @@ static int dispatch_bwd(int d, int K, const LfaBwdArgs& a, cudaStream_t st) {
     return R3D_EUNSUPPORTED;
 }
 
-template <int D, int K, int NT, int MODE>
+template <int D, int K, int NT, int MODE, int FINE = 0>
 static int launch_mom(const LfaMomArgs& a, cudaStream_t st) {
-    using C = LfaBwdCfg<D, K, NT>;
-    auto kern = lfa_moments_kernel<D, K, NT, MODE>;
-    constexpr size_t smem = LfaMomSmem<D, K, NT>::BYTES;
+    using C = LfaBwdCfg<D, K, NT, FINE>;
+    auto kern = lfa_moments_kernel<D, K, NT, MODE, FINE>;
+    constexpr size_t smem = LfaMomSmem<D, K, NT, FINE>::BYTES;
     static_assert(smem <= 232448, "moments tile does not fit shared memory");
     R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(a.N, C::PTS), a.B);
@@ -512,10 +536,26 @@ static int launch_mom(const LfaMomArgs& a, cudaStream_t st) {
 
 template <int MODE>
 static int dispatch_mom(int d, int K, const LfaMomArgs& a, cudaStream_t st) {
+    if (MODE == 3 && lfa_fine_tiles(d, K, a.B, a.N)) {      // pass 2 reads pass 1's du2 tiles: same tiling
+#define R3D_FINE(DD, KK) \
+    if (d == DD && K == KK) return launch_mom<DD, KK, 128, MODE, 1>(a, st);
+        R3D_FINE(128, 16) R3D_FINE(128, 32)
+#undef R3D_FINE
+    }
 #define R3D_CASE(DD, KK, NT) \
     if (d == DD && K == KK) return launch_mom<DD, KK, NT, MODE>(a, st);
     R3D_CASE(16, 16, 128) R3D_CASE(32, 16, 128) R3D_CASE(64, 16, 128) R3D_CASE(128, 16, 128) R3D_CASE(256, 16, 128)
     R3D_CASE(16, 32, 128) R3D_CASE(32, 32, 128) R3D_CASE(64, 32, 128) R3D_CASE(128, 32, 128) R3D_CASE(256, 32, 128)
+#undef R3D_CASE
+    return R3D_EUNSUPPORTED;
+}
+
+// points per CTA tile of the backward / moment kernels (layout of du2_tiles)
+static int default_tile_points(int K, int d) {
+#define R3D_CASE(DD, KK) \
+    if (d == DD && K == KK) return tile_points<DD, KK>();
+    R3D_CASE(16, 16) R3D_CASE(32, 16) R3D_CASE(64, 16) R3D_CASE(128, 16) R3D_CASE(256, 16)
+    R3D_CASE(16, 32) R3D_CASE(32, 32) R3D_CASE(64, 32) R3D_CASE(128, 32) R3D_CASE(256, 32)
 #undef R3D_CASE
     return R3D_EUNSUPPORTED;
 }
@@ -552,17 +592,13 @@ extern "C" int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstri
     return stage == 1 ? dispatch_bwd<1>(d, K, a, st) : dispatch_bwd<2>(d, K, a, st);
 }
 
-// points per CTA tile of the backward / moment kernels (layout of du2_tiles)
-template <int D, int K>
-static int tile_points() { return LfaBwdCfg<D, K, 128>::PTS; }
+extern "C" int r3d_lfa_tile_points(int K, int d) { return default_tile_points(K, d); }
 
-extern "C" int r3d_lfa_tile_points(int K, int d) {
-#define R3D_CASE(DD, KK) \
-    if (d == DD && K == KK) return tile_points<DD, KK>();
-    R3D_CASE(16, 16) R3D_CASE(32, 16) R3D_CASE(64, 16) R3D_CASE(128, 16) R3D_CASE(256, 16)
-    R3D_CASE(16, 32) R3D_CASE(32, 32) R3D_CASE(64, 32) R3D_CASE(128, 32) R3D_CASE(256, 32)
-#undef R3D_CASE
-    return R3D_EUNSUPPORTED;
+extern "C" int r3d_lfa_tile_points_for(int K, int d, int B, int N) {
+    const int pts = default_tile_points(K, d);
+    if (pts <= 0) return pts;
+    const bool fine_built = d == 128 && (K == 16 || K == 32);
+    return (fine_built && lfa_fine_tiles(d, K, B, N)) ? pts / 2 : pts;
 }
 
 extern "C" int r3d_lfa_pool2_bwd_train(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,

@@ -428,9 +428,9 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     d = 2 * h
     dev = xyz.device
     L = _cabi.lib()
-    pts = L.r3d_lfa_tile_points(K, d)
+    pts = L.r3d_lfa_tile_points_for(K, d, B, N)
     if pts <= 0:
-        raise ValueError(f"r3d_lfa_tile_points: unsupported shape d={d}, K={K}")
+        raise ValueError(f"r3d_lfa_tile_points_for: unsupported shape d={d}, K={K}")
     tiles = -(-N // pts)
     dpooled = dpooled.contiguous()
     n_df = B * N * h

@@ -146,13 +146,15 @@ int r3d_lfa_pool_bwd(int stage, const float* xyz, long long xyz_bstride, const i
 
 /* Train-mode backward of a STAGE-2 launch, split in the standard two BatchNorm passes (batch statistics of mlp_rpe2):
  *   r3d_lfa_pool2_bwd_train  pass 1: as r3d_lfa_pool_bwd(stage 2) up to du2 (gradient at mlp_rpe2's ReLU input),
- *                            which is written per CTA tile to du2_tiles ([b][tile][h][P*K], P = r3d_lfa_tile_points)
+ *                            which is written per CTA tile to du2_tiles ([b][tile][h][P*K], P = r3d_lfa_tile_points_for)
  *                            together with sum_du2 (2,h) fp64 += (sum du2, sum du2 * r2); dfeat, dw_score as before.
  *   r3d_lfa_bn2_bwd          pass 2: with bn2 (5,h) = a2, mean2, rstd2, mean(du2), mean(du2*zhat2):
  *                            dz2 = a2 (du2 - m1 - zhat2 m2), dw2 (h,h) fp64 += dz2^T r1, dr1 = dz2 W2,
  *                            du1 = dr1 [r1 > 0], g1 (h,16) fp64 += du1^T [rpe, 1].
  * Subtracting the mean/variance terms per row (not as row sums) keeps fp32 accuracy at any cloud size. */
 int r3d_lfa_tile_points(int K, int d);
+/* P for a given batch: small batches of the wide levels (d >= 128, <= 2 waves of default tiles) run half-size tiles */
+int r3d_lfa_tile_points_for(int K, int d, int B, int N);
 int r3d_lfa_pool2_bwd_train(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
                             long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
                             const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,

@@ -113,8 +113,10 @@ def _lfa_block_case(mods, n_in, d, K, N, train, seed):
     return fails
 
 
+# d >= 128 with few tiles (N=300/150) takes the fine-tile kernels, N=1300/640 the default ones (r3d_lfa_tile_points_for)
 @pytest.mark.parametrize("n_in,d,K,N", [(8, 16, 16, 1000), (32, 64, 16, 625), (128, 128, 16, 300), (256, 256, 16, 150),
-                                        (8, 16, 32, 500), (32, 64, 32, 300), (128, 256, 32, 100)])
+                                        (8, 16, 32, 500), (32, 64, 32, 300), (128, 256, 32, 100),
+                                        (128, 128, 16, 1300), (256, 256, 16, 640), (64, 128, 32, 200)])
 @pytest.mark.parametrize("train", [True, False])
 def test_lfa_block_fused_vs_autograd(mods, n_in, d, K, N, train):
     """Output, input gradient, every parameter gradient and the BatchNorm running statistics of one
