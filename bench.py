@@ -566,6 +566,15 @@ def main():
         tab[kname]["share_of_eager_step"] = tab[kname]["ms_per_step"] / eager_ms_per_step
         tab[kname]["launches"] //= n_eager
     roof = roofline_of(tab, peaks, fp32_peak)
+    # DRAM traffic of the dominant kernel comes from a committed ncu --set full capture (never measured under this run)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+            ent = json.load(fh).get(name, {}).get(roof["kernel"]) if roof else None
+        if ent:
+            roof["traffic"] = ent["bytes_per_launch"]
+            roof["traffic_source"] = ent["source"]
+    except (OSError, ValueError):
+        pass
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
