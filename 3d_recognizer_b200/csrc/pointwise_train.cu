@@ -12,6 +12,8 @@
 // Backward reference: autograd of modules.py:92-104 as driven by trainer.py:115-119.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace r3d {
 
 constexpr int kBnMaxC = 1024;
@@ -73,10 +75,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 
 // ----------------------------------------------------------------------------------- bn_bwd_reduce
 // stats2 (2C fp64): [c] += sum du, [C + c] += sum du * zhat
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
-                                                            long long M, int C, const float* __restrict__ save,
-                                                            const float* __restrict__ beta, int act, float slope,
-                                                            double* __restrict__ stats2) {
+__device__ __forceinline__ void bn_bwd_reduce_body(const float* __restrict__ dy, const float* __restrict__ z,
+                                                   long long M, int C, const float* __restrict__ save,
+                                                   const float* __restrict__ beta, int act, float slope,
+                                                   double* __restrict__ stats2, float (*red)[kBnMaxC]) {
     const int c4n = C / 4;                       // column quads
     const int rows_per_pass = blockDim.x / c4n;  // >= 1 (C <= 1024)
     const int q = threadIdx.x % c4n, rl = threadIdx.x / c4n;
@@ -103,7 +105,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
             }
         }
     }
-    __shared__ float red[2][kBnMaxC];
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) (&red[0][0])[i < C ? i : kBnMaxC + (i - C)] = 0.f;
     __syncthreads();
     // narrow layers: the lanes of a warp that hold the same column quad (lane % c4n) combine by shuffles first --
@@ -133,13 +134,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     }
 }
 
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            long long M, int C, const float* __restrict__ save,
+                                                            const float* __restrict__ beta, int act, float slope,
+                                                            double* __restrict__ stats2) {
+    __shared__ float red[2][kBnMaxC];
+    bn_bwd_reduce_body(dy, z, M, C, save, beta, act, slope, stats2, red);
+}
+
 // --------------------------------------------------------------------------------------- bn_bwd_dz
-__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ z,
-                                                        long long M, int C, const float* __restrict__ save,
-                                                        const float* __restrict__ beta, int act, float slope,
-                                                        const double* __restrict__ stats2, float* __restrict__ dz,
-                                                        float* __restrict__ dgb) {
-    __shared__ float sa[kBnMaxC], sm[kBnMaxC], sr[kBnMaxC], sc[kBnMaxC], m1[kBnMaxC], m2[kBnMaxC];
+struct BnDzSmem {
+    float sa[kBnMaxC], sm[kBnMaxC], sr[kBnMaxC], sc[kBnMaxC], m1[kBnMaxC], m2[kBnMaxC];
+};
+
+__device__ __forceinline__ void bn_bwd_dz_body(const float* __restrict__ dy, const float* __restrict__ z, long long M,
+                                               int C, const float* __restrict__ save, const float* __restrict__ beta,
+                                               int act, float slope, const double* stats2, float* __restrict__ dz,
+                                               float* __restrict__ dgb, BnDzSmem& S) {
+    float *sa = S.sa, *sm = S.sm, *sr = S.sr, *sc = S.sc, *m1 = S.m1, *m2 = S.m2;
     if (dgb && blockIdx.x == 0)
         for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) dgb[c] = (float)stats2[c];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -167,6 +179,33 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict_
         }
         reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                        long long M, int C, const float* __restrict__ save,
+                                                        const float* __restrict__ beta, int act, float slope,
+                                                        const double* __restrict__ stats2, float* __restrict__ dz,
+                                                        float* __restrict__ dgb) {
+    __shared__ BnDzSmem S;
+    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S);
+}
+
+// Both passes in ONE cooperative launch with a grid barrier between them: for the layers of a small cloud each pass
+// is a ~5 us kernel whose cost is its launch, and the second pass re-reads dy and z from L2 anyway.  The grid is
+// sized to be co-resident (r3d_bn_bwd); larger tensors take the two-launch path.
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                           long long M, int C, const float* __restrict__ save,
+                                                           const float* __restrict__ beta, int act, float slope,
+                                                           double* stats2, float* __restrict__ dz,
+                                                           float* __restrict__ dgb) {
+    __shared__ union {
+        float red[2][kBnMaxC];
+        BnDzSmem dzs;
+    } S;
+    bn_bwd_reduce_body(dy, z, M, C, save, beta, act, slope, stats2, S.red);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S.dzs);
 }
 
 // ------------------------------------------------------------------------------------ rowreduce_gemm
@@ -458,6 +497,45 @@ extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C
                                                                                              slope, stats2, dz, dgb);
     R3D_LAUNCH_CHECK("bn_bwd_dz_kernel");
     return R3D_OK;
+}
+
+extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                          int act, float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
+    if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
+    if (M == 0) return R3D_OK;
+    if (!dy || !z || !save || !beta || !stats2 || !dz) return R3D_EINVAL;
+    if (!is_aligned(dy, 16) || !is_aligned(z, 16) || !is_aligned(dz, 16)) return R3D_EALIGN;
+    // one cooperative launch while the whole grid can be co-resident (<= 4 CTAs per SM asked for) and the tensor is
+    // small enough for the launch cost to matter; two launches otherwise
+    static int max_blocks_per_sm = -1;
+    if (max_blocks_per_sm < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_bwd_fused_kernel, 256, 0) != cudaSuccess) n = 0;
+        max_blocks_per_sm = n;
+    }
+    const int rows_per_pass = 256 / (C / 4) > 0 ? 256 / (C / 4) : 1;
+    const long long want = (M + (long long)rows_per_pass * 2 - 1) / ((long long)rows_per_pass * 2);
+    const long long resident = (long long)kNumSMs * (max_blocks_per_sm < 4 ? max_blocks_per_sm : 4);
+    if (M * C <= (1LL << 22) && resident > 0) {
+        const long long blocks = want < resident ? want : resident;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(blocks < 1 ? 1 : blocks));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel, dy, z, M, C, save, beta, act, slope, stats2, dz, dgb));
+        R3D_LAUNCH_CHECK("bn_bwd_fused_kernel");
+        return R3D_OK;
+    }
+    int rc = r3d_bn_bwd_reduce(dy, z, M, C, save, beta, act, slope, stats2, stream);
+    if (rc != R3D_OK) return rc;
+    return r3d_bn_bwd_dz(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, stream);
 }
 
 extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,

@@ -276,7 +276,8 @@ def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bia
 
 def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0,
                 stats2: Optional[torch.Tensor] = None):
-    """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd_reduce`` + ``r3d_bn_bwd_dz``).
+    """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd``: the reduce and dz passes, one
+    cooperative launch for small tensors).
     ``stats2``: optional zero-filled (2C) fp64 scratch (the forward allocates it together with its own statistics
     buffer: one fill instead of two).  Returns (dz (M,C), dgamma (C), dbeta (C))."""
     M, C = z.shape
@@ -287,12 +288,9 @@ def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: tor
     s2 = torch.empty(2 * C, dtype=torch.float32, device=z.device)
     L = _cabi.lib()
     with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_backward[M={M},C={C}]", flops=12.0 * M * C, bytes=20.0 * M * C):
-        rc = L.r3d_bn_bwd_reduce(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
-                                 float(slope), _cabi.ptr(stats2), _cabi.stream_ptr(z.device))
-        _cabi.check(rc, "r3d_bn_bwd_reduce")
-        rc = L.r3d_bn_bwd_dz(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
-                             float(slope), _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.ptr(s2), _cabi.stream_ptr(z.device))
-    _cabi.check(rc, "r3d_bn_bwd_dz")
+        rc = L.r3d_bn_bwd(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act], float(slope),
+                          _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.ptr(s2), _cabi.stream_ptr(z.device))
+    _cabi.check(rc, "r3d_bn_bwd")
     return dz, s2[C:], s2[:C]
 
 

@@ -257,6 +257,10 @@ int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, int C, const
                       int act, float slope, double* stats2, r3d_stream_t stream);
 int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
                   float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream);
+/* Both passes: one cooperative launch (grid barrier between the passes) while the tensor is small (M*C <= 4 Mi
+ * elements) and its grid co-resident, r3d_bn_bwd_reduce + r3d_bn_bwd_dz otherwise.  Same arguments and results. */
+int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
+               float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream);
 /* Weight gradient of a per-point layer: out (Ca,Cb; ld_out, caller-zeroed) += A^T B for A (M,Ca), B (M,Cb). */
 int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
                        r3d_stream_t stream);
