@@ -23,6 +23,8 @@
 
 #include <atomic>
 #include <cooperative_groups.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace r3d {
 
@@ -435,6 +437,38 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
             }
         }
     }
+    if (SPLITK == 1 && a.bn.y) {
+        // fused train-mode BatchNorm: the accumulators are the conv outputs z (no affine / activation in this mode)
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int col = n0 + (RT == 8 ? h * (TN / 2) : 0) + tc * 4;
+            float ca[4], cc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ca[j] = cc[j] = 0.f;
+                if (col + j < a.cout) pw_bn_coeffs(a, col + j, M, blockIdx.x == 0 && tr == 0, ca[j], cc[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const long long m = m0 + tr * RT + i;
+                if (m >= M) continue;
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = apply_act(fmaf(acc[i][h * 4 + j], ca[j], cc[j]), a.bn.act, a.bn.slope);
+                float* yr = a.bn.y + (size_t)m * a.cout;
+                if (col + 3 < a.cout && (a.cout & 3) == 0) {
+                    *reinterpret_cast<float4*>(yr + col) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < a.cout) yr[col + j] = o[j];
+                }
+            }
+        }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.bn.num_batches) *a.bn.num_batches += 1;
+    }
 }
 
 // ----------------------------------------------------------------------------------- small kernel
@@ -540,6 +574,26 @@ __global__ void __launch_bounds__(256) pw_small_kernel(PwArgs a) {
         for (int j = 0; j < kPwSmallMaxCout; j += 4)
             if (j < a.cout) *reinterpret_cast<float4*>(yr + j) = make_float4(outv[j], outv[j + 1], outv[j + 2], outv[j + 3]);
     }
+    if (a.bn.y) {
+        // fused train-mode BatchNorm (cooperative launch): outv holds this row's conv outputs z
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+        float* yr = a.bn.y + (size_t)m * a.cout;
+#pragma unroll
+        for (int j = 0; j < kPwSmallMaxCout; ++j) {
+            if (j >= a.cout) break;
+            float ca, cc;
+            pw_bn_coeffs(a, j, M, blockIdx.x == 0 && threadIdx.x == 0, ca, cc);
+            outv[j] = apply_act(fmaf(outv[j], ca, cc), a.bn.act, a.bn.slope);
+            if (live && (a.cout & 3) != 0) yr[j] = outv[j];
+        }
+        if (live && (a.cout & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < kPwSmallMaxCout; j += 4)
+                if (j < a.cout) *reinterpret_cast<float4*>(yr + j) = make_float4(outv[j], outv[j + 1], outv[j + 2], outv[j + 3]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.bn.num_batches) *a.bn.num_batches += 1;
+    }
 }
 
 }  // namespace r3d
@@ -551,6 +605,112 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
                                    const float* wT, const float* scale, const float* shift, int act, float slope,
                                    float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
                                    double* stats, int w_out_in, r3d_stream_t stream);
+
+// ------------------------------------------------------------------------------------- launch helpers
+// Launches a per-point kernel.  When the fused BatchNorm tail is wanted (a.bn.y) the launch must be cooperative (grid
+// barrier) and the whole grid co-resident; otherwise a.bn.y is cleared and the caller runs r3d_bn_apply afterwards.
+template <typename Kern>
+static int pw_launch(Kern kern, dim3 grid, int threads, PwArgs& a, cudaStream_t st, bool* fused) {
+    if (a.bn.y) {
+        static std::mutex mu;
+        static std::unordered_map<const void*, int> per_sm_cache;
+        int per_sm = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = per_sm_cache.find(reinterpret_cast<const void*>(kern));
+            if (it == per_sm_cache.end()) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess) per_sm = 0;
+                per_sm_cache[reinterpret_cast<const void*>(kern)] = per_sm;
+            } else {
+                per_sm = it->second;
+            }
+        }
+        if ((long long)grid.x * grid.y * grid.z <= (long long)per_sm * kNumSMs) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+            if (fused) *fused = true;
+            return R3D_OK;
+        }
+        a.bn.y = nullptr;
+    }
+    kern<<<grid, threads, 0, st>>>(a);
+    return R3D_OK;
+}
+
+static int pw_run(PwArgs a, cudaStream_t st, bool* fused) {
+    const int ca = a.ca, cb = a.cb, cout = a.cout;
+    const long long M = (long long)a.B * a.n;
+    if (fused) *fused = false;
+    if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
+        int rc = pw_launch(pw_small_kernel, dim3((unsigned)((M + 255) / 256)), 256, a, st, fused);
+        if (rc != R3D_OK) return rc;
+        R3D_LAUNCH_CHECK("pw_small_kernel");
+        return R3D_OK;
+    }
+    const bool aligned = (ca % 4 == 0) && (cb % 4 == 0);
+    if (g_pw_tensor_cores.load() && pw_tc_eligible(a, g_pw_tensor_cores.load() == 2)) {
+        a.bn.y = nullptr;
+        return pw_tc_launch(a, st);
+    }
+    int rc = R3D_OK;
+    if (!aligned) {
+        a.bn.y = nullptr;
+        dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
+        pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
+    } else if (M <= 2048 && ca + cb >= 128) {
+        // a few hundred rows of a wide layer (the bottom of the encoder / decoder of a small cloud): the kernel is a
+        // chain of load -> barrier -> FMA steps on a handful of CTAs, each step exposed to the full L2 latency.
+        // 32-channel steps halve the chain, 32-row tiles put 2-4x more CTAs on the machine.
+        const long long tiles32 = ((M + 31) / 32) * ((cout + 31) / 32);
+        if (tiles32 <= 2 * kNumSMs && ca + cb >= 256) {
+            // long contraction on few tiles: clusters of 4 CTAs split the input channels (see SPLITK above)
+            a.bn.y = nullptr;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((M + 31) / 32), (cout + 31) / 32, 4);
+            cfg.blockDim = dim3(64);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 4;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, pw_gemm_fast_kernel<32, 32, 4, 32, 4>, a));
+        } else if (tiles32 <= 2 * kNumSMs) {
+            rc = pw_launch(pw_gemm_fast_kernel<32, 32, 4, 32>, dim3((unsigned)((M + 31) / 32), (cout + 31) / 32), 64, a, st,
+                           fused);
+        } else {
+            rc = pw_launch(pw_gemm_fast_kernel<32, 64, 4, 32>, dim3((unsigned)((M + 31) / 32), (cout + 63) / 64), 128, a, st,
+                           fused);
+        }
+    } else if (M <= 64 * 4 * kNumSMs / ((cout + 63) / 64)) {
+        // few rows: 64x64 tiles of 256 threads (4x4 per thread) put more CTAs and warps on the machine
+        rc = pw_launch(pw_gemm_fast_kernel<64, 64, 4>, dim3((unsigned)((M + 63) / 64), (cout + 63) / 64), 256, a, st, fused);
+    } else if (cout <= 32) {
+        rc = pw_launch(pw_gemm_fast_kernel<256, 32, 8>, dim3((unsigned)((M + 255) / 256), (cout + 31) / 32), 128, a, st,
+                       fused);
+    } else if (cout <= 64 || M < 64 * 148) {
+        rc = pw_launch(pw_gemm_fast_kernel<128, 64, 8>, dim3((unsigned)((M + 127) / 128), (cout + 63) / 64), 128, a, st,
+                       fused);
+    } else {
+        rc = pw_launch(pw_gemm_fast_kernel<64, 128, 8>, dim3((unsigned)((M + 63) / 64), (cout + 127) / 128), 128, a, st,
+                       fused);
+    }
+    if (rc != R3D_OK) return rc;
+    R3D_LAUNCH_CHECK("pw_gemm_kernel");
+    return R3D_OK;
+}
 
 extern "C" int r3d_pointwise(const float* xa, long long xa_bstride, int ca, const int32_t* gidx,
                              long long gidx_bstride, const float* xb, long long xb_bstride, int cb, const float* wT,
@@ -580,61 +740,29 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
     if ((ca % 4 == 0 && (xa_bstride % 4)) || (cb > 0 && cb % 4 == 0 && (xb_bstride % 4))) return R3D_EALIGN;
     PwArgs a{xa, xa_bstride, ca, gidx, gidx_bstride, xb, xb_bstride, cb, wT, scale, shift, act, slope,
              y, y_bstride, y_ld, cout, B, n, transpose_out, stats, w_out_in};
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long M = (long long)B * n;
-    if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
-        pw_small_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(a);
-        R3D_LAUNCH_CHECK("pw_small_kernel");
-        return R3D_OK;
-    }
-    const bool aligned = (ca % 4 == 0) && (cb % 4 == 0);
-    if (g_pw_tensor_cores.load() && pw_tc_eligible(a, g_pw_tensor_cores.load() == 2)) return pw_tc_launch(a, st);
-    if (!aligned) {
-        dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
-        pw_gemm_kernel<128, 64><<<grid, 128, 0, st>>>(a);
-    } else if (M <= 2048 && ca + cb >= 128) {
-        // a few hundred rows of a wide layer (the bottom of the encoder / decoder of a small cloud): the kernel is a
-        // chain of load -> barrier -> FMA steps on a handful of CTAs, each step exposed to the full L2 latency.
-        // 32-channel steps halve the chain, 32-row tiles put 2-4x more CTAs on the machine.
-        const long long tiles32 = ((M + 31) / 32) * ((cout + 31) / 32);
-        if (tiles32 <= 2 * kNumSMs && ca + cb >= 256) {
-            // long contraction on few tiles: clusters of 4 CTAs split the input channels (see SPLITK above)
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)((M + 31) / 32), (cout + 31) / 32, 4);
-            cfg.blockDim = dim3(64);
-            cfg.dynamicSmemBytes = 0;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 1;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 4;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, pw_gemm_fast_kernel<32, 32, 4, 32, 4>, a));
-        } else if (tiles32 <= 2 * kNumSMs) {
-            dim3 grid((unsigned)((M + 31) / 32), (cout + 31) / 32);
-            pw_gemm_fast_kernel<32, 32, 4, 32><<<grid, 64, 0, st>>>(a);
-        } else {
-            dim3 grid((unsigned)((M + 31) / 32), (cout + 63) / 64);
-            pw_gemm_fast_kernel<32, 64, 4, 32><<<grid, 128, 0, st>>>(a);
-        }
-    } else if (M <= 64 * 4 * kNumSMs / ((cout + 63) / 64)) {
-        // few rows: 64x64 tiles of 256 threads (4x4 per thread) put more CTAs and warps on the machine
-        dim3 grid((unsigned)((M + 63) / 64), (cout + 63) / 64);
-        pw_gemm_fast_kernel<64, 64, 4><<<grid, 256, 0, st>>>(a);
-    } else if (cout <= 32) {
-        dim3 grid((unsigned)((M + 255) / 256), (cout + 31) / 32);
-        pw_gemm_fast_kernel<256, 32, 8><<<grid, 128, 0, st>>>(a);
-    } else if (cout <= 64 || M < 64 * 148) {
-        dim3 grid((unsigned)((M + 127) / 128), (cout + 63) / 64);
-        pw_gemm_fast_kernel<128, 64, 8><<<grid, 128, 0, st>>>(a);
-    } else {
-        dim3 grid((unsigned)((M + 63) / 64), (cout + 127) / 128);
-        pw_gemm_fast_kernel<64, 128, 8><<<grid, 128, 0, st>>>(a);
-    }
-    R3D_LAUNCH_CHECK("pw_gemm_kernel");
-    return R3D_OK;
+    return pw_run(a, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+// Train-mode SharedMLP forward on dense rows: z = W x with batch statistics, then y = act(BatchNorm_batch(z)).  One
+// cooperative launch (grid barrier between the statistics and the normalisation, outputs still in registers) when
+// the layer's grid is co-resident and its kernel has the fused tail; r3d_pointwise_stats + r3d_bn_apply otherwise.
+extern "C" int r3d_pointwise_bn(const float* x, long long M, int cin, const float* w, int cout, double* stats,
+                                const float* gamma, const float* beta, const float* bias, float eps, float momentum,
+                                float* running_mean, float* running_var, long long* num_batches, int act,
+                                float slope, float* z, float* y, float* save, r3d_stream_t stream) {
+    if (M < 0 || M > 0x7fffffffLL || cin <= 0 || cout <= 0 || act < 0 || act > 2) return R3D_EINVAL;
+    if (M == 0) return R3D_OK;
+    if (!x || !w || !stats || !gamma || !beta || !z || !y || !save) return R3D_EINVAL;
+    if (!is_aligned(x, 16) || !is_aligned(w, 16) || !is_aligned(z, 16) || !is_aligned(y, 16)) return R3D_EALIGN;
+    PwArgs a{x, (long long)M * cin, cin, nullptr, 0, nullptr, 0, 0, w, nullptr, nullptr, 0, 0.f,
+             z, (long long)M * cout, cout, cout, 1, (int)M, 0, stats, 1};
+    a.bn = PwBnArgs{y, gamma, beta, bias, eps, momentum, running_mean, running_var, num_batches, save, act, slope};
+    if (!(bn_fused_mask() & 1)) a.bn.y = nullptr;
+    bool fused = false;
+    const int rc = pw_run(a, static_cast<cudaStream_t>(stream), &fused);
+    if (rc != R3D_OK || fused) return rc;
+    return r3d_bn_apply(z, stats, M, cout, gamma, beta, bias, eps, momentum, running_mean, running_var, num_batches, act,
+                        slope, y, save, stream);
 }
 
 // Which kernel r3d_pointwise runs for a layer under the current settings: 0 pw_small_kernel (thin layers, weights in

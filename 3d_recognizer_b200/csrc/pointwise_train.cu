@@ -13,8 +13,11 @@
 #include "common.cuh"
 
 #include <cooperative_groups.h>
+#include <atomic>
 
 namespace r3d {
+
+int bn_fused_mask();     // r3d_bn_set_fused, also read by pointwise.cu
 
 constexpr int kBnMaxC = 1024;
 
@@ -499,6 +502,18 @@ extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C
     return R3D_OK;
 }
 
+// Single-launch (cooperative, grid barrier) variants of the train-mode BatchNorm: bit 0 forward (r3d_pointwise_bn),
+// bit 1 backward (r3d_bn_bwd).  Default 0: measured on the 8 x 2 500-point step (same box, CUDA-graph replay, two
+// rounds) both fused 2.99 ms, forward only 2.86, backward only 2.80-2.91, none 2.77-2.89 -- a cooperative launch
+// needs its whole grid resident at once and so does not overlap the side-stream kernels the step relies on, which
+// costs more than the saved launch.  Returns the previous mask; a negative argument only queries.
+static std::atomic<int> g_bn_fused{0};
+int r3d::bn_fused_mask() { return g_bn_fused.load(); }
+extern "C" int r3d_bn_set_fused(int mask) {
+    if (mask < 0 || mask > 3) return g_bn_fused.load();
+    return g_bn_fused.exchange(mask);
+}
+
 extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
                           int act, float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
     if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
@@ -517,7 +532,7 @@ extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, c
     const int rows_per_pass = 256 / (C / 4) > 0 ? 256 / (C / 4) : 1;
     const long long want = (M + (long long)rows_per_pass * 2 - 1) / ((long long)rows_per_pass * 2);
     const long long resident = (long long)kNumSMs * (max_blocks_per_sm < 4 ? max_blocks_per_sm : 4);
-    if (M * C <= (1LL << 22) && resident > 0) {
+    if ((bn_fused_mask() & 2) && M * C <= (1LL << 22) && resident > 0) {
         const long long blocks = want < resident ? want : resident;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(blocks < 1 ? 1 : blocks));

@@ -101,8 +101,7 @@ class _SharedMLPTrainFn(torch.autograd.Function):
         cout = w.shape[0]
         scratch = ops.zeros(4 * cout, torch.float64, x.device)   # forward stats | backward stats
         stats = scratch[:2 * cout]
-        z = ops.pointwise(x.unsqueeze(0), w.contiguous(), stats=stats, w_out_in=True).squeeze(0)
-        y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
+        z, y, save = ops.pointwise_bn(x, w.contiguous(), stats, bn, bias, act, slope)
         ctx.act, ctx.slope = act, slope
         ctx.save_for_backward(x, w, z, save, beta, scratch)
         return y

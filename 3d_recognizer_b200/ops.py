@@ -274,6 +274,41 @@ def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bia
     return y, save
 
 
+def pointwise_bn(x: torch.Tensor, w: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d,
+                 bias: Optional[torch.Tensor], act, slope: float = 0.0):
+    """Train-mode SharedMLP forward on dense rows (C ABI ``r3d_pointwise_bn``): x (M,cin), w (cout,cin), stats (2*cout)
+    zero-filled fp64.  One cooperative launch when the layer's grid is co-resident, GEMM + ``bn_apply`` otherwise.
+    Updates bn's running statistics in place.  Returns (z (M,cout), y (M,cout), save (3,cout))."""
+    _cabi.require_cuda(x, "x")
+    M, cin = x.shape
+    cout = w.shape[0]
+    dev = x.device
+    if not (_cabi.lib().r3d_bn_set_fused(-1) & 1):
+        # default: two launches, each under its own name in bench.py's kernel table
+        z = pointwise(x.unsqueeze(0), w, stats=stats, w_out_in=True).squeeze(0)
+        y, save = bn_apply(z, stats, bn, bias, act, slope)
+        return z, y, save
+    z = torch.empty((M, cout), dtype=torch.float32, device=dev)
+    y = torch.empty((M, cout), dtype=torch.float32, device=dev)
+    save = torch.empty((3, cout), dtype=torch.float32, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    tname = "pointwise_bn"
+    if _cabi.KERNEL_TIMERS is not None:
+        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc")[_cabi.lib().r3d_pointwise_plan(cin, 0, cout, M, 0)]
+        if _cabi.TIMER_SHAPES:
+            tname += f"[M={M},{cin}->{cout},bn]"
+    with torch.cuda.device(dev), _cabi.kernel_timer(tname, flops=2.0 * M * cin * cout + 4.0 * M * cout,
+                                                    bytes=4.0 * M * (cin + 2 * cout)):
+        rc = _cabi.lib().r3d_pointwise_bn(
+            _cabi.ptr(x), M, cin, _cabi.ptr(w), cout, _cabi.ptr(stats), _cabi.ptr(bn.weight.detach()),
+            _cabi.ptr(bn.bias.detach()), _cabi.ptr(bias.detach()) if bias is not None else None, float(bn.eps),
+            float(bn.momentum), _cabi.ptr(bn.running_mean) if track else None,
+            _cabi.ptr(bn.running_var) if track else None, _cabi.ptr(bn.num_batches_tracked) if track else None,
+            _ACT[act], float(slope), _cabi.ptr(z), _cabi.ptr(y), _cabi.ptr(save), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_pointwise_bn")
+    return z, y, save
+
+
 def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0,
                 stats2: Optional[torch.Tensor] = None):
     """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd``: the reduce and dz passes, one

@@ -251,14 +251,25 @@ int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int transpose_o
 int r3d_bn_apply(const float* z, const double* stats, long long M, int C, const float* gamma, const float* beta,
                  const float* bias, float eps, float momentum, float* running_mean, float* running_var,
                  long long* num_batches, int act, float slope, float* y, float* save, r3d_stream_t stream);
+/* Train-mode SharedMLP forward in one call: z (M,cout) = x (M,cin) W^T with W (cout,cin), stats (2*cout fp64,
+ * caller-zeroed) += batch sums, then y = act(BatchNorm_batch(z)) and the running statistics / save (3,cout) exactly as
+ * r3d_bn_apply.  Runs as r3d_pointwise_stats + r3d_bn_apply, or (r3d_bn_set_fused bit 0) as ONE cooperative launch
+ * with a grid barrier when the layer's grid is co-resident; results are identical.  C % 4 == 0 as for r3d_bn_apply. */
+int r3d_pointwise_bn(const float* x, long long M, int cin, const float* w, int cout, double* stats, const float* gamma,
+                     const float* beta, const float* bias, float eps, float momentum, float* running_mean,
+                     float* running_var, long long* num_batches, int act, float slope, float* z, float* y, float* save,
+                     r3d_stream_t stream);
+/* Enables the single-launch (cooperative) variants: bit 0 r3d_pointwise_bn, bit 1 r3d_bn_bwd.  Default 0 (measured
+ * slower inside the multi-stream training step, see csrc/pointwise_train.cu).  Returns the previous mask. */
+int r3d_bn_set_fused(int mask);
 /* Backward: du = dy * act'(a z + c); stats2[2C] (fp64, caller-zeroed) += (sum du, sum du*zhat) = (dbeta, dgamma);
  * then dz = a (du - mean(du) - zhat * mean(du*zhat)); dgb (2C fp32, nullable) receives (dbeta, dgamma) rounded. */
 int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
                       int act, float slope, double* stats2, r3d_stream_t stream);
 int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
                   float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream);
-/* Both passes: one cooperative launch (grid barrier between the passes) while the tensor is small (M*C <= 4 Mi
- * elements) and its grid co-resident, r3d_bn_bwd_reduce + r3d_bn_bwd_dz otherwise.  Same arguments and results. */
+/* Both passes: r3d_bn_bwd_reduce + r3d_bn_bwd_dz, or (r3d_bn_set_fused bit 1) one cooperative launch with a grid
+ * barrier between the passes while the tensor is small (M*C <= 4 Mi elements).  Same arguments and results. */
 int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
                float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream);
 /* Weight gradient of a per-point layer: out (Ca,Cb; ld_out, caller-zeroed) += A^T B for A (M,Ca), B (M,Cb). */

@@ -137,9 +137,22 @@ def test_lfa_block_fused_vs_autograd(mods, n_in, d, K, N, train):
 @pytest.mark.parametrize("M,cin,cout,act", [(5000, 8, 8, "lrelu"), (1237, 3, 8, "lrelu"), (2048, 64, 32, "relu"),
                                             (700, 512, 512, "relu"), (333, 1024, 256, "relu"), (40000, 16, 32, None),
                                             (8192, 512, 512, "relu"), (5000, 96, 128, "relu"), (16384, 64, 32, "lrelu")])
-def test_shared_mlp_train_kernels_vs_torch(mods, M, cin, cout, act):
+@pytest.mark.parametrize("fused", [0, 3])
+def test_shared_mlp_train_kernels_vs_torch(mods, M, cin, cout, act, fused):
     """Train-mode SharedMLP (GEMM + batch-stat BatchNorm + activation) forward, dx, dW, dgamma, dbeta and the
-    running statistics: sm_100a per-point kernels vs fp64 tensor ops."""
+    running statistics: sm_100a per-point kernels vs fp64 tensor ops.  ``fused`` = r3d_bn_set_fused mask: the default
+    two-launch BatchNorm forward / backward, and the single cooperative launches."""
+    import copy
+    import importlib
+    L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+    prev = L.r3d_bn_set_fused(fused)
+    try:
+        _shared_mlp_train_case(mods, M, cin, cout, act)
+    finally:
+        L.r3d_bn_set_fused(prev)
+
+
+def _shared_mlp_train_case(mods, M, cin, cout, act):
     import copy
     modules, engine, _ = mods
     dev = torch.device("cuda")
