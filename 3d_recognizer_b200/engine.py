@@ -509,7 +509,9 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
         out = LFA_IMPL(lfa, xyz[:, :n_l], cur, enc_idx[lvl]) if lvl in enc_idx else LFA_IMPL(lfa, xyz[:, :n_l], cur)
         skips.append(out)
         n_l //= dec
-        cur = out[:, :n_l]
+        # random down-sampling = a prefix of the permuted cloud (modules.py:583); one dense copy here instead of one in
+        # every consumer of the strided view (mlp1 and shortcut of the next block, forward and backward)
+        cur = out[:, :n_l].contiguous() if out.is_cuda else out[:, :n_l]
     cur = shared_mlp(net.mlp, cur)
     for lvl, stage in enumerate(net.decoder):
         n_up = skips[-1].shape[1]          # N // dec^(l-1): the encoder level this stage returns to
