@@ -37,7 +37,7 @@ class _ZeroPool:
         aligned = (nbytes + 255) & ~255
         self.need += aligned
         # a block filled outside a CUDA-graph capture must not feed a captured step: its fill would not be replayed
-        capturing = torch.cuda.is_current_stream_capturing()
+        capturing = torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing()
         if (self.block is None or self.block.device != torch.device(device) or capturing != self.captured
                 or self.off + aligned > self.block.numel()):
             self.block = torch.zeros(max(self.hint, aligned), dtype=torch.uint8, device=device)

@@ -175,3 +175,51 @@ def test_sample_points_matches_reference_protocol():
     np.random.seed(5)
     assert np.array_equal(c, onet.sample_points(30, 2500, consistent=False))
     assert c.shape == (2500,) and c.max() < 30
+
+
+def test_zero_pool_hands_out_fresh_zero_slices(r3d):
+    """ops._ZeroPool (scratch for the kernels' atomics): every slice is zero-filled, aligned, disjoint from all earlier
+    ones for as long as they are referenced, sized from the previous step, and large requests bypass the pool."""
+    ops = importlib.import_module("3d_recognizer_b200.ops")
+    pool = ops._ZeroPool()
+    a = pool.take((3, 5), torch.float64, "cpu")
+    b = pool.take(7, torch.float32, "cpu")
+    assert a.shape == (3, 5) and a.dtype == torch.float64 and float(a.abs().sum()) == 0.0
+    assert b.shape == (7,) and float(b.abs().sum()) == 0.0
+    assert a.data_ptr() % 8 == 0 and (b.data_ptr() - a.data_ptr()) % 256 == 0
+    a.fill_(1.0)
+    b.fill_(2.0)
+    c = pool.take(1000, torch.float32, "cpu")
+    assert float(c.abs().sum()) == 0.0 and float(a.sum()) == 15.0 and float(b.sum()) == 14.0    # no aliasing
+    need = pool.need
+    pool.begin()                                                    # step boundary: new block, sized by the last step
+    assert pool.hint >= need and pool.block is None
+    d = pool.take((3, 5), torch.float64, "cpu")
+    assert float(d.abs().sum()) == 0.0 and float(a.sum()) == 15.0   # the previous step's buffers stay valid
+    big = pool.take(pool.MAX_BYTES // 4 + 1, torch.float32, "cpu")  # too large: its own allocation
+    assert float(big.abs().sum()) == 0.0 and big.numel() == pool.MAX_BYTES // 4 + 1
+    grown = [pool.take(1 << 16, torch.float32, "cpu") for _ in range(8)]   # outgrows the hint: further blocks
+    assert all(float(t.abs().sum()) == 0.0 for t in grown)
+    assert len({t.data_ptr() for t in grown}) == 8
+
+
+def test_knn_and_pointwise_plans_are_pure_functions_of_the_shape(built_lib):
+    """r3d_knn_plan / r3d_pointwise_plan / r3d_lfa_tile_points_for (host-only dispatch rules, no GPU needed)."""
+    L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+    assert L.r3d_knn_set_algorithm(-1) == 0
+    assert L.r3d_knn_plan(8, 2500, 2500, 16) == 2                      # uniform grid from 2048 support points
+    assert L.r3d_knn_plan(8, 625, 625, 16) in (2, 3) and L.r3d_knn_plan(8, 156, 156, 16) == 3
+    assert L.r3d_knn_plan(8, 625, 2500, 1) == 3                        # decoder 1-NN on a small support
+    prev = L.r3d_knn_set_algorithm(1)
+    try:
+        assert L.r3d_knn_plan(8, 156, 156, 16) == 1
+    finally:
+        L.r3d_knn_set_algorithm(prev)
+    assert L.r3d_pointwise_plan(3, 0, 8, 20000, 0) == 0                 # thin layer: weights in shared memory
+    assert L.r3d_pointwise_plan(64, 0, 128, 5000, 0) == 2               # FP32 GEMM
+    assert L.r3d_pointwise_plan(5, 0, 64, 5000, 0) == 1                 # channels not a multiple of 4
+    assert L.r3d_pointwise_plan(512, 0, 256, 1 << 20, 0) == 3           # tcgen05: many rows, long contraction
+    assert L.r3d_pointwise_plan(64, 0, 128, 1 << 20, 0) == 2            # mid-size layers stay on FP32
+    assert L.r3d_lfa_tile_points(16, 128) == 8 and L.r3d_lfa_tile_points_for(16, 128, 8, 156) == 4
+    assert L.r3d_lfa_tile_points_for(16, 128, 64, 2560) == 8 and L.r3d_lfa_tile_points_for(16, 256, 8, 39) == 4
+    assert L.r3d_bn_set_fused(-1) == 0
