@@ -211,8 +211,9 @@ class GraphedTrainStep:
             self.loss = fwd_bwd()
             if self.flat is None:
                 optimizer.step()
+            else:
+                self.flat.rebind()          # the gather of the fresh gradients into the flat buffer is part of the graph
         if self.flat is not None:
-            self.flat.rebind()
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
                 optimizer.step()

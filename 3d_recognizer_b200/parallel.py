@@ -19,33 +19,42 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class FlatGradients:
-    """Makes every parameter's ``.grad`` a view into one flat fp32 buffer, so that the data-parallel
-    reduction is a single collective on a single tensor."""
+    """One flat fp32 buffer for all gradients, so that the data-parallel reduction is a single collective on a single
+    tensor.  Per step: ``zero()`` clears the buffer and detaches every ``.grad`` (backward then hands each parameter a
+    fresh gradient tensor instead of running one in-place accumulation kernel per parameter into a pre-bound view:
+    ~100 tiny launches per step, measured as 0.25 ms of a 3 ms step), ``rebind()`` gathers the fresh gradients into the
+    buffer with one multi-tensor copy and makes every ``.grad`` a view of it, ``allreduce_mean()`` reduces it."""
 
     def __init__(self, module: torch.nn.Module):
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero(self) -> None:
         self.flat.zero_()
+        for p in self.params:
+            p.grad = None
 
     def rebind(self) -> None:
-        """Re-attach views after something replaced a ``.grad`` (e.g. zero_grad(set_to_none=True))."""
-        off = 0
-        for p in self.params:
-            view = self.flat[off:off + p.numel()].view_as(p)
-            if p.grad is None:
-                p.grad = view
-            elif p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
-                p.grad = view
-            off += p.numel()
+        """Gather the gradients backward produced into the flat buffer (one multi-tensor copy) and re-attach the
+        views; parameters without a gradient keep their zero slot."""
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def allreduce_mean(self, group=None) -> None:
         if not (dist.is_available() and dist.is_initialized()):
