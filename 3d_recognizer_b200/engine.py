@@ -74,6 +74,7 @@ class _fork:
         key = (device.index if device.index is not None else torch.cuda.current_device(), lane)
         if key not in _SIDE_STREAMS:
             _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+            ops.SIDE_STREAMS.add(_SIDE_STREAMS[key].cuda_stream)
         self.side = _SIDE_STREAMS[key]
         self.ctx = None
 
@@ -294,9 +295,10 @@ class _LfaPool1TrainFn(torch.autograd.Function):
         dfeat, dws, _, _, _ = ops.lfa_pool_bwd(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, None, wsT,
                                                ws.contiguous(), dpooled, g1_acc=g1)
         # stage 2's second BatchNorm pass (side stream, see _LfaPool2TrainFn.backward) has been adding to g1 too
-        dw2, dgamma2, dbeta2, fork = ctx.shared.pop("stage2", (None, None, None, None))
+        dw2, dgamma2, dbeta2, fork, keep_alive = ctx.shared.pop("stage2", (None, None, None, None, None))
         if fork is not None:
             fork.join()
+        del keep_alive
         dw1, dgamma1, dbeta1 = ops.lfa_rpe1_grads(w1f, m[10], m, ctx.count, gamma1.detach().contiguous(), save1, g1)
         return (None, None, dfeat, dws, dw1.view(ctx.w1_shape), dgamma1, dbeta1, dw2, dgamma2, dbeta2) + (None,) * 8
 
@@ -338,7 +340,10 @@ class _LfaPool2TrainFn(torch.autograd.Function):
             bn2, dgamma2, dbeta2 = ops.lfa_bn2_coeffs(sums, a2f, c2f, save2, float(idx32.numel()))
             _, dw2 = ops.lfa_bn2_bwd(xyz, idx32, w1f, a1f, c1f, du2, w2T, w2f, bn2, h, g1_acc=g1)
             dw2 = dw2.float().view(ctx.w2_shape)
-        ctx.shared["stage2"] = (dw2, dgamma2, dbeta2, fork)
+        # du2 and w2T were allocated on the main stream and are read by the side stream: everything the forked launches
+        # read stays referenced until the join (a freed block returns to the main stream's pool -- autograd drops the
+        # saved tensors when this function returns -- and could be handed out again while pass 2 still reads it)
+        ctx.shared["stage2"] = (dw2, dgamma2, dbeta2, fork, (du2, sums, bn2, w2T, a2f, c2f, save2))
         return (None, None, dfeat, dws) + (None,) * 9
 
 

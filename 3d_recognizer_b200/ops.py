@@ -42,12 +42,21 @@ class _ZeroPool:
                 or self.off + aligned > self.block.numel()):
             self.block = torch.zeros(max(self.hint, aligned), dtype=torch.uint8, device=device)
             self.off, self.captured = 0, capturing
+            if torch.device(device).type == "cuda" and not capturing:
+                # A block filled on a side stream (engine._fork registers them in SIDE_STREAMS) is used by the parent
+                # stream before the join: the fill must have completed first.  This only happens while a shape's
+                # first steps outgrow the block (afterwards it is sized by ``hint`` and allocated once per step on
+                # the main stream, whose forks are ordered behind it); a captured step never allocates mid-capture.
+                cur = torch.cuda.current_stream(device)
+                if cur.cuda_stream in SIDE_STREAMS:
+                    cur.synchronize()
         out = self.block[self.off:self.off + nbytes].view(dtype).view(shape)
         self.off += aligned
         return out
 
 
 ZEROS = _ZeroPool()
+SIDE_STREAMS = set()         # raw handles of the side streams engine._fork runs launches on
 
 
 def zeros(shape, dtype, device):
