@@ -74,6 +74,11 @@ SIGNATURES = {
                                   ctypes.c_float, c_void_p, c_void_p]),
     "r3d_bn_bwd_dz": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, ctypes.c_float,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_tversky_loss_fwd": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
+                                     c_int, c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "r3d_tversky_loss_bwd": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_pointwise_bn": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int,
                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

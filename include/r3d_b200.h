@@ -208,6 +208,18 @@ int r3d_lfa_rpe1_grads(const float* W, int cout, int cin, const double* S, int s
 int r3d_lfa_bn2_coeffs(const double* sums, const float* a2, const float* c2, const double* save, double rows, int h,
                        float* bn2, float* dgamma, float* dbeta, r3d_stream_t stream);
 
+/* ------------------------------------------------------------------------- Focal-Tversky / Dice loss
+ * randlanet/utils/losses.py:66-86 via trainer.py:245-269: p = softmax over classes, TI_c = (TP_c + eps) /
+ * (TP_c + alpha FN_c + (1 - alpha) FP_c + eps), loss = mean over classes >= first_class of (1 - TI_c)^gamma.
+ * logits (B,C,N) fp32 addressed through element strides (sb, sc, sn); labels (B,N) int64 dense; C <= 16.
+ * fwd: acc (3,C) fp64 caller-zeroed scratch; writes *loss and coef (2,C) fp32 for the backward.
+ * bwd: dlogits (same strides as logits) = *gout (nullable: 1) * d loss / d logits. */
+int r3d_tversky_loss_fwd(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
+                         int C, int N, int first_class, float alpha, float gamma, float eps, double* acc, float* loss,
+                         float* coef, r3d_stream_t stream);
+int r3d_tversky_loss_bwd(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
+                         int C, int N, const float* coef, const float* gout, float* dlogits, r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,
