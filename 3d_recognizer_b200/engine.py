@@ -138,6 +138,12 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
+        if OVERLAP_WEIGHT_GRADS and ctx.needs_input_grad[0]:
+            with _fork(dy.device) as f:               # parameter gradients next to the input-gradient GEMM
+                dw, db = ops.rowreduce_gemm(dy, x), dy.sum(dim=0)
+            dx = ops.pointwise(dy.unsqueeze(0), w.contiguous()).squeeze(0)
+            f.join()
+            return dx, dw, db
         dx = ops.pointwise(dy.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
         return dx, ops.rowreduce_gemm(dy, x), dy.sum(dim=0)
 
@@ -278,7 +284,7 @@ class _LfaPool1TrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, idx32, feat, ws, w1, gamma1, beta1, w2, gamma2, beta2, w1f, a1f, c1f, m, save1, g1, count,
                 shared):
-        wsT = ws.t().contiguous()
+        wsT = shared["wT"][0] if "wT" in shared else ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
             pooled = ops.lfa_pool_tc(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, ws.contiguous())
         else:
@@ -316,8 +322,11 @@ class _LfaPool2TrainFn(torch.autograd.Function):
     def forward(ctx, xyz, idx32, feat, ws, w2, w1f, a1f, c1f, a2f, c2f, save2, g1, shared):
         h = w1f.shape[0]
         w2f = w2.detach().view(h, h)
-        w2T = w2f.t().contiguous()
-        wsT = ws.t().contiguous()
+        if "wT" in shared:
+            _, wsT, w2T = shared["wT"]
+        else:
+            w2T = w2f.t().contiguous()
+            wsT = ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
             pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f, a2f, c2f, ws.contiguous())
         else:
@@ -396,7 +405,16 @@ def _eval_affine(smlp):
     return a, bn.bias + (smlp.conv.bias - bn.running_mean) * a
 
 
-def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None) -> torch.Tensor:
+def lfa_transposed_weights(lfa):
+    """(pool1 score weight^T, pool2 score weight^T, mlp_rpe2 weight^T): the [in][out] layouts the fused kernels
+    stream.  Plain values (no autograd): the functions differentiate with respect to the parameters themselves."""
+    h = lfa.mlp_rpe2.conv.weight.shape[0]
+    with torch.no_grad():
+        return (lfa.pool1.score_fn[0].weight.t().contiguous(), lfa.pool2.score_fn[0].weight.t().contiguous(),
+                lfa.mlp_rpe2.conv.weight.view(h, h).t().contiguous())
+
+
+def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None, wT=None) -> torch.Tensor:
     """LocalFeatureAggregation (modules.py:298-325) with gradients: KNN and the two fused LocSE + pooling
     halves run on the sm_100a kernels (forward AND backward); the per-point layers around them are
     differentiable tensor ops.  Works in train mode (batch statistics) and eval mode (running statistics)."""
@@ -422,7 +440,7 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tenso
         bn1, bn2 = r1m.batch_norm, r2m.batch_norm
         count = float(xyz.shape[0] * xyz.shape[1] * K)
         g1 = ops.zeros((h, 16), torch.float64, xyz.device)       # mlp_rpe1's gradient accumulator, both halves
-        shared = {}
+        shared = {} if wT is None else {"wT": wT}
         # the statistics kernels of stage 2 depend on the encoding only, not on pooled1: they run on the side stream
         # next to stage 1's pooling kernel and pool1.mlp (every kernel here fills a fraction of the SMs at this size)
         with torch.no_grad():
@@ -491,9 +509,12 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     # Every neighbour search depends on the coordinates only.  With the fused kernels the searches of the
     # down-sampled levels and of the decoder's 1-NN up-sampling run on a side stream while level 0 is processed
     # (each is a few-microsecond kernel on a fraction of the SMs; ~75 us of a 3 ms step on the main chain otherwise).
-    pre_fork, enc_idx, dec_idx = None, {}, {}
+    pre_fork, enc_idx, dec_idx, enc_wT = None, {}, {}, {}
     if LFA_IMPL is lfa_block_fused and OVERLAP_WEIGHT_GRADS and xyz.is_cuda and L > 1:
         with torch.no_grad(), _fork(xyz.device, lane=3) as pre_fork:
+            if net.training:
+                for lvl in range(1, L):              # weight transposes of the later levels: off the main chain too
+                    enc_wT[lvl] = lfa_transposed_weights(net.encoder[lvl])
             sizes = [N]
             for lvl in range(L):
                 sizes.append(sizes[-1] // dec)       # points kept after level lvl (floor, modules.py:583)
@@ -511,7 +532,8 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     for lvl, lfa in enumerate(net.encoder):
         if lvl == 1 and pre_fork is not None:
             pre_fork.join()
-        out = LFA_IMPL(lfa, xyz[:, :n_l], cur, enc_idx[lvl]) if lvl in enc_idx else LFA_IMPL(lfa, xyz[:, :n_l], cur)
+        out = (LFA_IMPL(lfa, xyz[:, :n_l], cur, enc_idx[lvl], enc_wT.get(lvl)) if lvl in enc_idx
+               else LFA_IMPL(lfa, xyz[:, :n_l], cur))
         skips.append(out)
         n_l //= dec
         # random down-sampling = a prefix of the permuted cloud (modules.py:583); one dense copy here instead of one in
