@@ -132,8 +132,11 @@ class Model:
         the update runs as torch's fused multi-tensor Adam (one launch per ~100 parameters instead of sixteen
         foreach launches per step: 0.27 ms of a 4 ms step)."""
         on_gpu = self._model.device.type == "cuda"
-        return torch.optim.Adam(self._model.parameters(), lr=learning_rate, capturable=capturable and on_gpu,
-                                fused=on_gpu)
+        capturable = capturable and on_gpu
+        # a capturable optimiser keeps the learning rate in a device tensor: the reference's StepLR scheduler
+        # (trainer.py:82) then updates it in place and a replayed graph sees the new value
+        lr = torch.tensor(float(learning_rate), device=self._model.device) if capturable else learning_rate
+        return torch.optim.Adam(self._model.parameters(), lr=lr, capturable=capturable, fused=on_gpu)
 
     def train_step(self, input, labels, optimizer: torch.optim.Optimizer, loss_function: str = "dice",
                    flat_grads=None) -> torch.Tensor:

@@ -195,3 +195,11 @@ def test_graphed_train_step_matches_eager(mods):
     # Adam normalises every gradient to a step of about lr, also where the gradient is pure round-off, so after four
     # steps two correct runs may differ by up to ~2 * 4 * lr in such parameters; the loss trajectory above is the check
     assert float((pa - pb).abs().max()) < 2 * 4 * 1e-3 + 1e-4
+    # the reference's StepLR (trainer.py:82) must reach the replayed optimiser: lr -> 0 freezes the parameters
+    sched = torch.optim.lr_scheduler.StepLR(opt_b, step_size=1, gamma=0.0)
+    sched.step()
+    assert float(opt_b.param_groups[0]["lr"]) == 0.0
+    before = torch.cat([p.detach().flatten() for p in b.module.parameters()]).clone()
+    gstep(x, y)
+    after = torch.cat([p.detach().flatten() for p in b.module.parameters()])
+    assert torch.equal(before, after)
