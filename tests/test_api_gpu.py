@@ -203,3 +203,43 @@ def test_graphed_train_step_matches_eager(mods):
     gstep(x, y)
     after = torch.cat([p.detach().flatten() for p in b.module.parameters()])
     assert torch.equal(before, after)
+
+
+@pytest.mark.parametrize("bound", [False, True])
+def test_flat_adam_matches_torch_adam(mods, bound):
+    """model.FlatAdam (one fused launch over a flat buffer the parameters are views of) == torch.optim.Adam on the
+    same gradients, also with the data-parallel flat gradient buffer bound, and with parameters that get no gradient."""
+    modules, _, model_mod = mods
+    parallel = importlib.import_module("3d_recognizer_b200.parallel")
+    torch.manual_seed(1)
+    net_a = modules.SharedMLP(8, 16, activation=torch.nn.ReLU()).cuda()
+    net_b = copy.deepcopy(net_a)
+    opt_a = torch.optim.Adam(net_a.parameters(), lr=3e-3)
+    opt_b = model_mod.FlatAdam(net_b, 3e-3, capturable=False)
+    flat = parallel.FlatGradients(net_b) if bound else None
+    if bound:
+        opt_b.bind_flat_gradients(flat.flat)
+    assert all(pb.data_ptr() != pa.data_ptr() for pa, pb in zip(net_a.parameters(), net_b.parameters()))
+    for step in range(3):
+        g = torch.Generator(device="cuda").manual_seed(step)
+        grads = [torch.randn(p.shape, device="cuda", generator=g) for p in net_a.parameters()]
+        if bound:
+            flat.zero()
+        else:
+            opt_b.zero_grad()
+        opt_a.zero_grad()
+        for i, (pa, pb, gr) in enumerate(zip(net_a.parameters(), net_b.parameters(), grads)):
+            if i == 1:
+                continue                         # the conv bias gets no gradient (None): must stay untouched
+            pa.grad = gr.clone()
+            pb.grad = gr.clone()
+        if bound:
+            flat.rebind()
+        opt_a.step()
+        opt_b.step()
+    for (k, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7), k
+    sd = net_b.state_dict()                          # checkpoints still see ordinary tensors
+    net_c = modules.SharedMLP(8, 16, activation=torch.nn.ReLU()).cuda()
+    net_c.load_state_dict(sd)
+    assert all(torch.equal(pb, pc) for pb, pc in zip(net_b.parameters(), net_c.parameters()))
