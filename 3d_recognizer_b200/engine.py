@@ -495,7 +495,10 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     if inp.is_cuda:
         ops.ZEROS.begin()          # one zero-filled scratch block for this forward/backward (ops._ZeroPool)
 
-    inp = inp.float()
+    # The reference permutes coordinates and features after fc_start (modules.py:565-573).  fc_start + BatchNorm act
+    # per point (the batch statistics are sums over points), so permuting the INPUT once gives the same tensors with
+    # one gather instead of two and no scatter at the very end of the backward.
+    inp = inp.float().index_select(1, perm)
     bn0 = net.bn_start[0]
     if USE_POINTWISE_KERNELS and _kernel_layer_ok(inp, bn0):
         feat = _SharedMLPTrainFn.apply(inp.reshape(B * N, -1), net.fc_start.weight, net.fc_start.bias, bn0.weight,
@@ -503,8 +506,7 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     else:
         feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
         feat = F.leaky_relu(batch_norm_lastdim(bn0, feat), net.bn_start[1].negative_slope)
-    xyz = inp[..., :3].index_select(1, perm).contiguous()
-    feat = feat.index_select(1, perm)
+    xyz = inp[..., :3].contiguous()
 
     # Every neighbour search depends on the coordinates only.  With the fused kernels the searches of the
     # down-sampled levels and of the decoder's 1-NN up-sampling run on a side stream while level 0 is processed
