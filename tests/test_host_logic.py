@@ -223,3 +223,38 @@ def test_knn_and_pointwise_plans_are_pure_functions_of_the_shape(built_lib):
     assert L.r3d_lfa_tile_points(16, 128) == 8 and L.r3d_lfa_tile_points_for(16, 128, 8, 156) == 4
     assert L.r3d_lfa_tile_points_for(16, 128, 64, 2560) == 8 and L.r3d_lfa_tile_points_for(16, 256, 8, 39) == 4
     assert L.r3d_bn_set_fused(-1) == 0
+
+
+def test_bench_roofline_picks_the_dominant_kernel_family():
+    """bench.py: per-kernel event samples -> table (event-pair overhead removed) -> roofline entry of the kernel with
+    the largest summed time, the two halves of an LFA block counted as one kernel, bound = the slower of FP32 / HBM."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.kernel_family("lfa_pool2_bwd[N=156,d=128]") == "lfa_pool_bwd"
+    assert bench.kernel_family("lfa_pool1[N=39,d=256]") == "lfa_pool"
+    assert bench.kernel_family("pw_gemm_fast[M=312,512->256]") == "pw_gemm_fast"
+
+    class Ev:                                          # stands in for a pair of CUDA events
+        def __init__(self, ms):
+            self.ms = ms
+
+        def elapsed_time(self, other):
+            return other.ms - self.ms
+
+    timers = {
+        "lfa_pool1_bwd[N=156,d=128]": [(Ev(0.0), Ev(0.103), dict(flops=2.0e9, bytes=6.0e6))],
+        "lfa_pool2_bwd[N=156,d=128]": [(Ev(0.0), Ev(0.113), dict(flops=2.2e9, bytes=1.1e7))],
+        "bn_apply[M=20000,C=8]": [(Ev(0.0), Ev(0.009), dict(flops=6.4e5, bytes=1.3e6)) for _ in range(4)],
+    }
+    tab = bench.kernel_table(timers, overhead_ms=0.003)
+    assert abs(tab["lfa_pool1_bwd[N=156,d=128]"]["ms_avg"] - 0.100) < 1e-9 and tab["bn_apply[M=20000,C=8]"]["launches"] == 4
+    roof = bench.roofline_of(tab, dict(hbm_gbs=6548.5, source="test"), dict(ffma=71.0, ffma2=74.0))
+    assert roof["kernel"] == "lfa_pool_bwd" and roof["launches"] == 2 and roof["bound"] == "fp32"
+    assert abs(roof["achieved"] - 4.2e9 / 0.210e-3 * 1e-12) < 1e-6 and abs(roof["frac"] - roof["achieved"] / 71.0) < 1e-12
+    # a memory-bound table: the bound flips to HBM
+    tab2 = bench.kernel_table({"bn_apply[M=2000000,C=64]": [(Ev(0.0), Ev(0.5), dict(flops=5.1e8, bytes=1.0e9))]})
+    roof2 = bench.roofline_of(tab2, dict(hbm_gbs=6548.5, source="test"), dict(ffma=71.0, ffma2=74.0))
+    assert roof2["bound"] == "hbm" and abs(roof2["achieved"] - 2000.0) < 1e-6
