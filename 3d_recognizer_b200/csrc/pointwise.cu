@@ -219,7 +219,6 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
     static_assert(A_PER >= 1 && W_PER >= 1 && (TM * (KC / 4)) % NT == 0 && (KC * TN / 4) % NT == 0, "tile/threads");
     __shared__ __align__(16) float As[2][KC][TMP];
     __shared__ __align__(16) float Ws[2][KC][TN];
-    __shared__ double csum[2][TN];   // fp64: see pw_gemm_kernel
 
     const int tid = threadIdx.x;
     const int tr = tid / (TN / RT);
@@ -309,8 +308,6 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
 #pragma unroll
         for (int j = 0; j < RT; ++j) acc[i][j] = 0.f;
 
-    if (a.stats)
-        for (int i = tid; i < 2 * TN; i += NT) (&csum[0][0])[i] = 0.0;
     // this CTA's share of the contraction (whole chunks)
     const int chunks_all = (cin + KC - 1) / KC;
     const int chunks_per = (chunks_all + SPLITK - 1) / SPLITK;
@@ -382,6 +379,8 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
 
     // ---- epilogue
     constexpr int NH = RT / 4;   // column quads per thread
+    static_assert(2 * (TM / RT) * TN <= 2 * KC * TMP, "statistics partials must fit the A staging buffer");
+    float* part = &As[0][0][0];  // free: the main loop (and the split-K exchange) ended with a barrier
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
         const int lcol = (RT == 8 ? h * (TN / 2) : 0) + tc * 4;
@@ -421,10 +420,12 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
             }
         }
         if (a.stats) {
+            // per-thread partial sums (its RT rows) into the free A staging buffer: [2][TM / RT][TN] floats.  No
+            // shared-memory atomics: fp64 ones are compare-and-swap loops and 16 threads share every column.
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                atomicAdd(&csum[0][lcol + j], (double)s1[j]);
-                atomicAdd(&csum[1][lcol + j], (double)s2[j]);
+                part[(0 * (TM / RT) + tr) * TN + lcol + j] = s1[j];
+                part[(1 * (TM / RT) + tr) * TN + lcol + j] = s2[j];
             }
         }
     }
@@ -432,8 +433,14 @@ __global__ void __launch_bounds__((TM / RT) * (TN / RT)) pw_gemm_fast_kernel(PwA
         __syncthreads();
         for (int i = tid; i < TN; i += NT) {
             if (n0 + i < a.cout) {
-                atomicAdd(a.stats + n0 + i, csum[0][i]);
-                atomicAdd(a.stats + a.cout + n0 + i, csum[1][i]);
+                double t1 = 0.0, t2 = 0.0;            // fp64 across the row groups: run-to-run reproducible
+#pragma unroll 4
+                for (int t = 0; t < TM / RT; ++t) {
+                    t1 += (double)part[(0 * (TM / RT) + t) * TN + i];
+                    t2 += (double)part[(1 * (TM / RT) + t) * TN + i];
+                }
+                atomicAdd(a.stats + n0 + i, t1);
+                atomicAdd(a.stats + a.cout + n0 + i, t2);
             }
         }
     }
