@@ -15,7 +15,7 @@ Two execution paths share this file:
 Neither path runs on the CPU; ``ops`` raises if a tensor is not on a CUDA device.
 """
 import os
-from typing import List, Tuple
+from typing import List
 
 import numpy as np
 import torch

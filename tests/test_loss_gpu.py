@@ -2,7 +2,6 @@
 formulation of the same file (which follows randlanet/utils/losses.py:66-86) and against the oracle's dice loss."""
 import importlib
 
-import numpy as np
 import pytest
 import torch
 

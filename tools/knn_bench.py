@@ -4,7 +4,6 @@ import importlib
 import json
 import os
 import sys
-import time
 
 import torch
 
