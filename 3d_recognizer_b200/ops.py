@@ -37,19 +37,18 @@ class _ZeroPool:
         aligned = (nbytes + 255) & ~255
         self.need += aligned
         # a block filled outside a CUDA-graph capture must not feed a captured step: its fill would not be replayed
-        capturing = torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing()
+        on_cuda = torch.device(device).type == "cuda"
+        capturing = on_cuda and torch.cuda.is_current_stream_capturing()
         if (self.block is None or self.block.device != torch.device(device) or capturing != self.captured
                 or self.off + aligned > self.block.numel()):
+            if on_cuda and torch.cuda.current_stream(device).cuda_stream in SIDE_STREAMS:
+                # Inside a fork (engine._fork registers its streams in SIDE_STREAMS): a block filled here would be used
+                # by the parent stream before the join, unordered against the fill (in a captured graph: no edge).
+                # This request gets its own buffer; the next step's block, sized by ``hint`` and allocated on the
+                # main stream before any fork, covers it.
+                return torch.zeros(shape, dtype=dtype, device=device)
             self.block = torch.zeros(max(self.hint, aligned), dtype=torch.uint8, device=device)
             self.off, self.captured = 0, capturing
-            if torch.device(device).type == "cuda" and not capturing:
-                # A block filled on a side stream (engine._fork registers them in SIDE_STREAMS) is used by the parent
-                # stream before the join: the fill must have completed first.  This only happens while a shape's
-                # first steps outgrow the block (afterwards it is sized by ``hint`` and allocated once per step on
-                # the main stream, whose forks are ordered behind it); a captured step never allocates mid-capture.
-                cur = torch.cuda.current_stream(device)
-                if cur.cuda_stream in SIDE_STREAMS:
-                    cur.synchronize()
         out = self.block[self.off:self.off + nbytes].view(dtype).view(shape)
         self.off += aligned
         return out
