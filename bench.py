@@ -5,13 +5,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One JSON line on rank 0.  A "step" is one pass of the RandLA-Net hot path over one batch of synthetic
+One SHORT JSON line (< 1 200 characters) on rank 0; the per-kernel table and everything bulky goes to
+profiles/bench_<workload>_n<N>.json (and gpurun_out/).  A "step" is one pass of the RandLA-Net hot path over one batch of synthetic
 clouds.  Workloads (BASELINE.json `configs`):
 
-  train2500   (default; configs[1]) training step — forward + dice loss + backward + Adam — on a
-              fingertip-style batch of 8 clouds x 2 500 points (train.py:50-56 cloud size), K=16,
-              4 encoder levels [16,64,128,256], per GPU (weak scaling; NCCL gradient all-reduce at N>1)
-  train40960  (configs[3]) the same step on 40 960-point clouds, global batch 64 split over the GPUs
+  train40960  (default; configs[3]) training step — forward + dice loss + backward + Adam — on fingertip-style
+              clouds of 40 960 points, K=16, 4 encoder levels [16,64,128,256], global batch 64 split over the
+              GPUs (strong scaling; NCCL gradient all-reduce at N>1)
+  train2500   (configs[1]) the same step on 8 clouds x 2 500 points (train.py:50-56 cloud size) per GPU (weak)
   infer16k | infer64k | infer256k   (configs[2]) eval forward, global batch 32 split over the GPUs
   knn1m_k16 | knn1m_k32             (configs[4]) 1 M x 1 M exact KNN micro-benchmark (1 GPU)
 
@@ -50,6 +51,7 @@ WORKLOADS = {
     "knn1m_k16": dict(kind="knn", n=1 << 20, k=16, per_gpu_batch=1, scaling="weak"),
     "knn1m_k32": dict(kind="knn", n=1 << 20, k=32, per_gpu_batch=1, scaling="weak"),
 }
+DEFAULT_WORKLOAD = "train40960"
 SETTINGS = dict(n_classes=2, n_features=0, decimation=4, layer_sizes=[16, 64, 128, 256], knn="naive",
                 upsampling="nni")
 L2_FLUSH_BYTES = 256 << 20        # > the 126 MB L2
@@ -362,13 +364,77 @@ def run_reference(args, wl, name):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------ output
+MAX_LINE_CHARS = 1200          # the driver keeps a short tail of stdout: the bench line must fit in it
+
+
+def _r(x, nd=4):
+    """Round floats (significant digits for small values) so that the line stays short."""
+    if isinstance(x, float):
+        return float(f"{x:.{nd + 2}g}")
+    return x
+
+
+def compose_line(*, metric, value, unit, world, args, ms_per_step, wl, name, n, k, gbatch, batch, e2e_value, h2d,
+                 d2h, launches, clocks, roof, cpu_base, tab, fp32_peak, wall, graphed, eager_ms_per_step, extras):
+    """(the ONE short JSON line printed on stdout, the full record for the side file).  Everything bulky — the
+    per-kernel table, the roofline's shape list and prose, the extras — goes to the side file only."""
+    roof_short = None
+    if roof:
+        roof_short = {a: _r(roof[a]) for a in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic")}
+        roof_short["launches"] = roof["launches"]
+    cpu_short = None
+    if cpu_base:
+        cpu_short = dict(value=_r(cpu_base["value"]), unit=cpu_base["unit"], cores=cpu_base["cores"],
+                         kind=cpu_base["kind"], sample=cpu_base["sample"][:80])
+    clocks_short = dict(sm_mhz=clocks.get("sm_mhz"), sm_max_mhz=clocks.get("sm_max_mhz"),
+                        reasons=clocks.get("reasons", []))
+    par = f"dp{world}" + ("+nccl_allreduce" if wl["kind"] == "train" and world > 1 else "")
+    short = dict(metric=metric, value=_r(value), unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                 ms_per_step=_r(ms_per_step), higher_is_better=True, scaling=wl["scaling"], vs_baseline=None,
+                 dtype="f32", data="synthetic",
+                 config=dict(workload=name, n_points=n, k=k, global_batch=gbatch, per_gpu_batch=batch,
+                             l2="flushed between steps", parallelism=par),
+                 e2e=dict(value=_r(e2e_value), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                 gpu_launches=int(launches), clocks=clocks_short, roofline=roof_short, cpu_baseline=cpu_short,
+                 execution=("cuda-graph replay" if graphed else "eager"))
+    line = json.dumps(short, separators=(",", ":"))
+    if len(line) > MAX_LINE_CHARS:             # never let prose push the line out of the driver's tail
+        if cpu_short:
+            cpu_short.pop("sample", None)
+        short["config"].pop("l2", None)
+        line = json.dumps(short, separators=(",", ":"))
+    assert len(line) <= MAX_LINE_CHARS, len(line)
+    side = dict(short, config=dict(short["config"], layer_sizes=SETTINGS["layer_sizes"],
+                                   l2="flushed between steps (256 MB write)"),
+                roofline=roof, cpu_baseline=cpu_base, clocks=clocks,
+                kernels={kn: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in kv.items()}
+                         for kn, kv in tab.items()},
+                fp32_peak_tflops=fp32_peak, wall_s_timed_region=wall, eager_ms_per_step=eager_ms_per_step,
+                extras=extras)
+    return line, side
+
+
+def write_side_file(side, name, world):
+    """Full record (kernel table, roofline shapes, extras) next to the short line: profiles/ (tracked) and
+    gpurun_out/ (what comes back from a GPU box)."""
+    for d in ("profiles", "gpurun_out"):
+        try:
+            os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+            with open(os.path.join(ROOT, d, f"bench_{name}_n{world}.json"), "w") as fh:
+                json.dump(side, fh, indent=1)
+        except OSError:
+            pass
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="train2500", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -590,20 +656,13 @@ def main():
                                    "randlanet/utils/modules.py + exact KNN, torch threads = all host cores")
 
     if rank == 0:
-        line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_per_step, higher_is_better=True, scaling=wl["scaling"], vs_baseline=None,
-                    dtype="f32", data="synthetic",
-                    config=dict(workload=name, n_points=n, k=k, global_batch=gbatch, per_gpu_batch=batch,
-                                layer_sizes=SETTINGS["layer_sizes"], l2="flushed between steps (256 MB write)",
-                                parallelism=f"dp{world}" + (" + NCCL grad all-reduce" if wl["kind"] == "train" and world > 1 else "")),
-                    e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base,
-                    kernels={kn: {a: (round(b, 6) if isinstance(b, float) else b) for a, b in kv.items()}
-                             for kn, kv in tab.items()},
-                    fp32_peak_tflops=fp32_peak, wall_s_timed_region=wall,
-                    execution=("cuda-graph replay" if graphed else "eager"), eager_ms_per_step=eager_ms_per_step,
-                    extras=extras)
-        print(json.dumps(line), flush=True)
+        line, side = compose_line(
+            metric=metric, value=value, unit=unit, world=world, args=args, ms_per_step=ms_per_step, wl=wl, name=name,
+            n=n, k=k, gbatch=gbatch, batch=batch, e2e_value=e2e_value, h2d=h2d, d2h=d2h, launches=launches,
+            clocks=clocks, roof=roof, cpu_base=cpu_base, tab=tab, fp32_peak=fp32_peak, wall=wall, graphed=graphed,
+            eager_ms_per_step=eager_ms_per_step, extras=extras)
+        write_side_file(side, name, world)
+        print(line, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

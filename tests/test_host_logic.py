@@ -258,3 +258,42 @@ def test_bench_roofline_picks_the_dominant_kernel_family():
     tab2 = bench.kernel_table({"bn_apply[M=2000000,C=64]": [(Ev(0.0), Ev(0.5), dict(flops=5.1e8, bytes=1.0e9))]})
     roof2 = bench.roofline_of(tab2, dict(hbm_gbs=6548.5, source="test"), dict(ffma=71.0, ffma2=74.0))
     assert roof2["bound"] == "hbm" and abs(roof2["achieved"] - 2000.0) < 1e-6
+
+
+def test_bench_line_is_short_and_round_trips():
+    """The driver keeps only a short tail of stdout: the bench line must stay under 1 200 characters whatever the size
+    of the per-kernel table, parse as JSON and carry every contract key; the bulky record goes to the side file."""
+    import argparse
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tab = {f"pw_gemm_fast[M={m},{a}->{b}]": dict(launches=3, ms_total=0.1, ms_avg=0.033, flops=1e9, bytes=1e7,
+                                                 tflops=3.0, frac_fp32_peak=0.04, gbs=10.0, frac_hbm_peak=0.01)
+           for m in range(40) for a in (64, 128) for b in (64, 128, 256)}                 # 240 rows ≈ 50 KB
+    roof = dict(kernel="lfa_pool_bwd", launches=8, ms_avg=7.7, traffic=123456789.0, shapes=sorted(tab),
+                algorithmic_flops_per_launch=1.0e11, algorithmic_bytes_per_launch=1.0e9, bound="fp32",
+                achieved=28.612345678, peak=70.961234, unit="TFLOP/s", frac=0.40321234, peak_source="x" * 300)
+    wl = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    assert bench.DEFAULT_WORKLOAD == "train40960" and wl["scaling"] == "strong" and wl["global_batch"] == 64
+    args = argparse.Namespace(steps=20, warmup=5)
+    line, side = bench.compose_line(
+        metric="train_step_points_per_sec", value=17912345.678, unit="points/s", world=8, args=args,
+        ms_per_step=146.31234567, wl=wl, name="train40960", n=40960, k=16, gbatch=64, batch=8, e2e_value=17812345.6,
+        h2d=52428800, d2h=4, launches=6780, clocks=dict(sm_mhz=1965.0, sm_max_mhz=1965.0, reasons=["sw_power_cap"],
+                                                        samples=33),
+        roof=roof, cpu_base=dict(value=111500.123, unit="points/s", cores=16, kind="port", sample="y" * 400), tab=tab,
+        fp32_peak=dict(ffma=70.9, ffma2=74.0), wall=3.2, graphed=True, eager_ms_per_step=150.0, extras={"a": 1})
+    assert len(line) < bench.MAX_LINE_CHARS <= 1200 and "\n" not in line
+    d = json.loads(line)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["value"] > 0 and d["n_gpus"] == 8 and d["config"]["workload"] == "train40960"
+    assert set(d["e2e"]) == {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "cores", "kind"} <= set(d["cpu_baseline"])
+    assert "kernels" not in d and len(side["kernels"]) == 240 and side["roofline"]["shapes"]
+    assert json.loads(json.dumps(side))["extras"] == {"a": 1}
