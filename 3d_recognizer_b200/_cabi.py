@@ -37,7 +37,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_pool_tc": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
@@ -87,6 +87,8 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_rowreduce_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p]),
     "r3d_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_tc16_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float,
+                               ctypes.c_float, c_void_p]),
     "r3d_fp32_probe_floats": (c_size_t, []),
     "r3d_fp32_probe": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(ctypes.c_double), c_void_p]),
 }

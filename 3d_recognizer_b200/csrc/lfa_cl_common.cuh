@@ -1,0 +1,200 @@
+// Building blocks of the tensor-core ("channel-lane") fused LocSE + attentive-pooling kernels (lfa_cl.cu forward,
+// lfa_cl_bwd.cu backward / moments).  Design:
+//
+//  * TRANSPOSED contraction.  The score Linear of AttentivePooling (modules.py:234-237, 246-252) is issued as
+//        S^T (channels x rows) = Ws (channels x channels) . X^T (channels x rows)
+//    so that the accumulator's TMEM LANE is the CHANNEL and its COLUMNS are the (point, neighbour) rows.  A thread then
+//    owns one channel: the softmax over a point's K neighbours and the weighted sum are in-thread loops over K
+//    consecutive columns (no shuffles), per-channel parameters live in registers, the reductions over rows of the
+//    backward are in-thread too, and the neighbour-feature scatter is coalesced across the lanes of a warp.
+//  * 128 VIRTUAL CHANNELS.  A tcgen05 MMA wants M = 128 lanes.  Layers narrower than 128 channels stack SUB = 128/d
+//    sub-tiles, each with its own rows, on the lanes; the weight operand becomes block-diagonal (SUB copies of Ws) and
+//    the row operand holds, for virtual channel v = (sub, c) and row slot n, channel c of row n of sub-tile sub.  The
+//    zero blocks cost tensor-core time only, which is not the bound of these layers.  Lane order: lanes 0..63 carry the
+//    position-encoding halves (r) of all sub-tiles, lanes 64..127 the gathered-feature halves (F), so that warps are
+//    uniform in role.
+//  * SPLIT-FP16 operands (tc16_common.cuh): fp32 accuracy at half the shared-memory footprint of 3xTF32.
+//  * One operand layout for every role: 16-byte units of 8 consecutive rows of one channel, 8 channels adjacent
+//    (128-byte core matrix), read K-major or MN-major as the GEMM at hand needs (S = X Ws^T, dX = dS Ws, dWs = dS^T X
+//    all read the same two tiles).
+//  * Warp specialisation: NG worker groups of 128 threads (lane = TMEM lane) take tiles round-robin and each run
+//    row-info -> produce operand -> [MMA] -> epilogue; ONE extra warp's elected thread issues every MMA, polling the
+//    groups' "operand ready" mbarriers, and commits completion to the group's "accumulator ready" mbarrier.  While one
+//    group waits for the tensor core the others gather / convert / reduce.
+#pragma once
+#include "lfa_common.cuh"
+#include "tc16_common.cuh"
+
+namespace r3d {
+
+constexpr int kClLanes = 128;       // virtual channels = TMEM lanes = threads of a worker group
+constexpr int kClR = 64;            // row slots per sub-tile = MMA N = TMEM columns of an accumulator
+constexpr float kClSx = 16.0f;      // fixed scale of activation operands: |x| < 4094 (status bit 0 reports a violation)
+constexpr int kClRinfo = 12;        // floats per row of the row-info table: rpe[10], neighbour offset, spare
+
+template <int D, int K>
+struct ClCfg {
+    static_assert(D == 16 || D == 32 || D == 64 || D == 128, "width");
+    static_assert(K == 16 || K == 32, "neighbours");
+    static constexpr int H = D / 2;
+    static constexpr int SUB = kClLanes / D;          // sub-tiles stacked on the lanes
+    static constexpr int R = kClR;
+    static constexpr int PTS = R / K;                 // points per sub-tile
+    static constexpr int TPTS = SUB * PTS;            // points per tile
+    static constexpr int ROWS = SUB * R;              // (point, neighbour) rows per tile
+    static constexpr int SUB_RI = R * kClRinfo + 4;   // floats between the row-info blocks of two sub-tiles (bank skew)
+    static constexpr int RINFO_FLOATS = SUB * SUB_RI;
+    static constexpr int OP_BYTES = kClLanes * R * 2; // one fp16 plane (hi or lo) of a row operand: 16 KB
+    static constexpr int OP_CS = (R / 8) * 128;       // byte stride between channel groups (8 channels) of a row operand
+    static constexpr int W_BYTES = kClLanes * kClLanes * 2;   // one plane of the 128 x 128 virtual weight matrix
+    static constexpr int W_IS = (kClLanes / 8) * 128; // byte stride between input-channel groups of a weight plane
+};
+
+// lane -> (part, sub-tile, channel inside the part); real channel = part * H + c
+template <int D>
+struct ClLane {
+    int part, sub, c;
+    __device__ __forceinline__ explicit ClLane(int l) {
+        constexpr int H = D / 2;
+        part = l >> 6;
+        sub = (l & 63) / H;
+        c = (l & 63) % H;
+    }
+    __device__ __forceinline__ int channel() const { return part * (D / 2) + c; }
+};
+
+// power-of-two scale that brings absmax into [2^11, 2^12)
+__device__ __forceinline__ float cl_pow2_scale(float absmax) {
+    if (!(absmax > 0.f) || !isfinite(absmax)) return 1.0f;
+    int e;
+    frexpf(absmax, &e);                // absmax = m 2^e, m in [0.5, 1)
+    return exp2f((float)(12 - e));
+}
+
+// block-wide max of |w[i]|, i < n (every thread of the CTA calls it; `red` = 33 floats of shared memory)
+__device__ __forceinline__ float cl_block_absmax(const float* __restrict__ w, int n, float* red) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) red[32] = v;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// Virtual (block-diagonal) image of a weight matrix as the hi/lo planes of a K-major A operand:
+//   element (vo, vi) at (vi/8) * W_IS + (vo/8) * 128 + (vo%8) * 16 + (vi%8) * 2.
+// FULL = true : the d x d score weight, w (D,D) [out][in]; virtual channel v <-> real channel part*H + c of sub-tile sub.
+// FULL = false: the h x h mlp_rpe2 weight, w (H,H) [out][in], on the r lanes (0..63) only; rows/columns >= 64 are zero.
+template <int D, bool FULL>
+__device__ __forceinline__ void cl_build_weight_image(const float* __restrict__ w, float scale, unsigned char* hi,
+                                                      unsigned char* lo) {
+    constexpr int H = D / 2;
+    constexpr int W_IS = (kClLanes / 8) * 128;
+    constexpr int NVI = FULL ? kClLanes : 64;
+    for (int e = threadIdx.x; e < kClLanes * NVI; e += blockDim.x) {
+        const int vo = e / NVI, vi = e % NVI;
+        float v = 0.f;
+        if (FULL) {
+            const ClLane<D> lo_(vo), li_(vi);
+            if (lo_.sub == li_.sub) v = w[lo_.channel() * D + li_.channel()];
+        } else if (vo < 64) {
+            if (vo / H == vi / H) v = w[(vo % H) * H + (vi % H)];
+        }
+        v *= scale;
+        const __half hh = __float2half_rn(v);
+        const __half ll = __float2half_rn(v - __half2float(hh));
+        const int off = (vi >> 3) * W_IS + (vo >> 3) * 128 + (vo & 7) * 16 + (vi & 7) * 2;
+        *reinterpret_cast<__half*>(hi + off) = hh;
+        *reinterpret_cast<__half*>(lo + off) = ll;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- row info
+// rinfo[sub][n] = {rpe[10], feature offset of the neighbour (uint32 bits), global point (int bits)}
+template <int D, int K>
+__device__ __forceinline__ void cl_row_info(float* __restrict__ rinfo, const float* __restrict__ xyz, long long xyz_bstride,
+                                            const int32_t* __restrict__ idx, long long feat_bstride, int N,
+                                            long long npts, long long tile, int l) {
+    using C = ClCfg<D, K>;
+    for (int row = l; row < C::ROWS; row += kClLanes) {
+        const int sub = row / C::R, n = row % C::R;
+        const int p = n / K, k = n % K;
+        long long gp = tile * C::TPTS + sub * C::PTS + p;
+        if (gp >= npts) gp = npts - 1;                       // tail rows recompute the last point (never written)
+        const int b = (int)(gp / N);
+        const int pi = (int)(gp - (long long)b * N);
+        const int pj = idx[gp * K + k];
+        float rpe[10];
+        rpe_of_row(xyz + (size_t)b * xyz_bstride, pi, pj, rpe);
+        float4* dst = reinterpret_cast<float4*>(rinfo + sub * C::SUB_RI + n * kClRinfo);
+        dst[0] = make_float4(rpe[0], rpe[1], rpe[2], rpe[3]);
+        dst[1] = make_float4(rpe[4], rpe[5], rpe[6], rpe[7]);
+        const uint32_t off = (uint32_t)((long long)b * feat_bstride + (long long)pj * C::H);
+        dst[2] = make_float4(rpe[8], rpe[9], __uint_as_float(off), 0.f);
+    }
+}
+
+// r1 = relu(a1 (W1 . rpe) + b1) for one row, W1 row in registers (same FMA order as rpe_mlp1 of lfa_common.cuh)
+__device__ __forceinline__ float cl_mlp1(const float (&w)[10], float a1, float b1, const float4& q0, const float4& q1,
+                                         const float4& q2) {
+    float z = w[0] * q0.x;
+    z = fmaf(w[1], q0.y, z); z = fmaf(w[2], q0.z, z); z = fmaf(w[3], q0.w, z);
+    z = fmaf(w[4], q1.x, z); z = fmaf(w[5], q1.y, z); z = fmaf(w[6], q1.z, z);
+    z = fmaf(w[7], q1.w, z); z = fmaf(w[8], q2.x, z); z = fmaf(w[9], q2.y, z);
+    return fmaxf(fmaf(z, a1, b1), 0.f);
+}
+
+// 8 scaled values of one channel (rows ng*8 .. ng*8+7) -> the hi/lo planes of a row operand
+__device__ __forceinline__ void cl_store_unit(unsigned char* hi, unsigned char* lo, int unit_off, const float (&v)[8]) {
+    uint4 h, l;
+    split16_2(v[0], v[1], h.x, l.x);
+    split16_2(v[2], v[3], h.y, l.y);
+    split16_2(v[4], v[5], h.z, l.z);
+    split16_2(v[6], v[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + unit_off) = h;
+    *reinterpret_cast<uint4*>(lo + unit_off) = l;
+}
+__device__ __forceinline__ void cl_load_unit(const unsigned char* hi, const unsigned char* lo, int unit_off, float (&v)[8]) {
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + unit_off);
+    const uint4 l = *reinterpret_cast<const uint4*>(lo + unit_off);
+    float2 t;
+    t = join16_2(h.x, l.x); v[0] = t.x; v[1] = t.y;
+    t = join16_2(h.y, l.y); v[2] = t.x; v[3] = t.y;
+    t = join16_2(h.z, l.z); v[4] = t.x; v[5] = t.y;
+    t = join16_2(h.w, l.w); v[6] = t.x; v[7] = t.y;
+}
+
+// byte offset of the unit (channel lane l, row group ng) inside a row-operand plane
+template <int D, int K>
+__device__ __forceinline__ int cl_unit_off(int l, int ng) {
+    return (l >> 3) * ClCfg<D, K>::OP_CS + ng * 128 + (l & 7) * 16;
+}
+
+// --------------------------------------------------------------------------------------------- MMA issue
+// D[tmem] (+)= A B^T over `ksteps` K steps of 16, three split products per step.
+//   a_*: hi/lo plane addresses of the A operand, a_lbo / a_sbo its core-matrix strides along K / along M
+//   b_*: likewise for B.   The per-step advance along K is two core matrices: 2 * lbo.
+__device__ __forceinline__ void cl_mma_3x(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo,
+                                          uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
+                                          int ksteps, bool accumulate) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ah = umma_desc_b(a_hi + ks * 2 * a_lbo, a_lbo, a_sbo);
+        const uint64_t al = umma_desc_b(a_lo + ks * 2 * a_lbo, a_lbo, a_sbo);
+        const uint64_t bh = umma_desc_b(b_hi + ks * 2 * b_lbo, b_lbo, b_sbo);
+        const uint64_t bl = umma_desc_b(b_lo + ks * 2 * b_lbo, b_lbo, b_sbo);
+        umma_f16(tmem_d, ah, bh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        umma_f16(tmem_d, ah, bl, idesc, 1u);
+        umma_f16(tmem_d, al, bh, idesc, 1u);
+    }
+}
+
+}  // namespace r3d

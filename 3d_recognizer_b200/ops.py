@@ -156,17 +156,38 @@ def _rows_view(x: torch.Tensor):
     return x, (x.stride(0) if B > 1 else n * C)
 
 
-# tcgen05 path of the fused forward (d in TC_WIDTHS, K in TC_NEIGHBORS).  Parity-green (1e-6 relative against the
-# CUDA-core kernel) but OFF by default: with one thread per row its gather prologue and shuffle softmax are latency
-# bound at 4 warps/SM, and it measures 2x slower than the register-tiled FP32 kernel at d = 64/128
-# (profiles/r01_lfa_tc_vs_cuda_core.log).  It pays only once prologue, MMA and epilogue of successive tiles overlap
-# (warp-specialised persistent kernel) — see DESIGN.md.
-USE_TENSOR_CORES = False
-TC_WIDTHS, TC_NEIGHBORS = (64, 128), (16, 32)
+# tcgen05 path of the fused LocSE + pooling kernels (csrc/lfa_cl*.cu, "channel-lane" kernels: transposed contraction,
+# split-fp16 operands, warp-specialised persistent CTAs).  d in TC_WIDTHS, K in TC_NEIGHBORS; d = 256 stays on the
+# FP32 CUDA-core kernels (its 256 x 256 weight image does not fit shared memory next to the row operands).
+USE_TENSOR_CORES = True
+TC_WIDTHS, TC_NEIGHBORS = (16, 32, 64, 128), (16, 32)
+_TC_STATUS = {}
 
 
 def lfa_pool_tc_supported(d: int, k: int) -> bool:
     return USE_TENSOR_CORES and d in TC_WIDTHS and k in TC_NEIGHBORS
+
+
+def tc_status(device) -> torch.Tensor:
+    """Per-device int32 status word of the tensor-core kernels (bit 0: an activation left the range of the fixed
+    split-fp16 operand scale, |x| >= 4094).  Allocated once, never reset by the kernels."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    t = _TC_STATUS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _TC_STATUS[key] = t
+    return t
+
+
+def check_tc_status(device) -> None:
+    """Raise if a tensor-core LFA kernel has reported an out-of-range activation since the last check (one device ->
+    host read: call it where the host synchronises anyway, e.g. after reading the loss or the predictions)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    t = _TC_STATUS.get(key)
+    if t is not None and int(t.item()) != 0:
+        t.zero_()
+        raise FloatingPointError("a fused LFA tensor-core kernel saw an activation with |x| >= 4094: outside the range "
+                                 "of its split-fp16 operands (set ops.USE_TENSOR_CORES = False for this model)")
 
 
 def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Tensor, w_rpe1, a_rpe1, b_rpe1,
@@ -186,7 +207,7 @@ def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.
         rc = _cabi.lib().r3d_lfa_pool_tc(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
                                          _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2),
                                          _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_score), _cabi.ptr(pooled),
-                                         B, N, K, d, _cabi.stream_ptr(dev))
+                                         _cabi.ptr(tc_status(dev)), B, N, K, d, _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_lfa_pool_tc")
     return pooled
 

@@ -115,13 +115,18 @@ int r3d_lfa_pool(int stage, const float* xyz, long long xyz_bstride, const int32
                  const float* w_rpe2T, const float* a_rpe2, const float* b_rpe2, const float* w_scoreT,
                  float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
 
-/* r3d_lfa_pool with the score GEMM (and mlp_rpe2) on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in
- * TMEM: fp32-level accuracy).  Same operator and arguments, except that the weights come in their stored
- * [out][in] layout: w_rpe2 (h,h), w_score (d,d).  Supported: d in {64,128}, K in {16,32}; else R3D_EUNSUPPORTED. */
+/* r3d_lfa_pool on the tcgen05 tensor cores (csrc/lfa_cl.cu, "channel-lane" kernel): the score GEMM (and mlp_rpe2) run
+ * as kind::f16 MMAs on split-fp16 operands (hi/lo halves of power-of-two scaled values, three products per K step,
+ * fp32 accumulation in TMEM: fp32-level accuracy) in transposed form — TMEM lane = channel, columns = rows — so that
+ * the softmax over K and the weighted sum are in-thread; persistent warp-specialised CTAs (worker groups + one MMA
+ * warp).  Same operator and arguments as r3d_lfa_pool, except that the weights come in their stored [out][in] layout:
+ * w_rpe2 (h,h), w_score (d,d).  status (device int, nullable): bit 0 is OR-ed in when an activation left the range the
+ * fixed operand scale covers (|x| >= 4094; never seen behind a BatchNorm) — results are then invalid and the host
+ * raises.  Supported: d in {16,32,64,128}, K in {16,32}; else R3D_EUNSUPPORTED. */
 int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
                     long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
                     const float* w_rpe2, const float* a_rpe2, const float* b_rpe2, const float* w_score,
-                    float* pooled, int B, int N, int K, int d, r3d_stream_t stream);
+                    float* pooled, int* status, int B, int N, int K, int d, r3d_stream_t stream);
 
 /* Backward of one r3d_lfa_pool launch (autograd of modules.py:316-323 as driven by trainer.py:115-119).
  * Inputs as in the forward plus
@@ -293,6 +298,14 @@ int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long lon
  * 3xTF32 (operands split hi/lo on the fly, three MMAs per K step); terms = 1: plain TF32.
  * N a multiple of 32 in [32,256], K a multiple of 4; A, W, C dense, 16-byte aligned.  (csrc/tc_gemm.cu) */
 int r3d_tc_gemm(const float* A, const float* W, float* C, int M, int N, int K, int terms, r3d_stream_t stream);
+
+/* Unit test of the split-fp16 ("fp16x2") tensor-core building blocks used by the fused LFA kernels (csrc/tc16_common.cuh):
+ * ONE CTA computes D (M,N) = A (M,K) B (N,K)^T with kind::f16 MMAs on hi/lo fp16 halves of the scaled operands,
+ * each operand staged K-major (0) or MN-major (1) in shared memory, and writes the raw accumulator window
+ * out (128 TMEM lanes, N) divided by scale_a*scale_b (cells no MMA wrote read as NaN).  M in {64,128},
+ * N, K multiples of 16 <= 256.  A, B, out dense fp32 device buffers. */
+int r3d_tc16_probe(const float* A, const float* B, float* out, int M, int N, int K, int a_mn_major, int b_mn_major,
+                   float scale_a, float scale_b, r3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------ FP32 peak probe
  * Roofline denominator of the CUDA-core kernels, measured live by bench.py (MEASURED_PEAKS.json has

@@ -204,13 +204,14 @@ def test_tcgen05_gemm_3xtf32_matches_fp64(M, N, K):
     assert 1e-5 < errs[1] < 5e-3, errs
 
 
-@pytest.mark.parametrize("d,K", [(64, 16), (128, 16), (64, 32), (128, 32)])
+@pytest.mark.parametrize("d,K", [(16, 16), (32, 16), (64, 16), (128, 16), (16, 32), (64, 32), (128, 32)])
 @pytest.mark.parametrize("stage", [1, 2])
-def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage):
-    """r3d_lfa_pool_tc (score GEMM + mlp_rpe2 on tcgen05, 3xTF32) against the FP32 CUDA-core kernel."""
+@pytest.mark.parametrize("B,N", [(2, 1000), (3, 37), (1, 20011)])
+def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage, B, N):
+    """r3d_lfa_pool_tc (channel-lane kernel: score GEMM + mlp_rpe2 as split-fp16 tcgen05 MMAs) against the FP32
+    CUDA-core kernel; ragged sizes (tail tiles, clouds that end inside a tile), 1 to ~150 tiles per CTA group."""
     _, _, ops = mods
     h = d // 2
-    B, N = 2, 1000
     g = torch.Generator(device="cuda").manual_seed(d + K + stage)
     xyz = torch.rand(B, N, 3, device="cuda", generator=g)
     feat = torch.randn(B, N, h, device="cuda", generator=g)
@@ -226,3 +227,4 @@ def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage):
     got = ops.lfa_pool_tc(stage, xyz, idx, feat, w1, a1, b1, w2 if s2 else None, a1 if s2 else None,
                           b1 if s2 else None, ws)
     assert rel_err(got, ref) < 1e-5
+    ops.check_tc_status(xyz.device)
