@@ -39,6 +39,11 @@ SIGNATURES = {
     "r3d_lfa_pool_tc": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_tc_du2_floats": (ctypes.c_longlong, [c_int, c_int, c_int, c_int]),
+    "r3d_absmax": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
+    "r3d_lfa_tc_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
+                       [c_void_p] * 8 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
+                       [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
                          [c_int, c_int, c_int, c_int, c_void_p]),

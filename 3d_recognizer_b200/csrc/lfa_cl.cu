@@ -39,7 +39,7 @@ struct LfaClArgs {
 template <int D, int K, int STAGE, int NG>
 struct LfaClFwdSmem {
     using C = ClCfg<D, K>;
-    static constexpr int W2_BYTES = (STAGE == 2) ? 8 * C::W_IS : 0;               // 64 input channels x 128 rows, one plane
+    static constexpr int W2_BYTES = (STAGE == 2) ? kClW2Bytes : 0;              // compact 64 x 64 image, one plane
     static constexpr int GROUP_BYTES = 2 * C::OP_BYTES + C::RINFO_FLOATS * 4;
     static constexpr int OFF_W2 = 2 * C::W_BYTES;
     static constexpr int OFF_GROUPS = OFF_W2 + 2 * W2_BYTES;
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
     if (warp == NG * 4) tmem_alloc_warp(tmem_slot, TMEM_COLS);
     // weights: power-of-two scales from their absmax, block-diagonal fp16 hi/lo images
     const float sw = cl_pow2_scale(cl_block_absmax(a.w_score, D * D, red));
-    cl_build_weight_image<D, true>(a.w_score, sw, Whi, Wlo);
+    cl_build_weight_image<D>(a.w_score, sw, Whi, Wlo);
     float sw2 = 1.f;
     if (STAGE == 2) {
         sw2 = cl_pow2_scale(cl_block_absmax(a.w_rpe2, H * H, red));
-        cl_build_weight_image<D, false>(a.w_rpe2, sw2, W2hi, W2lo);
+        cl_build_w2_image<D>(a.w_rpe2, sw2, W2hi, W2lo);
     }
     fence_async_smem();
     tc_fence_before_sync();
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
                         const uint32_t xlo = xhi + C::OP_BYTES;
                         const uint32_t dcol = tmem + (uint32_t)(g * R);
                         if (STAGE == 2 && (step[g] & 1) == 0)
-                            cl_mma_3x(dcol, smem_u32(W2hi), smem_u32(W2lo), C::W_IS, 128, xhi, xlo, C::OP_CS, 128, idesc, 4,
+                            cl_mma_3x(dcol, smem_u32(W2hi), smem_u32(W2lo), kClW2Is, 128, xhi, xlo, C::OP_CS, 128, idesc, 4,
                                       false);
                         else
                             cl_mma_3x(dcol, smem_u32(Whi), smem_u32(Wlo), C::W_IS, 128, xhi, xlo, C::OP_CS, 128, idesc, 8,
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
             const long long tile = (long long)blockIdx.x + (long long)(it * NG + g) * gridDim.x;
             if (tile >= a.ntiles) break;
             // ---- A: row info
-            cl_row_info<D, K>(rinfo, a.xyz, a.xyz_bstride, a.idx, a.feat_bstride, a.N, a.npts, tile, l);
+            cl_row_info<D, K>(rinfo, a.xyz, a.xyz_bstride, a.idx, a.feat_bstride, 0, a.N, a.npts, tile, l);
             named_bar_sync(1 + g, kClLanes);
             // ---- B: row operand X^T (scaled by sx), this thread's channel, 8 rows per unit
             if (ln.part == 0) {
@@ -310,8 +310,8 @@ extern "C" int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstrid
         a.ntiles = (a.npts + ClCfg<DD, KK>::TPTS - 1) / ClCfg<DD, KK>::TPTS;                \
         return stage == 1 ? launch_cl_fwd<DD, KK, 1, NG1>(a, st) : launch_cl_fwd<DD, KK, 2, NG2>(a, st); \
     }
-    R3D_CL_CASE(128, 16, 4, 3) R3D_CL_CASE(64, 16, 4, 3) R3D_CL_CASE(32, 16, 3, 2) R3D_CL_CASE(16, 16, 2, 2)
-    R3D_CL_CASE(128, 32, 4, 3) R3D_CL_CASE(64, 32, 4, 3) R3D_CL_CASE(32, 32, 3, 2) R3D_CL_CASE(16, 32, 2, 2)
+    R3D_CL_CASE(128, 16, 4, 4) R3D_CL_CASE(64, 16, 4, 3) R3D_CL_CASE(32, 16, 3, 2) R3D_CL_CASE(16, 16, 2, 2)
+    R3D_CL_CASE(128, 32, 4, 4) R3D_CL_CASE(64, 32, 4, 3) R3D_CL_CASE(32, 32, 3, 2) R3D_CL_CASE(16, 32, 2, 2)
 #undef R3D_CL_CASE
     return R3D_EUNSUPPORTED;
 }

@@ -63,13 +63,17 @@ struct ClLane {
     __device__ __forceinline__ int channel() const { return part * (D / 2) + c; }
 };
 
-// power-of-two scale that brings absmax into [2^11, 2^12)
-__device__ __forceinline__ float cl_pow2_scale(float absmax) {
+// power-of-two scale that brings absmax into [2^(target-1), 2^target)
+__device__ __forceinline__ float cl_pow2_scale_to(float absmax, int target) {
     if (!(absmax > 0.f) || !isfinite(absmax)) return 1.0f;
     int e;
     frexpf(absmax, &e);                // absmax = m 2^e, m in [0.5, 1)
-    return exp2f((float)(12 - e));
+    e = target - e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    return exp2f((float)e);
 }
+// weights: absmax -> [2^11, 2^12)
+__device__ __forceinline__ float cl_pow2_scale(float absmax) { return cl_pow2_scale_to(absmax, 12); }
 
 // block-wide max of |w[i]|, i < n (every thread of the CTA calls it; `red` = 33 floats of shared memory)
 __device__ __forceinline__ float cl_block_absmax(const float* __restrict__ w, int n, float* red) {
@@ -90,25 +94,19 @@ __device__ __forceinline__ float cl_block_absmax(const float* __restrict__ w, in
     return red[32];
 }
 
-// Virtual (block-diagonal) image of a weight matrix as the hi/lo planes of a K-major A operand:
-//   element (vo, vi) at (vi/8) * W_IS + (vo/8) * 128 + (vo%8) * 16 + (vi%8) * 2.
-// FULL = true : the d x d score weight, w (D,D) [out][in]; virtual channel v <-> real channel part*H + c of sub-tile sub.
-// FULL = false: the h x h mlp_rpe2 weight, w (H,H) [out][in], on the r lanes (0..63) only; rows/columns >= 64 are zero.
-template <int D, bool FULL>
+// Virtual (block-diagonal) image of the d x d score weight, w (D,D) [out][in], as the hi/lo planes of an operand whose
+// 16-byte units hold 8 consecutive INPUT channels of one output channel:
+//   element (vo, vi) at (vi/8) * W_IS + (vo/8) * 128 + (vo%8) * 16 + (vi%8) * 2,   v <-> real channel part*H + c of a sub-tile.
+// Read K-major it is the A operand of S^T = Ws X^T (M = vo, K = vi); read MN-major that of dX^T = Ws^T dS^T (M = vi, K = vo).
+template <int D>
 __device__ __forceinline__ void cl_build_weight_image(const float* __restrict__ w, float scale, unsigned char* hi,
                                                       unsigned char* lo) {
-    constexpr int H = D / 2;
     constexpr int W_IS = (kClLanes / 8) * 128;
-    constexpr int NVI = FULL ? kClLanes : 64;
-    for (int e = threadIdx.x; e < kClLanes * NVI; e += blockDim.x) {
-        const int vo = e / NVI, vi = e % NVI;
+    for (int e = threadIdx.x; e < kClLanes * kClLanes; e += blockDim.x) {
+        const int vo = e / kClLanes, vi = e % kClLanes;
         float v = 0.f;
-        if (FULL) {
-            const ClLane<D> lo_(vo), li_(vi);
-            if (lo_.sub == li_.sub) v = w[lo_.channel() * D + li_.channel()];
-        } else if (vo < 64) {
-            if (vo / H == vi / H) v = w[(vo % H) * H + (vi % H)];
-        }
+        const ClLane<D> lo_(vo), li_(vi);
+        if (lo_.sub == li_.sub) v = w[lo_.channel() * D + li_.channel()];
         v *= scale;
         const __half hh = __float2half_rn(v);
         const __half ll = __float2half_rn(v - __half2float(hh));
@@ -117,19 +115,41 @@ __device__ __forceinline__ void cl_build_weight_image(const float* __restrict__ 
         *reinterpret_cast<__half*>(lo + off) = ll;
     }
 }
+// Same for the h x h mlp_rpe2 weight, w (H,H) [out][in], on the 64 r lanes: a COMPACT 64 x 64 image (8 KB per plane),
+//   element (vo, vi) at (vi/8) * 1024 + (vo/8) * 128 + (vo%8) * 16 + (vi%8) * 2,   vo, vi < 64.
+// MMAs read it with M = 128: rows 64..127 alias whatever follows in shared memory and produce garbage in TMEM lanes
+// 64..127, which nobody reads (the bytes behind the lo plane must be mapped shared memory).
+constexpr int kClW2Is = 1024;
+constexpr int kClW2Bytes = 8 * kClW2Is;     // one plane
+template <int D>
+__device__ __forceinline__ void cl_build_w2_image(const float* __restrict__ w, float scale, unsigned char* hi,
+                                                  unsigned char* lo) {
+    constexpr int H = D / 2;
+    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+        const int vo = e >> 6, vi = e & 63;
+        float v = (vo / H == vi / H) ? w[(vo % H) * H + (vi % H)] * scale : 0.f;
+        const __half hh = __float2half_rn(v);
+        const __half ll = __float2half_rn(v - __half2float(hh));
+        const int off = (vi >> 3) * kClW2Is + (vo >> 3) * 128 + (vo & 7) * 16 + (vi & 7) * 2;
+        *reinterpret_cast<__half*>(hi + off) = hh;
+        *reinterpret_cast<__half*>(lo + off) = ll;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- row info
-// rinfo[sub][n] = {rpe[10], feature offset of the neighbour (uint32 bits), global point (int bits)}
+// rinfo[sub][n] = {rpe[10], feature offset of the neighbour (uint32 bits), gradient offset of the neighbour (uint32
+// bits; 0xffffffff marks a padding row past the last point)}
 template <int D, int K>
 __device__ __forceinline__ void cl_row_info(float* __restrict__ rinfo, const float* __restrict__ xyz, long long xyz_bstride,
-                                            const int32_t* __restrict__ idx, long long feat_bstride, int N,
-                                            long long npts, long long tile, int l) {
+                                            const int32_t* __restrict__ idx, long long feat_bstride,
+                                            long long dfeat_bstride, int N, long long npts, long long tile, int l) {
     using C = ClCfg<D, K>;
     for (int row = l; row < C::ROWS; row += kClLanes) {
         const int sub = row / C::R, n = row % C::R;
         const int p = n / K, k = n % K;
         long long gp = tile * C::TPTS + sub * C::PTS + p;
-        if (gp >= npts) gp = npts - 1;                       // tail rows recompute the last point (never written)
+        const bool valid = gp < npts;
+        if (!valid) gp = npts - 1;                           // padding rows recompute the last point (never written)
         const int b = (int)(gp / N);
         const int pi = (int)(gp - (long long)b * N);
         const int pj = idx[gp * K + k];
@@ -139,7 +159,8 @@ __device__ __forceinline__ void cl_row_info(float* __restrict__ rinfo, const flo
         dst[0] = make_float4(rpe[0], rpe[1], rpe[2], rpe[3]);
         dst[1] = make_float4(rpe[4], rpe[5], rpe[6], rpe[7]);
         const uint32_t off = (uint32_t)((long long)b * feat_bstride + (long long)pj * C::H);
-        dst[2] = make_float4(rpe[8], rpe[9], __uint_as_float(off), 0.f);
+        const uint32_t doff = valid ? (uint32_t)((long long)b * dfeat_bstride + (long long)pj * C::H) : 0xffffffffu;
+        dst[2] = make_float4(rpe[8], rpe[9], __uint_as_float(off), __uint_as_float(doff));
     }
 }
 

@@ -341,7 +341,7 @@ class _LfaPool2TrainFn(torch.autograd.Function):
         xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1 = ctx.saved_tensors
         h = w1f.shape[0]
         dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,
-                                                        ws.contiguous(), dpooled)
+                                                        ws.contiguous(), dpooled, w_rpe2=w2f.contiguous())
         # The second pass only produces parameter gradients (dW2, and mlp_rpe1's through g1): it runs on the side
         # stream, overlapping pool1.mlp's and stage 1's backward, and is joined in _LfaPool1TrainFn.backward, which
         # also hands (dW2, dgamma2, dbeta2) to autograd (w2 is a pass-through input there).

@@ -160,12 +160,18 @@ def _rows_view(x: torch.Tensor):
 # split-fp16 operands, warp-specialised persistent CTAs).  d in TC_WIDTHS, K in TC_NEIGHBORS; d = 256 stays on the
 # FP32 CUDA-core kernels (its 256 x 256 weight image does not fit shared memory next to the row operands).
 USE_TENSOR_CORES = True
-TC_WIDTHS, TC_NEIGHBORS = (16, 32, 64, 128), (16, 32)
+TC_WIDTHS, TC_NEIGHBORS = (64, 128), (16, 32)          # forward: widths where the tensor-core kernel is the faster one
+TC_BWD_WIDTHS = (64, 128)                              # backward / moments
+TC_ALL_WIDTHS = (16, 32, 64, 128)                      # what the kernels are built for (tests run all of them)
 _TC_STATUS = {}
 
 
 def lfa_pool_tc_supported(d: int, k: int) -> bool:
     return USE_TENSOR_CORES and d in TC_WIDTHS and k in TC_NEIGHBORS
+
+
+def lfa_bwd_tc_supported(d: int, k: int) -> bool:
+    return USE_TENSOR_CORES and d in TC_BWD_WIDTHS and k in TC_NEIGHBORS
 
 
 def tc_status(device) -> torch.Tensor:
@@ -372,6 +378,31 @@ def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _lfa_tc_bwd(mode: int, name: str, flops: float, nbytes: float, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1,
+                w_rpe2=None, a_rpe2=None, b_rpe2=None, w_score=None, dpooled=None, dfeat=None, dws=None, g1=None,
+                du2=None, sums=None, bn2=None, dw2=None, m_r1=None, s_r1=None, scal=None):
+    """One launch of the tensor-core backward / moments kernel family (C ABI ``r3d_lfa_tc_bwd``, csrc/lfa_cl_bwd.cu)."""
+    B, N, K = idx32.shape
+    d = 2 * w_rpe1.shape[0]
+    dev = xyz.device
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"{name}[N={N},d={d}]", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_tc_bwd(
+            mode, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
+            _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2), _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_score),
+            _cabi.ptr(dpooled), _cabi.raw(dfeat), 0, _cabi.raw(dws), _cabi.raw(g1), _cabi.raw(du2), _cabi.raw(sums),
+            _cabi.ptr(bn2), _cabi.raw(dw2), _cabi.raw(m_r1), _cabi.raw(s_r1), _cabi.raw(scal),
+            _cabi.ptr(tc_status(dev)), B, N, K, d, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_tc_bwd")
+
+
+def _absmax_into(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[0] = max |x| (C ABI ``r3d_absmax``; ``out`` zero-filled): the gradient-side operand scale of the tensor-core
+    backward is a power of two derived from it on the device."""
+    with torch.cuda.device(x.device), _cabi.kernel_timer("absmax", flops=float(x.numel()), bytes=4.0 * x.numel()):
+        rc = _cabi.lib().r3d_absmax(_cabi.ptr(x), x.numel(), _cabi.raw(out), _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "r3d_absmax")
+
+
 def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_rpe2s, w_scoreT,
                  w_score, dpooled, g1_acc=None):
     """Backward of ``lfa_pool`` (C ABI ``r3d_lfa_pool_bwd``).  Returns (dfeat (B,N,h), dw_score (d,d)
@@ -398,6 +429,12 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
         g2c = acc64[h * 16 + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
+    if stage == 1 and lfa_bwd_tc_supported(d, K):
+        scal = zeros(2, torch.float32, dev)
+        _absmax_into(dpooled, scal)
+        _lfa_tc_bwd(1, "lfa_cl_bwd1", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1, w_score=w_score,
+                    dpooled=dpooled, dfeat=dfeat, dws=dws, g1=g1, scal=scal)
+        return dfeat, dws, g1, g2m, g2c
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_pool_bwd(
             stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
@@ -425,6 +462,9 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
         g1 = zeros((h, 16), torch.float64, dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
+    if mode == 1 and lfa_bwd_tc_supported(d, K):
+        _lfa_tc_bwd(4, "lfa_cl_mom", flops, nbytes, xyz, xs, idx32, None, 0, w_rpe1, a_rpe1, b_rpe1, m_r1=m_r1, s_r1=s_r1)
+        return m_r1, s_r1
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_moments(mode, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1),
                                          _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.raw(m_rpe), _cabi.raw(m_r1),
@@ -480,9 +520,12 @@ def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments
     return dw, dgb[0], dgb[1], dm, ds
 
 
-def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT, w_score, dpooled):
-    """Pass 1 of the train-mode stage-2 backward (C ABI ``r3d_lfa_pool2_bwd_train``).
-    Returns (dfeat (B,N,h), dw_score (d,d), du2_tiles, sum_du2 (2,h) fp64)."""
+def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT, w_score, dpooled,
+                        w_rpe2=None):
+    """Pass 1 of the train-mode stage-2 backward (C ABI ``r3d_lfa_pool2_bwd_train``, or mode 2 of ``r3d_lfa_tc_bwd``
+    on the tensor cores, which wants ``w_rpe2`` in its stored [out][in] layout).
+    Returns (dfeat (B,N,h), dw_score (d,d), du2_tiles, sum_du2 (2,h) fp64); du2_tiles is opaque (its layout belongs to
+    the kernel family that wrote it) and goes to ``lfa_bn2_bwd`` unchanged."""
     xyz, xs = _cloud_view(xyz)
     feat, fs = _rows_view(feat.detach())
     B, N, K = idx32.shape
@@ -490,6 +533,21 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     d = 2 * h
     dev = xyz.device
     L = _cabi.lib()
+    if lfa_bwd_tc_supported(d, K):
+        if w_rpe2 is None:
+            w_rpe2 = w_rpe2T.t().contiguous()
+        dpooled = dpooled.contiguous()
+        n_df = B * N * h
+        acc = zeros(n_df + d * d + 2, torch.float32, dev)
+        dfeat, dws, scal = acc[:n_df].view(B, N, h), acc[n_df:n_df + d * d].view(d, d), acc[n_df + d * d:]
+        du2 = torch.empty(L.r3d_lfa_tc_du2_floats(B, N, K, d), dtype=torch.float32, device=dev)
+        sums = zeros((2, h), torch.float64, dev)
+        _absmax_into(dpooled, scal)
+        _lfa_tc_bwd(2, "lfa_cl_bwd2", float(B) * N * (2 * K * (10 * h + 3 * d * d + d + h * h)),
+                    float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 8 * K * h), xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1,
+                    b_rpe1, w_rpe2=w_rpe2, a_rpe2=a_rpe2, b_rpe2=b_rpe2, w_score=w_score, dpooled=dpooled, dfeat=dfeat,
+                    dws=dws, du2=du2, sums=sums, scal=scal)
+        return dfeat, dws, (du2, scal), sums
     pts = L.r3d_lfa_tile_points_for(K, d, B, N)
     if pts <= 0:
         raise ValueError(f"r3d_lfa_tile_points_for: unsupported shape d={d}, K={K}")
@@ -523,6 +581,11 @@ def lfa_bn2_bwd(xyz, idx32, w_rpe1, a_rpe1, b_rpe1, du2_tiles, w_rpe2T, w_rpe2, 
     g1, dw2 = (buf[:h * 16].view(h, 16) if g1_acc is None else g1_acc), buf[h * 16:].view(h, h)
     flops = float(B) * N * K * 2 * (10 * h + 3 * h * h + 16 * h)
     nbytes = float(B) * N * (12 + 4 * K + 4 * K * h)
+    if isinstance(du2_tiles, tuple):                 # written by the tensor-core pass 1: (tiles, operand-scale scalars)
+        du2, scal = du2_tiles
+        _lfa_tc_bwd(3, "lfa_cl_bn2", flops, nbytes, xyz, xs, idx32, None, 0, w_rpe1, a_rpe1, b_rpe1, w_rpe2=w_rpe2,
+                    g1=g1, du2=du2, bn2=bn2, dw2=dw2, scal=scal)
+        return g1, dw2
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_bn2_bwd[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_bn2_bwd(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
                                          _cabi.ptr(b_rpe1), _cabi.ptr(du2_tiles), _cabi.ptr(w_rpe2T), _cabi.ptr(w_rpe2),

@@ -128,6 +128,27 @@ int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstride, const in
                     const float* w_rpe2, const float* a_rpe2, const float* b_rpe2, const float* w_score,
                     float* pooled, int* status, int B, int N, int K, int d, r3d_stream_t stream);
 
+/* Training-mode companions of r3d_lfa_pool_tc on the tensor cores (csrc/lfa_cl_bwd.cu; same channel-lane design,
+ * weight-gradient-like sums accumulated in TMEM across the tiles of a persistent CTA).  One entry point, four modes;
+ * arguments a mode does not use may be NULL.  Weights in their stored [out][in] layouts; outputs ACCUMULATED into
+ * caller-zeroed buffers exactly as documented for the FP32 entry points below:
+ *   mode 1  = r3d_lfa_pool_bwd(stage 1):        dfeat, dw_score, g1            (needs scal[0])
+ *   mode 2  = r3d_lfa_pool2_bwd_train (pass 1): dfeat, dw_score, du2_tiles, sum_du2; scal[1] <- max |du2| (atomic max)
+ *   mode 3  = r3d_lfa_bn2_bwd (pass 2):         g1, dw2 from du2_tiles, bn2    (needs scal[1])
+ *   mode 4  = r3d_lfa_moments(mode 1):          m_r1, s_r1
+ * du2_tiles: r3d_lfa_tc_du2_floats(B,N,K,d) floats, 16-byte aligned, layout private to modes 2/3.
+ * scal (2 floats, device): [0] = max |dpooled| written by r3d_absmax before a mode 1/2 launch (the power-of-two scale of
+ * the gradient-side fp16x2 operands is derived from it on the device; [1] zero-filled before mode 2).
+ * status as for r3d_lfa_pool_tc.  Supported: d in {16,32,64,128}, K in {16,32}; else R3D_EUNSUPPORTED. */
+long long r3d_lfa_tc_du2_floats(int B, int N, int K, int d);
+int r3d_absmax(const float* x, long long n, float* out, r3d_stream_t stream);
+int r3d_lfa_tc_bwd(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                   long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                   const float* w_rpe2, const float* a_rpe2, const float* b_rpe2, const float* w_score,
+                   const float* dpooled, float* dfeat, long long dfeat_bstride, float* dw_score, double* g1,
+                   float* du2_tiles, double* sum_du2, const float* bn2, double* dw2, double* m_r1, double* s_r1,
+                   float* scal, int* status, int B, int N, int K, int d, r3d_stream_t stream);
+
 /* Backward of one r3d_lfa_pool launch (autograd of modules.py:316-323 as driven by trainer.py:115-119).
  * Inputs as in the forward plus
  *   w_rpe2s  (h,h)  [out][in] mlp_rpe2 weight with row j scaled by a_rpe2[j]         (stage 2)
