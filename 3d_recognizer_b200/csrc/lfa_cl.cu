@@ -142,16 +142,15 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
         unsigned char* Xlo = Xhi + C::OP_BYTES;
         float* rinfo = reinterpret_cast<float*>(Xlo + C::OP_BYTES);
         const float* ri = rinfo + ln.sub * C::SUB_RI;
-        float w1[10], a1s = 0.f, b1s = 0.f, a2s = 0.f, b2s = 0.f;
-        if (ln.part == 0) {
+        const int lr = l & 63, hh = l >> 6;          // producer role: r lane lr and F lane 64 + lr, row groups [4 hh, 4 hh + 4)
+        const int rc = lr % H;
+        float w1[10], a2s = 0.f, b2s = 0.f;
 #pragma unroll
-            for (int q = 0; q < 10; ++q) w1[q] = a.w_rpe1[ln.c * 10 + q];
-            a1s = a.a_rpe1[ln.c] * kClSx;
-            b1s = a.b_rpe1[ln.c] * kClSx;
-            if (STAGE == 2) {
-                a2s = a.a_rpe2[ln.c] / sw2;            // u2 = acc / (sx sw2); r2 * sx = relu(acc * a2/sw2 + b2 * sx)
-                b2s = a.b_rpe2[ln.c] * kClSx;
-            }
+        for (int q = 0; q < 10; ++q) w1[q] = a.w_rpe1[rc * 10 + q];
+        const float a1s = a.a_rpe1[rc] * kClSx, b1s = a.b_rpe1[rc] * kClSx;
+        if (STAGE == 2) {
+            a2s = a.a_rpe2[rc] / sw2;                  // u2 = acc / (sx sw2); r2 * sx = relu(acc * a2/sw2 + b2 * sx)
+            b2s = a.b_rpe2[rc] * kClSx;
         }
         const uint32_t tbase = tmem + ((uint32_t)((l >> 5) * 32) << 16) + (uint32_t)(g * R);
         const float cs = 1.4426950408889634f / (kClSx * sw);     // log2(e) / (sx sw): scores leave the MMA scaled
@@ -164,32 +163,34 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
             // ---- A: row info
             cl_row_info<D, K>(rinfo, a.xyz, a.xyz_bstride, a.idx, a.feat_bstride, 0, a.N, a.npts, tile, l);
             named_bar_sync(1 + g, kClLanes);
-            // ---- B: row operand X^T (scaled by sx), this thread's channel, 8 rows per unit
-            if (ln.part == 0) {
-#pragma unroll 2
-                for (int ng = 0; ng < R / 8; ++ng) {
+            // ---- B: row operand X^T (scaled by sx).  Thread pair (l, l ^ 64) shares r lane lr and F lane 64 + lr, half
+            // the rows each: every thread carries the same mix of gather latency and mlp_rpe1 arithmetic.
+            {
+                float fv[32];
+                const float* fb = a.feat + rc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) fv[j] = fb[__float_as_uint(ri[(hh * 32 + j) * kClRinfo + 10])];
+#pragma unroll 1
+                for (int u = 0; u < 4; ++u) {
+                    const int ng = hh * 4 + u;
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4* q = reinterpret_cast<const float4*>(ri + (ng * 8 + j) * kClRinfo);
                         v[j] = cl_mlp1(w1, a1s, b1s, q[0], q[1], q[2]);
-                        amax = fmaxf(amax, v[j]);
                     }
-                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(l, ng), v);
+                    amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
                 }
-            } else {
-                const float* fb = a.feat + ln.c;
-#pragma unroll 4
-                for (int ng = 0; ng < R / 8; ++ng) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fb[__float_as_uint(ri[(ng * 8 + j) * kClRinfo + 10])];
-#pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        v[j] *= kClSx;
+                        v[j] = fv[u * 8 + j] * kClSx;
                         amax = fmaxf(amax, fabsf(v[j]));
                     }
-                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(l, ng), v);
+                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(64 + lr, hh * 4 + u), v);
                 }
             }
             fence_async_smem();

@@ -92,6 +92,15 @@ class _fork:
         self.cur.wait_stream(self.side)
 
 
+def _once(ctx, what: str) -> None:
+    """The backward kernels accumulate into scratch that the forward zero-filled once: a second backward over the
+    same graph (retain_graph=True, gradient penalties) would add onto stale sums.  Refuse it loudly."""
+    if getattr(ctx, "_r3d_consumed", False):
+        raise RuntimeError(f"{what}: backward was already run on this graph; the fused kernels accumulate into "
+                           "forward-allocated scratch and cannot be differentiated twice (rerun the forward)")
+    ctx._r3d_consumed = True
+
+
 class _SharedMLPTrainFn(torch.autograd.Function):
     """SharedMLP with train-mode BatchNorm on dense rows x (M,Cin): the sm_100a per-point kernels forward
     (GEMM + batch statistics, normalise + activation) and backward (BatchNorm backward, dx GEMM, dW row-reduction)."""
@@ -109,6 +118,7 @@ class _SharedMLPTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        _once(ctx, "SharedMLP")
         x, w, z, save, beta, scratch = ctx.saved_tensors
         cout = w.shape[0]
         dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope, stats2=scratch[2 * cout:])
@@ -297,6 +307,7 @@ class _LfaPool1TrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpooled):
+        _once(ctx, "LocalFeatureAggregation stage 1")
         xyz, idx32, feat, ws, wsT, gamma1, w1f, a1f, c1f, m, save1, g1 = ctx.saved_tensors
         dfeat, dws, _, _, _ = ops.lfa_pool_bwd(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, None, wsT,
                                                ws.contiguous(), dpooled, g1_acc=g1)
@@ -338,6 +349,7 @@ class _LfaPool2TrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpooled):
+        _once(ctx, "LocalFeatureAggregation stage 2")
         xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1 = ctx.saved_tensors
         h = w1f.shape[0]
         dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,

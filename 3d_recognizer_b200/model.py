@@ -247,7 +247,12 @@ class GraphedTrainStep:
         self.x = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
         self.y = torch.zeros((B, N), dtype=torch.int64, device=dev)
         self.perm = torch.arange(N, dtype=torch.int64, device=dev)
-        self.perm_host = torch.empty(N, dtype=torch.int64).pin_memory()
+        # The host runs ahead of the GPU (no sync per step): the pinned staging buffer of step i may still be in flight
+        # when step i+1 is prepared, so the permutation rotates through a small ring of pinned buffers, each guarded by
+        # an event recorded after its H2D copy; a slot is rewritten only once its copy has completed.
+        self._perm_ring = [torch.empty(N, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        self._perm_done = [None] * self.RING
+        self._slot = 0
         crit = losses.get_loss(loss_function)
         net.train()
 
@@ -293,13 +298,27 @@ class GraphedTrainStep:
         else:
             self.optimizer.zero_grad(set_to_none=True)
 
+    RING = 3
+
     def __call__(self, input: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """input (B,N,3+F) fp32 and labels (B,N) int64, host (pinned) or device.  Returns the loss (a static
-        device scalar, overwritten by the next call)."""
-        self.perm_host.copy_(torch.from_numpy(np.random.permutation(self.perm.shape[0])))
-        self.perm.copy_(self.perm_host, non_blocking=True)
+        device scalar, overwritten by the next call).  Host ``input`` / ``labels`` are copied asynchronously: the caller
+        must leave them untouched until ``self.inputs_consumed`` (a CUDA event recorded after the copies) has
+        completed — ``inputs_consumed.synchronize()`` — or simply not reuse a buffer for the next RING steps."""
+        slot = self._slot
+        self._slot = (slot + 1) % self.RING
+        if self._perm_done[slot] is not None:
+            self._perm_done[slot].synchronize()                 # this slot's previous copy has left the host buffer
+        host = self._perm_ring[slot]
+        host.copy_(torch.from_numpy(np.random.permutation(self.perm.shape[0])))
+        self.perm.copy_(host, non_blocking=True)
+        ev = self._perm_done[slot] or torch.cuda.Event()
+        ev.record()
+        self._perm_done[slot] = ev
         self.x.copy_(input, non_blocking=True)
         self.y.copy_(labels, non_blocking=True)
+        self.inputs_consumed = torch.cuda.Event()
+        self.inputs_consumed.record()
         self.graph.replay()
         if self.graph_opt is not None:
             self.flat.allreduce_mean()

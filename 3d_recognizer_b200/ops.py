@@ -4,6 +4,7 @@ any non-zero status.  No wrapper has a PyTorch or CPU fallback."""
 from typing import Optional, Tuple
 
 import ctypes
+import os
 import numpy as np
 import torch
 
@@ -22,10 +23,12 @@ class _ZeroPool:
 
     def __init__(self):
         self.block, self.off, self.need, self.hint, self.captured = None, 0, 0, 1 << 20, False
+        self.block_stream, self.block_ready, self.waited = None, None, set()
 
     def begin(self):
         self.hint = max(1 << 20, self.need)
         self.block, self.off, self.need = None, 0, 0
+        self.block_stream, self.block_ready, self.waited = None, None, set()
 
     def take(self, shape, dtype, device):
         numel = 1
@@ -49,6 +52,20 @@ class _ZeroPool:
                 return torch.zeros(shape, dtype=dtype, device=device)
             self.block = torch.zeros(max(self.hint, aligned), dtype=torch.uint8, device=device)
             self.off, self.captured = 0, capturing
+            if on_cuda:
+                # the fill is ordered on the creating stream only: remember it, and an event behind the fill
+                self.block_stream = torch.cuda.current_stream(device).cuda_stream
+                self.block_ready = torch.cuda.Event()
+                self.block_ready.record()
+                self.waited = set()
+        if on_cuda and self.block_stream is not None:
+            # A slice taken on ANOTHER stream (a fork, or an autograd node replayed on the stream its forward ran on)
+            # is only ordered after the fill if that stream has synchronised with the creating stream since; make it
+            # wait for the fill once per block (cheap; a graph edge under capture).
+            cur = torch.cuda.current_stream(device)
+            if cur.cuda_stream != self.block_stream and cur.cuda_stream not in self.waited:
+                cur.wait_event(self.block_ready)
+                self.waited.add(cur.cuda_stream)
         out = self.block[self.off:self.off + nbytes].view(dtype).view(shape)
         self.off += aligned
         return out
@@ -163,6 +180,10 @@ USE_TENSOR_CORES = True
 TC_WIDTHS, TC_NEIGHBORS = (64, 128), (16, 32)          # forward: widths where the tensor-core kernel is the faster one
 TC_BWD_WIDTHS = (64, 128)                              # backward / moments
 TC_ALL_WIDTHS = (16, 32, 64, 128)                      # what the kernels are built for (tests run all of them)
+if os.environ.get("R3D_TC_WIDTHS"):                   # tuning override: "fwd widths;bwd widths", e.g. "64,128;16,64,128"
+    _f, _, _b = os.environ["R3D_TC_WIDTHS"].partition(";")
+    TC_WIDTHS = tuple(int(v) for v in _f.split(",") if v)
+    TC_BWD_WIDTHS = tuple(int(v) for v in (_b or _f).split(",") if v)
 _TC_STATUS = {}
 
 

@@ -3,7 +3,7 @@
 CPU restatement of the reference's RandLA-Net hot path (matthiasverstraete/3d_recognizer),
 used as the parity checker.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this package; the
-product package ``3d_recognizer_b200`` never does (tests/test_no_oracle_in_product.py
+product package ``3d_recognizer_b200`` never does (tests/test_host_logic.py (test_product_never_imports_oracle)
 enforces it).
 
 Parity status: the reference ships no tests or golden vectors, so the oracle

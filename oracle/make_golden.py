@@ -225,6 +225,35 @@ def gen_predict(rmod):
     np.savez_compressed(os.path.join(GOLD, "predict_golden.npz"), **out)
 
 
+LOSS_PARAMS = {"dice": (0.5, 1.0), "tversky": (0.7, 1.0), "focal_tversky": (0.7, 4.0 / 3.0)}   # trainer.py:245-269
+
+
+def gen_loss():
+    """The reference's FocalTverskyLoss (losses.py:59-87) with the three parameter sets of Trainer._get_loss
+    (trainer.py:245-269) on seeded logits: loss value and d loss / d logits; also pins oracle.network.dice_loss."""
+    import_reference()
+    from randlanet.utils.losses import FocalTverskyLoss
+    out = {}
+    rng = np.random.RandomState(77)
+    for cname, (B, C, N) in {"b2c2n300": (2, 2, 300), "b3c3n257": (3, 3, 257), "b1c5n64": (1, 5, 64)}.items():
+        logits = (rng.randn(B, C, N) * 2.0).astype(np.float32)
+        labels = rng.randint(0, C, (B, N)).astype(np.int64)
+        out[f"{cname}/logits"], out[f"{cname}/labels"] = logits, labels
+        for name, (alpha, gamma) in LOSS_PARAMS.items():
+            x = torch.from_numpy(logits).requires_grad_(True)
+            loss = FocalTverskyLoss(alpha=alpha, gamma=gamma, neglect_background=True)(x, torch.from_numpy(labels))
+            loss.backward()
+            xo = torch.from_numpy(logits).requires_grad_(True)
+            lo = onet.dice_loss(xo, torch.from_numpy(labels), alpha, gamma)
+            lo.backward()
+            assert abs(float(lo) - float(loss)) < 1e-7 and float((xo.grad - x.grad).abs().max()) < 1e-7 * float(
+                x.grad.abs().max()) + 1e-12, f"oracle loss differs from the reference ({cname}, {name})"
+            out[f"{cname}/{name}/loss"] = np.float32(loss.item())
+            out[f"{cname}/{name}/dlogits"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "loss_golden.npz"), **out)
+    print("loss golden:", len(out), "arrays; oracle.network.dice_loss pinned against the reference's FocalTverskyLoss")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     build(ref=True)
@@ -234,6 +263,7 @@ def main():
     rmod = import_reference()
     gen_e2e(rmod)
     gen_predict(rmod)
+    gen_loss()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 

@@ -55,3 +55,48 @@ def test_tversky_loss_degenerate_labels():
         ref = onet.dice_loss(x.detach().cpu(), lab.cpu())
         assert torch.isfinite(loss) and torch.isfinite(x.grad).all()
         assert abs(float(loss) - float(ref)) < 2e-6
+
+
+LOSS_PARAMS = {"dice": (0.5, 1.0), "tversky": (0.7, 1.0), "focal_tversky": (0.7, 4.0 / 3.0)}   # trainer.py:245-269
+
+
+@pytest.mark.parametrize("name", list(LOSS_PARAMS))
+@pytest.mark.parametrize("case", ["b2c2n300", "b3c3n257", "b1c5n64"])
+def test_loss_kernels_vs_reference_golden(name, case):
+    """Fused loss kernels against the REFERENCE's FocalTverskyLoss (losses.py:59-87) with the parameter sets of
+    Trainer._get_loss: loss value and every d loss / d logits entry (fixtures written by oracle/make_golden.py from
+    the imported reference class)."""
+    import os
+
+    import numpy as np
+
+    from conftest import GOLDEN
+    losses = importlib.import_module("3d_recognizer_b200.losses")
+    g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
+    x = torch.from_numpy(g[f"{case}/logits"]).cuda().requires_grad_(True)
+    labels = torch.from_numpy(g[f"{case}/labels"]).cuda()
+    assert losses.USE_LOSS_KERNELS
+    loss = losses.get_loss(name)(x, labels)
+    loss.backward()
+    ref_loss, ref_grad = float(g[f"{case}/{name}/loss"]), torch.from_numpy(g[f"{case}/{name}/dlogits"])
+    assert abs(float(loss) - ref_loss) < 1e-6
+    assert float((x.grad.cpu() - ref_grad).abs().max()) < 1e-5 * float(ref_grad.abs().max())
+
+
+@pytest.mark.parametrize("name", list(LOSS_PARAMS))
+def test_loss_kernels_vs_oracle_large(name):
+    """The three Tversky variants against the oracle's restatement (pinned to the reference by make_golden.py) at a
+    training-step size, logits in the transposed layout the network hands over."""
+    losses = importlib.import_module("3d_recognizer_b200.losses")
+    alpha, gamma = LOSS_PARAMS[name]
+    gen = torch.Generator().manual_seed(5)
+    base = torch.randn(4, 40960, 2, generator=gen) * 3.0
+    labels = (torch.rand(4, 40960, generator=gen) < 0.03).long()            # fingertip-style class imbalance
+    x = base.cuda().requires_grad_(True)
+    loss = losses.get_loss(name)(x.transpose(1, 2), labels.cuda())
+    loss.backward()
+    xo = base.clone().double().requires_grad_(True)
+    lo = onet.dice_loss(xo.transpose(1, 2), labels, alpha, gamma)
+    lo.backward()
+    assert abs(float(loss) - float(lo)) < 2e-6
+    assert float((x.grad.cpu().double() - xo.grad).abs().max()) < 2e-5 * float(xo.grad.abs().max())

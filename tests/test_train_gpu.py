@@ -204,9 +204,14 @@ def _train_step_case(mods, name):
     ref = torch.from_numpy(g[f"{name}/train_logits"]).cuda()
     if not rel_err(logits.detach(), ref) < TOL:
         fails.append(("logits", rel_err(logits.detach(), ref)))
-    loss = onet.dice_loss(logits, labels)
+    # the product's own loss (fused Dice kernel, csrc/loss.cu) drives the backward; the oracle's is the checker
+    losses = importlib.import_module("3d_recognizer_b200.losses")
+    assert losses.USE_LOSS_KERNELS
+    loss = losses.get_loss("dice")(logits, labels)
     if not abs(loss.item() - float(g[f"{name}/train_loss"])) < 1e-5:
         fails.append(("loss", loss.item()))
+    if not abs(loss.item() - float(onet.dice_loss(logits.detach(), labels))) < 1e-5:
+        fails.append(("loss vs oracle", loss.item()))
     net.zero_grad()
     loss.backward()
     got = {k: onet.grad_fixture_view(p.grad) for k, p in net.named_parameters()}
