@@ -44,6 +44,10 @@ SIGNATURES = {
     "r3d_lfa_tc_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                        [c_void_p] * 8 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
                        [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_r1_rows": (c_int, [c_void_p, ctypes.c_longlong] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_du2_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_tc_wide": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
+                        [c_void_p] * 8 + [ctypes.c_longlong] + [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_pool_bwd": (c_int, [c_int, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong] +
                          [c_void_p] * 10 + [c_void_p, ctypes.c_longlong] + [c_void_p] * 4 +
                          [c_int, c_int, c_int, c_int, c_void_p]),

@@ -339,8 +339,11 @@ class _LfaPool2TrainFn(torch.autograd.Function):
             w2T = w2f.t().contiguous()
             wsT = ws.t().contiguous()
         if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
-            pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f, a2f, c2f, ws.contiguous())
+            ctx.tc_cache = {}           # d = 256: the r2 rows the forward materialised, reused by pass 1 of the backward
+            pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f.contiguous(), a2f, c2f, ws.contiguous(),
+                                     cache=ctx.tc_cache)
         else:
+            ctx.tc_cache = None
             pooled = ops.lfa_pool(2, xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT)
         ctx.w2_shape = w2.shape
         ctx.shared = shared
@@ -353,7 +356,8 @@ class _LfaPool2TrainFn(torch.autograd.Function):
         xyz, idx32, feat, ws, w1f, a1f, c1f, w2f, w2T, wsT, a2f, c2f, save2, g1 = ctx.saved_tensors
         h = w1f.shape[0]
         dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(xyz, idx32, feat, w1f, a1f, c1f, w2T, a2f, c2f, wsT,
-                                                        ws.contiguous(), dpooled, w_rpe2=w2f.contiguous())
+                                                        ws.contiguous(), dpooled, w_rpe2=w2f.contiguous(),
+                                                        cache=ctx.tc_cache)
         # The second pass only produces parameter gradients (dW2, and mlp_rpe1's through g1): it runs on the side
         # stream, overlapping pool1.mlp's and stage 1's backward, and is joined in _LfaPool1TrainFn.backward, which
         # also hands (dW2, dgamma2, dbeta2) to autograd (w2 is a pass-through input there).

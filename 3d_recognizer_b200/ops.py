@@ -177,9 +177,10 @@ def _rows_view(x: torch.Tensor):
 # split-fp16 operands, warp-specialised persistent CTAs).  d in TC_WIDTHS, K in TC_NEIGHBORS; d = 256 stays on the
 # FP32 CUDA-core kernels (its 256 x 256 weight image does not fit shared memory next to the row operands).
 USE_TENSOR_CORES = True
-TC_WIDTHS, TC_NEIGHBORS = (64, 128), (16, 32)          # forward: widths where the tensor-core kernel is the faster one
-TC_BWD_WIDTHS = (64, 128)                              # backward / moments
-TC_ALL_WIDTHS = (16, 32, 64, 128)                      # what the kernels are built for (tests run all of them)
+TC_WIDTHS, TC_NEIGHBORS = (64, 128, 256), (16, 32)     # forward: widths where the tensor-core kernel is the faster one
+TC_BWD_WIDTHS = (64, 128, 256)                         # backward (d = 256: stage-1 backward and pass 1 of stage 2)
+TC_MOM_WIDTHS = (16, 64, 128)                          # r1 moments
+TC_ALL_WIDTHS = (16, 32, 64, 128, 256)                 # what the kernels are built for (tests run all of them)
 if os.environ.get("R3D_TC_WIDTHS"):                   # tuning override: "fwd widths;bwd widths", e.g. "64,128;16,64,128"
     _f, _, _b = os.environ["R3D_TC_WIDTHS"].partition(";")
     TC_WIDTHS = tuple(int(v) for v in _f.split(",") if v)
@@ -193,6 +194,40 @@ def lfa_pool_tc_supported(d: int, k: int) -> bool:
 
 def lfa_bwd_tc_supported(d: int, k: int) -> bool:
     return USE_TENSOR_CORES and d in TC_BWD_WIDTHS and k in TC_NEIGHBORS
+
+
+def lfa_mom_tc_supported(d: int, k: int) -> bool:
+    return USE_TENSOR_CORES and d in TC_MOM_WIDTHS and d <= 128 and k in TC_NEIGHBORS
+
+
+def _lfa_tc_wide(mode: int, name: str, flops: float, nbytes: float, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1,
+                 w_score, rmat=None, pooled=None, dpooled=None, dfeat=None, dws=None, g1=None, du2_part=None, sums=None,
+                 scal=None):
+    """One launch of the d = 256 tensor-core kernel (C ABI ``r3d_lfa_tc_wide``, csrc/lfa_cl_wide.cu)."""
+    B, N, K = idx32.shape
+    dev = xyz.device
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"{name}[N={N},d=256]", flops=flops, bytes=nbytes):
+        rc = _cabi.lib().r3d_lfa_tc_wide(
+            mode, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs, _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
+            _cabi.ptr(b_rpe1), _cabi.ptr(rmat), _cabi.ptr(w_score), _cabi.ptr(pooled), _cabi.ptr(dpooled),
+            _cabi.raw(dfeat), 0, _cabi.raw(dws), _cabi.raw(g1), _cabi.ptr(du2_part), _cabi.raw(sums), _cabi.raw(scal),
+            _cabi.ptr(tc_status(dev)), B, N, K, 256, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_tc_wide")
+
+
+def lfa_r2_rows(xyz, xs, idx32, w_rpe1, a_rpe1, b_rpe1, w_rpe2, a_rpe2, b_rpe2) -> torch.Tensor:
+    """r2 = relu(a2 (W2 r1) + c2) for every (point, neighbour) row, (B*N*K, h): the materialised encoding the d = 256
+    kernels read (``r3d_lfa_r1_rows`` + one per-point layer).  w_rpe2 (h,h) [out][in]."""
+    B, N, K = idx32.shape
+    h = w_rpe1.shape[0]
+    dev = xyz.device
+    rows = B * N * K
+    r1 = torch.empty((rows, h), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_r1_rows[N={N},h={h}]", flops=22.0 * rows * h, bytes=4.0 * rows * h):
+        rc = _cabi.lib().r3d_lfa_r1_rows(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
+                                         _cabi.ptr(b_rpe1), _cabi.ptr(r1), B, N, K, h, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_r1_rows")
+    return pointwise(r1.unsqueeze(0), w_rpe2.contiguous(), a_rpe2, b_rpe2, act="relu", w_out_in=True).squeeze(0)
 
 
 def tc_status(device) -> torch.Tensor:
@@ -218,8 +253,9 @@ def check_tc_status(device) -> None:
 
 
 def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Tensor, w_rpe1, a_rpe1, b_rpe1,
-                w_rpe2, a_rpe2, b_rpe2, w_score) -> torch.Tensor:
-    """``lfa_pool`` on the tensor cores (C ABI ``r3d_lfa_pool_tc``): weights in their stored [out][in] layout."""
+                w_rpe2, a_rpe2, b_rpe2, w_score, cache: Optional[dict] = None) -> torch.Tensor:
+    """``lfa_pool`` on the tensor cores (C ABI ``r3d_lfa_pool_tc``; ``r3d_lfa_tc_wide`` for d = 256): weights in their
+    stored [out][in] layout.  ``cache``: a dict the d = 256 stage-2 forward leaves its r2 rows in for the backward."""
     _cabi.require_cuda(xyz, "xyz")
     xyz, xs = _cloud_view(xyz)
     feat, fs = _rows_view(feat.detach())
@@ -230,6 +266,15 @@ def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.
     pooled = torch.empty((B, N, d), dtype=torch.float32, device=dev)
     flops = float(B) * N * (2 * K * (10 * h + d * d + d + (h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d)
+    if d == 256:
+        rmat = None
+        if stage == 2:
+            rmat = lfa_r2_rows(xyz, xs, idx32, w_rpe1, a_rpe1, b_rpe1, w_rpe2, a_rpe2, b_rpe2)
+            if cache is not None:
+                cache["r2"] = rmat
+        _lfa_tc_wide(0, f"lfa_cl_fwd{stage}", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1,
+                     w_score.contiguous(), rmat=rmat, pooled=pooled)
+        return pooled
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_tc[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_pool_tc(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
                                          _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2),
@@ -450,6 +495,12 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
         g2c = acc64[h * 16 + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
+    if stage == 1 and d == 256 and lfa_bwd_tc_supported(d, K):
+        scal = zeros(2, torch.float32, dev)
+        _absmax_into(dpooled, scal)
+        _lfa_tc_wide(1, "lfa_cl_bwd1", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1, w_score,
+                     dpooled=dpooled, dfeat=dfeat, dws=dws, g1=g1, scal=scal)
+        return dfeat, dws, g1, g2m, g2c
     if stage == 1 and lfa_bwd_tc_supported(d, K):
         scal = zeros(2, torch.float32, dev)
         _absmax_into(dpooled, scal)
@@ -483,7 +534,7 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
         g1 = zeros((h, 16), torch.float64, dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
-    if mode == 1 and lfa_bwd_tc_supported(d, K):
+    if mode == 1 and lfa_mom_tc_supported(d, K):
         _lfa_tc_bwd(4, "lfa_cl_mom", flops, nbytes, xyz, xs, idx32, None, 0, w_rpe1, a_rpe1, b_rpe1, m_r1=m_r1, s_r1=s_r1)
         return m_r1, s_r1
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -542,7 +593,7 @@ def bn_from_moments_bwd(w, s, m, count: float, gamma, save, ga, gc, need_moments
 
 
 def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT, w_score, dpooled,
-                        w_rpe2=None):
+                        w_rpe2=None, cache: Optional[dict] = None):
     """Pass 1 of the train-mode stage-2 backward (C ABI ``r3d_lfa_pool2_bwd_train``, or mode 2 of ``r3d_lfa_tc_bwd``
     on the tensor cores, which wants ``w_rpe2`` in its stored [out][in] layout).
     Returns (dfeat (B,N,h), dw_score (d,d), du2_tiles, sum_du2 (2,h) fp64); du2_tiles is opaque (its layout belongs to
@@ -554,6 +605,30 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     d = 2 * h
     dev = xyz.device
     L = _cabi.lib()
+    if d == 256 and lfa_bwd_tc_supported(d, K):
+        if w_rpe2 is None:
+            w_rpe2 = w_rpe2T.t().contiguous()
+        rmat = cache.pop("r2", None) if cache is not None else None
+        if rmat is None:
+            rmat = lfa_r2_rows(xyz, xs, idx32, w_rpe1, a_rpe1, b_rpe1, w_rpe2, a_rpe2, b_rpe2)
+        dpooled = dpooled.contiguous()
+        n_df = B * N * h
+        acc = zeros(n_df + d * d + 2, torch.float32, dev)
+        dfeat, dws, scal = acc[:n_df].view(B, N, h), acc[n_df:n_df + d * d].view(d, d), acc[n_df + d * d:]
+        rows = B * N * K
+        part = torch.empty((2, rows, h), dtype=torch.float32, device=dev)
+        sums = zeros((2, h), torch.float64, dev)
+        _absmax_into(dpooled, scal)
+        _lfa_tc_wide(2, "lfa_cl_bwd2", float(B) * N * (2 * K * (10 * h + 3 * d * d + d + h * h)),
+                     float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 8 * K * h), xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1,
+                     b_rpe1, w_score, rmat=rmat, dpooled=dpooled, dfeat=dfeat, dws=dws, du2_part=part, sums=sums, scal=scal)
+        pts = L.r3d_lfa_tile_points_for(K, d, B, N)
+        du2 = torch.empty(B * (-(-N // pts)) * h * pts * K, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_du2_combine[N={N},d={d}]", flops=float(rows) * h,
+                                                        bytes=12.0 * rows * h):
+            rc = L.r3d_lfa_du2_combine(_cabi.ptr(part), _cabi.ptr(du2), B, N, K, h, pts, _cabi.stream_ptr(dev))
+        _cabi.check(rc, "r3d_lfa_du2_combine")
+        return dfeat, dws, du2, sums
     if lfa_bwd_tc_supported(d, K):
         if w_rpe2 is None:
             w_rpe2 = w_rpe2T.t().contiguous()

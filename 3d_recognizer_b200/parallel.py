@@ -62,8 +62,11 @@ class FlatGradients:
         world = dist.get_world_size(group)
         if world == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(world)
+        if self.flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # the mean inside the collective: no div_ launch
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)      # gloo (CPU tests) has no AVG
+            self.flat.div_(world)
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

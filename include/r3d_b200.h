@@ -149,6 +149,23 @@ int r3d_lfa_tc_bwd(int mode, const float* xyz, long long xyz_bstride, const int3
                    float* du2_tiles, double* sum_du2, const float* bn2, double* dw2, double* m_r1, double* s_r1,
                    float* scal, int* status, int B, int N, int K, int d, r3d_stream_t stream);
 
+/* The widest level, d = 256 (csrc/lfa_cl_wide.cu): a CTA owns one HALF of the score channels (weights of that half
+ * resident as split-fp16 planes, dWs half in TMEM), the two halves add their partial dX.  mode 0 forward (pooled), mode 1
+ * = r3d_lfa_pool_bwd(stage 1) (dfeat, dw_score, g1), mode 2 = pass 1 of the train-mode stage-2 backward (dfeat,
+ * dw_score, sum_du2 and du2_part = the two halves' partial du2, [half][B*N*K][128]; r3d_lfa_du2_combine adds them into
+ * the tile layout r3d_lfa_bn2_bwd reads, tile_points = r3d_lfa_tile_points_for).  rmat (B*N*K,128), nullable: the r
+ * half of the row operand read from memory instead of evaluating mlp_rpe1 — stage 2 passes r2 = relu(a2 (W2 r1) + c2),
+ * built from r3d_lfa_r1_rows (out (B*N*K,h) = r1 rows) and a per-point layer.  scal[0] = max |dpooled| (r3d_absmax).
+ * Supported: d = 256, K in {16,32}. */
+int r3d_lfa_r1_rows(const float* xyz, long long xyz_bstride, const int32_t* idx, const float* w_rpe1, const float* a_rpe1,
+                    const float* b_rpe1, float* out, int B, int N, int K, int h, r3d_stream_t stream);
+int r3d_lfa_du2_combine(const float* part, float* out, int B, int N, int K, int h, int tile_points, r3d_stream_t stream);
+int r3d_lfa_tc_wide(int mode, const float* xyz, long long xyz_bstride, const int32_t* idx, const float* feat,
+                    long long feat_bstride, const float* w_rpe1, const float* a_rpe1, const float* b_rpe1,
+                    const float* rmat, const float* w_score, float* pooled, const float* dpooled, float* dfeat,
+                    long long dfeat_bstride, float* dw_score, double* g1, float* du2_part, double* sum_du2,
+                    const float* scal, int* status, int B, int N, int K, int d, r3d_stream_t stream);
+
 /* Backward of one r3d_lfa_pool launch (autograd of modules.py:316-323 as driven by trainer.py:115-119).
  * Inputs as in the forward plus
  *   w_rpe2s  (h,h)  [out][in] mlp_rpe2 weight with row j scaled by a_rpe2[j]         (stage 2)

@@ -130,7 +130,7 @@ class Kinks:
             self.found += [(site, int(i), float(flat[i]) / max(rms, 1e-300)) for i in near]
         mask = u > 0
         if site in self.flips:
-            mask = mask.clone()
+            mask = mask.contiguous().clone()          # flat indices are in logical (row-major) order, as recorded
             m = mask.view(-1)
             m[self.flips[site]] = ~m[self.flips[site]]
         return torch.where(mask, u, u * slope)

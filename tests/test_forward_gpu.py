@@ -204,7 +204,8 @@ def test_tcgen05_gemm_3xtf32_matches_fp64(M, N, K):
     assert 1e-5 < errs[1] < 5e-3, errs
 
 
-@pytest.mark.parametrize("d,K", [(16, 16), (32, 16), (64, 16), (128, 16), (16, 32), (64, 32), (128, 32)])
+@pytest.mark.parametrize("d,K", [(16, 16), (32, 16), (64, 16), (128, 16), (256, 16), (16, 32), (64, 32), (128, 32),
+                                 (256, 32)])
 @pytest.mark.parametrize("stage", [1, 2])
 @pytest.mark.parametrize("B,N", [(2, 1000), (3, 37), (1, 20011)])
 def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage, B, N):

@@ -27,13 +27,13 @@ class _force:
 
     def __enter__(self):
         o = self.ops
-        self.saved = (o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS)
+        self.saved = (o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS)
         o.USE_TENSOR_CORES = self.on
-        o.TC_BWD_WIDTHS = o.TC_WIDTHS = o.TC_ALL_WIDTHS
+        o.TC_BWD_WIDTHS = o.TC_WIDTHS = o.TC_MOM_WIDTHS = o.TC_ALL_WIDTHS
 
     def __exit__(self, *exc):
         o = self.ops
-        o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS = self.saved
+        o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS = self.saved
         return False
 
 
@@ -57,7 +57,7 @@ def _case(d, K, B, N, seed):
     return t
 
 
-SHAPES = [(16, 16), (32, 16), (64, 16), (128, 16), (16, 32), (64, 32), (128, 32)]
+SHAPES = [(16, 16), (32, 16), (64, 16), (128, 16), (256, 16), (16, 32), (64, 32), (128, 32), (256, 32)]
 SIZES = [(2, 1000), (3, 37), (1, 9001)]
 
 
@@ -129,10 +129,10 @@ def test_stage2_train_backward_tc_vs_fp32(ops, d, K, B, N):
             dfeat, dws, du2, sums = ops.lfa_pool2_bwd_train(t["xyz"], idx, t["feat"], t["w1"], t["a1"], t["b1"],
                                                             t["w2"].t().contiguous(), a2, c2, t["ws"].t().contiguous(),
                                                             t["ws"], t["dp"], w_rpe2=t["w2"])
-        if on:
+        if on and isinstance(du2, tuple):
             can = _du2_canonical_tc(du2[0], B, N, K, d)
             assert abs(float(du2[1][1]) - float(can.abs().max())) <= 1e-6 * float(can.abs().max())    # absmax for pass 2
-        else:
+        else:                                          # d = 256 hands pass 2 the CUDA-core layout from either family
             can = _du2_canonical_fp32(du2, B, N, K, d, cabi.lib().r3d_lfa_tile_points_for(K, d, B, N))
         # the kernel's batch sums are the sums of its own du2
         assert rel(sums[0], can.double().sum(dim=(0, 1))) < 1e-5
@@ -145,6 +145,8 @@ def test_stage2_train_backward_tc_vs_fp32(ops, d, K, B, N):
     bad = (a - b).abs() > 2e-5 * b.abs().max()
     assert int(bad.sum()) <= max(2, int(1e-5 * a.numel())), int(bad.sum())
     assert bool((((a == 0) | (b == 0)) | ~bad).all()), "du2 differs by more than a ReLU branch flip"
+    if d == 256:
+        return                                         # pass 2 of the widest level runs on the CUDA-core kernel either way
     # pass 2 on identical inputs
     bn2, _, _ = ops.lfa_bn2_coeffs(out[False]["sums"], a2, c2, save2, rows)
     scal = torch.tensor([0.0, float(b.abs().max())], device="cuda")
@@ -162,7 +164,7 @@ def test_stage2_train_backward_tc_vs_fp32(ops, d, K, B, N):
     assert rel(res[True][1], res[False][1]) < 5e-5, rel(res[True][1], res[False][1])
 
 
-@pytest.mark.parametrize("d,K", SHAPES)
+@pytest.mark.parametrize("d,K", [s for s in SHAPES if s[0] <= 128])
 @pytest.mark.parametrize("B,N", SIZES)
 def test_r1_moments_tc_vs_fp32(ops, d, K, B, N):
     t = _case(d, K, B, N, 3 * d + K + N)
