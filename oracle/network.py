@@ -110,13 +110,15 @@ class Kinks:
     """Instrument for the piecewise-linear activations of the network (ReLU / LeakyReLU, modules.py:96-103, :325,
     :565-566).  The reference's arithmetic is unchanged; this only (a) RECORDS, per activation site in call order, the
     elements whose pre-activation lies within ``threshold`` x rms(site) of the kink, and (b) lets a test PIN branches:
-    ``flips[site]`` = flat indices whose branch is toggled against the sign the run itself computes.  Two correct fp32
-    evaluations may put such an element on different sides of the kink (see grad_parity); with the ambiguous elements
-    enumerated by an fp64 run and their branches pinned to the ones the implementation under test took, every
-    gradient entry can be held to the strict tolerance with no outliers (tests/test_kink_pinned_gpu.py)."""
+    ``pins[site]`` = (flat indices, branch values): those elements take the given branch (True = the positive one)
+    whatever sign the run itself computes.  Two correct fp32 evaluations — this port included: its threaded CPU
+    reductions are not bit-reproducible from run to run — may put such an element on different sides of the kink (see
+    grad_parity); with the ambiguous elements enumerated by an fp64 run and ALL of them pinned, every oracle run is
+    deterministic in its branches and every gradient entry can be held to the strict tolerance with no outliers
+    (tests/test_kink_pinned_gpu.py)."""
 
-    def __init__(self, threshold: float = 0.0, flips: "Optional[Dict[int, torch.Tensor]]" = None):
-        self.threshold, self.flips = threshold, flips or {}
+    def __init__(self, threshold: float = 0.0, pins: "Optional[Dict[int, Tuple[torch.Tensor, torch.Tensor]]]" = None):
+        self.threshold, self.pins = threshold, pins or {}
         self.site = 0
         self.found: "List[Tuple[int, int, float]]" = []     # (site, flat index, pre-activation / rms)
 
@@ -129,10 +131,10 @@ class Kinks:
             flat = u.detach().reshape(-1)
             self.found += [(site, int(i), float(flat[i]) / max(rms, 1e-300)) for i in near]
         mask = u > 0
-        if site in self.flips:
+        if site in self.pins:
             mask = mask.contiguous().clone()          # flat indices are in logical (row-major) order, as recorded
-            m = mask.view(-1)
-            m[self.flips[site]] = ~m[self.flips[site]]
+            idx, val = self.pins[site]
+            mask.view(-1)[idx] = val
         return torch.where(mask, u, u * slope)
 
 

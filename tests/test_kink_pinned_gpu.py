@@ -6,11 +6,12 @@ explains why the other gradient tests set a few outliers aside or repeat a step)
 instead of tolerating it:
 
   1. an fp64 run of the oracle enumerates the AMBIGUOUS elements: |pre-activation| <= 2e-6 x rms of its tensor
-     (fp32 evaluations of this network differ by ~1e-6 relative; nothing farther from the kink can flip);
-  2. the implementation under test runs ONCE; if all its gradients already agree with the fp32 oracle, done;
-  3. otherwise the oracle is re-run with one ambiguous element's branch toggled at a time, which gives that toggle's
-     effect on every gradient entry; a least-squares fit over those effects, rounded to {0,1}, says which branches the
-     implementation took;
+     (fp32 evaluations of this network differ by ~1e-6 relative; nothing farther from the kink can flip), with their
+     exact branches.  Every fp32 oracle run below pins ALL of them (the port's own threaded reductions are not
+     bit-reproducible, so an unpinned run may itself flip one of them);
+  2. the implementation under test runs ONCE; if all its gradients agree with the oracle on the exact branches, done;
+  3. otherwise the oracle is re-run with one ambiguous element on the other branch at a time, which gives that
+     toggle's effect on every gradient entry; a subset fit over those effects says which branches the implementation took;
   4. the oracle is run with exactly those branches pinned and EVERY gradient entry (1.3 M) must agree within 1e-4 of
      its tensor's maximum, logits and loss at the same bar.  Deviations that are not branch toggles at ambiguous
      elements cannot be fitted and fail the test.
@@ -29,7 +30,17 @@ TOL = 1e-4
 BAND = 2e-6
 
 
-def _oracle_step(sd, st, x, labels, perm_seed, flips=None, dtype=torch.float32, threshold=0.0):
+def _pins(candidates, state):
+    """{site: (indices, branch values)} for ALL ambiguous elements: candidate j takes branch state[j]."""
+    by_site = {}
+    for (s, i), on in zip(candidates, state):
+        by_site.setdefault(s, ([], []))
+        by_site[s][0].append(i)
+        by_site[s][1].append(bool(on))
+    return {s: (torch.tensor(i), torch.tensor(v)) for s, (i, v) in by_site.items()}
+
+
+def _oracle_step(sd, st, x, labels, perm_seed, pins=None, dtype=torch.float32, threshold=0.0):
     sd_run = {k: (v.to(dtype) if v.is_floating_point() else v.clone()).clone() for k, v in sd.items()}
     leaves = {}
     for k, v in sd_run.items():
@@ -37,7 +48,7 @@ def _oracle_step(sd, st, x, labels, perm_seed, flips=None, dtype=torch.float32, 
             v.requires_grad_(True)
             leaves[k] = v
     np.random.seed(perm_seed)
-    with onet.kinks(onet.Kinks(threshold=threshold, flips=flips)) as kk:
+    with onet.kinks(onet.Kinks(threshold=threshold, pins=pins)) as kk:
         logits = onet.forward(sd_run, st, x.to(dtype), training=True, dropout_p=0.0)
     loss = onet.dice_loss(logits, labels)
     loss.backward()
@@ -65,6 +76,36 @@ def _rel(got, ref, den):
     return torch.cat(out)
 
 
+def _fit_branches(A: torch.Tensor, d: torch.Tensor):
+    """Subset s in {0,1}^k minimising ||d - A s||_2 by greedy coordinate toggling (the toggles' effects are additive to
+    first order; near-collinear columns — two ambiguous elements of one channel — make a real-valued least-squares
+    solution split the weight between them, so rounding it is not good enough)."""
+    k = A.shape[1]
+    on = [False] * k
+    r = d.clone()
+    sq = (A * A).sum(dim=0)
+    for _ in range(4 * k):
+        proj = A.t() @ r
+        gain = torch.where(torch.tensor(on), -2 * proj - sq, 2 * proj - sq)      # reduction of ||r||^2 by toggling i
+        i = int(gain.argmax())
+        if float(gain[i]) <= 0:
+            break
+        r = r + A[:, i] if on[i] else r - A[:, i]
+        on[i] = not on[i]
+    # a toggle that moves only a few entries (one channel of a bias) hardly shows in the 2-norm: finish on the max-norm
+    for _ in range(2 * k):
+        worst = float(r.abs().max())
+        if worst < TOL:
+            break
+        trial = [float((r + A[:, i] if on[i] else r - A[:, i]).abs().max()) for i in range(k)]
+        i = min(range(k), key=lambda j: trial[j])
+        if trial[i] >= worst:
+            break
+        r = r + A[:, i] if on[i] else r - A[:, i]
+        on[i] = not on[i]
+    return on
+
+
 @pytest.mark.parametrize("N,B,seed", [(1024, 2, 11), (2500, 2, 12), (16384, 1, 41)])
 def test_every_gradient_entry_with_pinned_branches(N, B, seed):
     modules = importlib.import_module("3d_recognizer_b200.modules")
@@ -73,9 +114,10 @@ def test_every_gradient_entry_with_pinned_branches(N, B, seed):
     x = torch.from_numpy(make_input(B, N, 0, seed))
     labels = torch.from_numpy(np.random.RandomState(seed).randint(0, 2, (B, N)))
 
-    # 1. ambiguous elements, from exact (fp64) pre-activations
+    # 1. ambiguous elements and their exact branches, from fp64 pre-activations
     _, _, _, k64 = _oracle_step(sd, st, x, labels, 78, dtype=torch.float64, threshold=BAND)
     candidates = [(s, i) for s, i, _ in k64.found]
+    exact = [v > 0 for _, _, v in k64.found]
 
     # 2. the implementation under test, once
     net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
@@ -89,31 +131,37 @@ def test_every_gradient_entry_with_pinned_branches(N, B, seed):
     got = {k: p.grad for k, p in net.named_parameters()}
     logits, loss = logits.detach().cpu(), float(loss)
 
-    ref_logits, ref_loss, ref, _ = _oracle_step(sd, st, x, labels, 78)
+    # the fp32 oracle with every ambiguous element on its exact branch
+    state = list(exact)
+    ref_logits, ref_loss, ref, _ = _oracle_step(sd, st, x, labels, 78, pins=_pins(candidates, state))
     den = _denominators(ref)
     d = _rel(got, ref, den)
-    pinned = []
     if float(d.abs().max()) >= TOL:
         # 3. effect of each ambiguous element's branch on every gradient entry, then fit
         assert candidates, f"gradients differ by {float(d.abs().max()):.2e} and no pre-activation is near a kink"
         cols = []
-        for s, i in candidates:
-            _, _, gi, _ = _oracle_step(sd, st, x, labels, 78, flips={s: torch.tensor([i])})
+        for j in range(len(candidates)):
+            flipped = [(not b) if q == j else b for q, b in enumerate(exact)]
+            _, _, gi, _ = _oracle_step(sd, st, x, labels, 78, pins=_pins(candidates, flipped))
             cols.append(_rel(gi, ref, den))
         A = torch.stack(cols, dim=1)
-        sol = torch.linalg.lstsq(A, d.unsqueeze(1)).solution.reshape(-1)
-        pinned = [c for c, w in zip(candidates, sol.tolist()) if w > 0.5]
-        flips = {}
-        for s, i in pinned:
-            flips.setdefault(s, []).append(i)
-        flips = {s: torch.tensor(v) for s, v in flips.items()}
-        # 4. the oracle with the implementation's branches
-        ref_logits, ref_loss, ref, _ = _oracle_step(sd, st, x, labels, 78, flips=flips)
-        d = _rel(got, ref, den)
+        # 4. the oracle with the implementation's branches.  The toggles' effects are additive only to first order (two
+        # toggles in one BatchNorm channel interact through its statistics), so the fit is repeated on what the pinned
+        # run leaves: at most four oracle runs, the implementation itself is never re-run.
+        for _ in range(4):
+            toggles = _fit_branches(A, d)
+            if not any(toggles):
+                break
+            state = [a != b for a, b in zip(state, toggles)]
+            ref_logits, ref_loss, ref, _ = _oracle_step(sd, st, x, labels, 78, pins=_pins(candidates, state))
+            d = _rel(got, ref, den)
+            if float(d.abs().max()) < TOL:
+                break
+    pinned = [c for c, a, b in zip(candidates, state, exact) if a != b]
     worst = float(d.abs().max())
     assert worst < TOL, (f"{int((d.abs() >= TOL).sum())} of {d.numel()} gradient entries beyond 1e-4 (worst {worst:.2e}) "
-                         f"with {len(pinned)} of {len(candidates)} ambiguous branches pinned")
+                         f"with {len(pinned)} of {len(candidates)} ambiguous branches off their exact side")
     assert float((logits - ref_logits).abs().max() / ref_logits.abs().max()) < TOL
     assert abs(loss - float(ref_loss)) < 1e-5
     print(f"N={N}: {d.numel()} gradient entries within {worst:.1e}; {len(pinned)} of {len(candidates)} ambiguous "
-          "branches pinned")
+          "branches off their exact side")
