@@ -71,6 +71,7 @@ def main():
     err = float((flat.flat.double() - mean).abs().max() / mean.abs().max())
     res["allreduce_mean_rel_err"] = err
     res["ranks_differ_before"] = bool(not torch.equal(gathered[0], gathered[-1]))
+    del loss          # a live autograd graph keeps AccumulateGrad nodes bound to this stream: the capture below would trip on them
 
     # (c) a graphed data-parallel step keeps the replicas' weights identical
     opt = model.make_optimizer(1e-2, capturable=True)
