@@ -542,6 +542,72 @@ extern "C" int r3d_knn(const float* support, long long support_batch_stride, con
     }
 }
 
+// ------------------------------------------------------------------------------------------ host-buffer drop-in
+// Per host thread: two non-blocking streams (search, copy-back), a grow-only device arena and two events.  Nothing here
+// touches the legacy default stream, allocates per call or synchronises the device: a search issued from one thread
+// does not serialise against a training step running in another (reference: main.py:71-89 predicts on the Tk thread
+// while train.py:108-115 trains in a child).
+namespace {
+struct KnnHostCtx {
+    int device = -1;
+    cudaStream_t run = nullptr, copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0;
+    void release() {
+        if (device < 0) return;
+        // the CUDA context may already be gone at thread exit: errors are ignored
+        if (arena) cudaFree(arena);
+        if (run) cudaStreamDestroy(run);
+        if (copy) cudaStreamDestroy(copy);
+        for (auto& e : ready)
+            if (e) cudaEventDestroy(e);
+        *this = KnnHostCtx();
+    }
+    KnnHostCtx() = default;
+    KnnHostCtx(const KnnHostCtx&) = default;
+    KnnHostCtx& operator=(const KnnHostCtx&) = default;
+    ~KnnHostCtx() {
+        if (device >= 0) {
+            if (arena) cudaFree(arena);
+            if (run) cudaStreamDestroy(run);
+            if (copy) cudaStreamDestroy(copy);
+            for (auto& e : ready)
+                if (e) cudaEventDestroy(e);
+        }
+    }
+};
+thread_local KnnHostCtx g_knn_host;
+
+int knn_host_prepare(KnnHostCtx& c, size_t bytes) {
+    int dev = 0;
+    R3D_CUDA_TRY(cudaGetDevice(&dev));
+    if (c.device != dev) {
+        c.release();                  // the thread moved to another device: drop the old resources
+        R3D_CUDA_TRY(cudaStreamCreateWithFlags(&c.run, cudaStreamNonBlocking));
+        R3D_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        for (auto& e : c.ready) R3D_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c.device = dev;
+    }
+    if (c.arena_bytes < bytes) {
+        if (c.arena) {
+            R3D_CUDA_TRY(cudaStreamSynchronize(c.run));
+            R3D_CUDA_TRY(cudaStreamSynchronize(c.copy));
+            R3D_CUDA_TRY(cudaFree(c.arena));
+            c.arena = nullptr;
+            c.arena_bytes = 0;
+        }
+        const size_t want = align_up(bytes + bytes / 4, (size_t)1 << 20);
+        R3D_CUDA_TRY(cudaMalloc(&c.arena, want));
+        c.arena_bytes = want;
+    }
+    return R3D_OK;
+}
+}  // namespace
+
+// Host buffers may be pageable or page-locked.  The search runs in chunks of clouds (or of queries when there are few
+// clouds); chunk i's results travel back on the copy stream while chunk i+1 is searched.  Into page-locked outputs
+// (what the Python host allocates) that copy is a direct DMA at PCIe rate.
 extern "C" int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq, int K, int64_t* idx64,
                             float* dist_sq) {
     if (B < 0 || Ns < 0 || Nq < 0 || K <= 0) return R3D_EINVAL;
@@ -551,27 +617,48 @@ extern "C" int r3d_knn_host(const float* support, const float* query, int B, int
     if (!support || !query || !idx64 || !dist_sq) return R3D_EINVAL;
     const size_t sb = (size_t)B * Ns * 3 * sizeof(float), qb = (size_t)B * Nq * 3 * sizeof(float);
     const size_t ib = (size_t)B * Nq * K * sizeof(int64_t), db = (size_t)B * Nq * K * sizeof(float);
-    const size_t wb = r3d_knn_workspace_bytes(B, Ns, Nq, K);
     const bool self = (support == query && Ns == Nq);
-    unsigned char* dev = nullptr;
+    // chunking: whole clouds when there are many, query ranges of one cloud otherwise
+    const long long total_q = (long long)B * Nq;
+    int nchunk = (int)(total_q / 196608);
+    nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
+    const bool by_cloud = B >= nchunk * 2 || Nq < 4096;
+    const int cb = by_cloud ? ceil_div(B, nchunk) : 1;                 // clouds per chunk
+    const int cq = by_cloud ? Nq : ceil_div(Nq, nchunk);               // queries per chunk
+    const size_t wb = r3d_knn_workspace_bytes(cb, Ns, cq, K);
     const size_t o_s = 0, o_q = align_up(sb, 256), o_i = o_q + (self ? 0 : align_up(qb, 256)),
                  o_d = o_i + align_up(ib, 256), o_w = o_d + align_up(db, 256);
-    R3D_CUDA_TRY(cudaMalloc(&dev, o_w + wb));
-    cudaStream_t st = nullptr;
+    KnnHostCtx& c = g_knn_host;
+    const int prc = knn_host_prepare(c, o_w + wb);
+    if (prc != R3D_OK) return prc;
+    unsigned char* dev = c.arena;
+    float* d_s = reinterpret_cast<float*>(dev + o_s);
+    float* d_q = self ? d_s : reinterpret_cast<float*>(dev + o_q);
+    int64_t* d_i = reinterpret_cast<int64_t*>(dev + o_i);
+    float* d_d = reinterpret_cast<float*>(dev + o_d);
     int rc = R3D_OK;
-    cudaError_t e = cudaMemcpyAsync(dev + o_s, support, sb, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && !self) e = cudaMemcpyAsync(dev + o_q, query, qb, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        rc = r3d_knn(reinterpret_cast<float*>(dev + o_s), 0, reinterpret_cast<float*>(dev + (self ? o_s : o_q)), 0, B,
-                     Ns, Nq, K, reinterpret_cast<int64_t*>(dev + o_i), nullptr, nullptr,
-                     reinterpret_cast<float*>(dev + o_d), dev + o_w, wb, st);
-        if (rc == R3D_OK) {
-            e = cudaMemcpyAsync(idx64, dev + o_i, ib, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(dist_sq, dev + o_d, db, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaMemcpyAsync(d_s, support, sb, cudaMemcpyHostToDevice, c.run);
+    if (e == cudaSuccess && !self) e = cudaMemcpyAsync(d_q, query, qb, cudaMemcpyHostToDevice, c.run);
+    int n = 0;
+    for (int b0 = 0; b0 < B && e == cudaSuccess && rc == R3D_OK; b0 += cb) {
+        const int nb = (B - b0 < cb) ? B - b0 : cb;
+        for (int q0 = 0; q0 < Nq && e == cudaSuccess && rc == R3D_OK; q0 += cq, ++n) {
+            const int nq = (Nq - q0 < cq) ? Nq - q0 : cq;
+            const size_t off = ((size_t)b0 * Nq + q0) * K;             // first result of this chunk (contiguous: nb == 1 or nq == Nq)
+            const size_t cnt = (size_t)nb * nq * K;
+            rc = r3d_knn(d_s + (size_t)b0 * Ns * 3, 0, d_q + ((size_t)b0 * Nq + q0) * 3, by_cloud ? 0 : (long long)Nq * 3,
+                         nb, Ns, nq, K, d_i + off, nullptr, nullptr, d_d + off, dev + o_w, wb, c.run);
+            if (rc != R3D_OK) break;
+            cudaEvent_t ev = c.ready[n & 1];
+            e = cudaEventRecord(ev, c.run);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c.copy, ev, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(idx64 + off, d_i + off, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, c.copy);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dist_sq + off, d_d + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c.copy);
         }
     }
-    cudaFree(dev);
+    // always drain both streams: the arena is reused by the next call
+    const cudaError_t e1 = cudaStreamSynchronize(c.run), e2 = cudaStreamSynchronize(c.copy);
+    if (e == cudaSuccess) e = (e1 != cudaSuccess) ? e1 : e2;
     if (e != cudaSuccess) {
         set_cuda_error(e, "r3d_knn_host");
         return R3D_ECUDA;

@@ -232,16 +232,19 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
             mbar_wait(&done[g], done_phase);
             done_phase ^= 1u;
             tc_fence_after_sync();
-#pragma unroll 2
+            uint32_t un[K];                                            // scores of the NEXT point, loaded while this one is reduced
+#pragma unroll
+            for (int k0 = 0; k0 < K; k0 += 16) tmem_ld16_nowait(tbase + (uint32_t)k0, *reinterpret_cast<uint32_t(*)[16]>(un + k0));
+            tmem_ld_wait();
+#pragma unroll
             for (int p = 0; p < C::PTS; ++p) {
                 float s[K], x[K];
 #pragma unroll
-                for (int k0 = 0; k0 < K; k0 += 16) {
-                    uint32_t u[16];
-                    tmem_ld16_nowait(tbase + (uint32_t)(p * K + k0), u);
-                    tmem_ld_wait();
+                for (int k = 0; k < K; ++k) s[k] = __uint_as_float(un[k]);
+                if (p + 1 < C::PTS) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) s[k0 + j] = __uint_as_float(u[j]);
+                    for (int k0 = 0; k0 < K; k0 += 16)
+                        tmem_ld16_nowait(tbase + (uint32_t)((p + 1) * K + k0), *reinterpret_cast<uint32_t(*)[16]>(un + k0));
                 }
 #pragma unroll
                 for (int k0 = 0; k0 < K; k0 += 8) {
@@ -250,19 +253,22 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[k0 + j] = t[j];
                 }
-                float m = s[0];
+                float m = fmaxf(s[0], s[1]);
 #pragma unroll
-                for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+                for (int k = 2; k < K; k += 2) m = fmaxf(m, fmaxf(s[k], s[k + 1]));
                 const float mc = m * cs;
-                float den = 0.f, num = 0.f;
+                float den0 = 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float e = ex2_approx(fmaf(s[k], cs, -mc));
-                    den += e;
-                    num = fmaf(e, x[k], num);
+                for (int k = 0; k < K; k += 2) {
+                    const float e0 = ex2_approx(fmaf(s[k], cs, -mc)), e1 = ex2_approx(fmaf(s[k + 1], cs, -mc));
+                    den0 += e0;
+                    den1 += e1;
+                    num0 = fmaf(e0, x[k], num0);
+                    num1 = fmaf(e1, x[k + 1], num1);
                 }
                 const long long gp = tile * C::TPTS + ln.sub * C::PTS + p;
-                if (gp < a.npts) a.pooled[gp * D + ln.channel()] = (num * inv_sx) / den;
+                if (gp < a.npts) a.pooled[gp * D + ln.channel()] = ((num0 + num1) * inv_sx) / (den0 + den1);
+                if (p + 1 < C::PTS) tmem_ld_wait();
             }
             tc_fence_before_sync();
         }

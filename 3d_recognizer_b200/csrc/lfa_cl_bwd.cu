@@ -365,20 +365,30 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
 
             if (MODE == 1 || MODE == 2) {
                 // ---- C: softmax, pooled, dS -> operand planes, g A -> TMEM (initial value of dX^T)
+                // the upstream gradient of this lane's channel for the tile's points: in flight while the MMA runs
+                float gpre[C::PTS];
+#pragma unroll
+                for (int p = 0; p < C::PTS; ++p) {
+                    const long long gp = tile * C::TPTS + ln.sub * C::PTS + p;
+                    gpre[p] = (gp < a.npts) ? a.dpooled[gp * D + ln.channel()] : 0.f;
+                }
                 mbar_wait(&done[g], done_phase);
                 done_phase ^= 1u;
                 tc_fence_after_sync();
                 const float gsw = sg * sw;
-#pragma unroll 1
+                uint32_t un[K];                                        // scores of the NEXT point, loaded while this one is reduced
+#pragma unroll
+                for (int k0 = 0; k0 < K; k0 += 16) tmem_ld16_nowait(tacc + (uint32_t)k0, *reinterpret_cast<uint32_t(*)[16]>(un + k0));
+                tmem_ld_wait();
+#pragma unroll
                 for (int p = 0; p < C::PTS; ++p) {
                     float s[K], x[K];
 #pragma unroll
-                    for (int k0 = 0; k0 < K; k0 += 16) {
-                        uint32_t u[16];
-                        tmem_ld16_nowait(tacc + (uint32_t)(p * K + k0), u);
-                        tmem_ld_wait();
+                    for (int k = 0; k < K; ++k) s[k] = __uint_as_float(un[k]);
+                    if (p + 1 < C::PTS) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) s[k0 + j] = __uint_as_float(u[j]);
+                        for (int k0 = 0; k0 < K; k0 += 16)
+                            tmem_ld16_nowait(tacc + (uint32_t)((p + 1) * K + k0), *reinterpret_cast<uint32_t(*)[16]>(un + k0));
                     }
 #pragma unroll
                     for (int k0 = 0; k0 < K; k0 += 8) {
@@ -387,22 +397,23 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
 #pragma unroll
                         for (int j = 0; j < 8; ++j) x[k0 + j] = t[j];
                     }
-                    float m = s[0];
+                    float m = fmaxf(s[0], s[1]);
 #pragma unroll
-                    for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+                    for (int k = 2; k < K; k += 2) m = fmaxf(m, fmaxf(s[k], s[k + 1]));
                     const float mc = m * cs;
-                    float den = 0.f, num = 0.f;
+                    float den0 = 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
+                    for (int k = 0; k < K; k += 2) {
                         s[k] = ex2_approx_b(fmaf(s[k], cs, -mc));
-                        den += s[k];
-                        num = fmaf(s[k], x[k], num);
+                        s[k + 1] = ex2_approx_b(fmaf(s[k + 1], cs, -mc));
+                        den0 += s[k];
+                        den1 += s[k + 1];
+                        num0 = fmaf(s[k], x[k], num0);
+                        num1 = fmaf(s[k + 1], x[k + 1], num1);
                     }
-                    const float inv = 1.0f / den;
-                    const float pooled = num * inv;                       // scaled by sx like x
-                    const long long gp = tile * C::TPTS + ln.sub * C::PTS + p;
-                    const float gv = (gp < a.npts) ? a.dpooled[gp * D + ln.channel()] * sg : 0.f;
-                    const float gi = gv * inv;
+                    const float inv = 1.0f / (den0 + den1);
+                    const float pooled = (num0 + num1) * inv;             // scaled by sx like x
+                    const float gi = gpre[p] * sg * inv;
 #pragma unroll
                     for (int k0 = 0; k0 < K; k0 += 16) {
                         uint32_t u[16];
@@ -421,6 +432,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                         for (int j = 0; j < 8; ++j) t[j] = x[k0 + j];
                         cl_store_unit(Shi, Slo, cl_unit_off<D, K>(l, (p * K + k0) / 8), t);
                     }
+                    if (p + 1 < C::PTS) tmem_ld_wait();
                 }
                 tmem_st_wait();
                 fence_async_smem();
@@ -436,16 +448,21 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                 if (ln.part == 1) {
                     // feature half: dfeat[idx[row]] += dX, lanes = consecutive channels
                     float* df = a.dfeat + ln.c;
-#pragma unroll 1
+                    uint32_t un[16];
+                    tmem_ld16_nowait(tacc, un);
+                    tmem_ld_wait();
+#pragma unroll
                     for (int c0 = 0; c0 < R; c0 += 16) {
                         uint32_t u[16];
-                        tmem_ld16_nowait(tacc + (uint32_t)c0, u);
-                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) u[j] = un[j];
+                        if (c0 + 16 < R) tmem_ld16_nowait(tacc + (uint32_t)(c0 + 16), un);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const uint32_t off = __float_as_uint(ri[(c0 + j) * kClRinfo + 11]);
                             if (off != 0xffffffffu) red_add_f32(df + off, __uint_as_float(u[j]) * inv2);
                         }
+                        if (c0 + 16 < R) tmem_ld_wait();
                     }
                 } else {
                     float part[11];

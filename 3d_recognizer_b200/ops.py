@@ -151,8 +151,14 @@ def knn_host(support: np.ndarray, query: np.ndarray, k: int) -> Tuple[np.ndarray
         raise ValueError("support and query must have shape (B, N, 3)")
     B, Ns, _ = support.shape
     Nq = query.shape[1]
-    idx = np.empty((B, Nq, k), dtype=np.int64)
-    d2 = np.empty((B, Nq, k), dtype=np.float32)
+    # page-locked outputs (torch's caching host allocator: a buffer released by the caller is reused by the next call):
+    # the device -> host copies of r3d_knn_host are then direct DMAs that overlap the search of the next chunk
+    if torch.cuda.is_available():
+        idx = torch.empty((B, Nq, k), dtype=torch.int64, pin_memory=True).numpy()
+        d2 = torch.empty((B, Nq, k), dtype=torch.float32, pin_memory=True).numpy()
+    else:
+        idx = np.empty((B, Nq, k), dtype=np.int64)
+        d2 = np.empty((B, Nq, k), dtype=np.float32)
     rc = _cabi.lib().r3d_knn_host(ctypes.c_void_p(support.ctypes.data), ctypes.c_void_p(query.ctypes.data), B, Ns, Nq,
                                   k, ctypes.c_void_p(idx.ctypes.data), ctypes.c_void_p(d2.ctypes.data))
     _cabi.check(rc, "r3d_knn_host")

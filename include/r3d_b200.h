@@ -75,7 +75,10 @@ int r3d_knn(const float* support, long long support_batch_stride, const float* q
             long long query_batch_stride, int B, int Ns, int Nq, int K,
             int64_t* idx64, int32_t* idx32, float* dist, float* dist_sq,
             void* workspace, size_t workspace_bytes, r3d_stream_t stream);
-/* host-buffer drop-in for knn_tpk.knn: (idx int64, d2 fp32), both (B,Nq,K), caller-allocated. */
+/* host-buffer drop-in for knn_tpk.knn: (idx int64, d2 fp32), both (B,Nq,K), caller-allocated, pageable or page-locked
+ * (into page-locked outputs the results arrive by direct DMA, chunk by chunk, while the next chunk is searched).  Uses
+ * per-thread non-blocking streams and a cached grow-only device arena: no allocation per call after the first, never the
+ * legacy default stream, no device-wide synchronisation. */
 int r3d_knn_host(const float* support, const float* query, int B, int Ns, int Nq, int K,
                  int64_t* idx64, float* dist_sq);
 /* tuning hook for benchmarks/tests: 0 exact scalar, 1 FMA-prefilter scalar, 2 FMA-prefilter

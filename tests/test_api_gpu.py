@@ -243,3 +243,70 @@ def test_flat_adam_matches_torch_adam(mods, bound):
     net_c = modules.SharedMLP(8, 16, activation=torch.nn.ReLU()).cuda()
     net_c.load_state_dict(sd)
     assert all(torch.equal(pb, pc) for pb, pc in zip(net_b.parameters(), net_c.parameters()))
+
+
+def test_eval_forward_65536_vs_oracle(mods):
+    """BASELINE config 3's middle size, one cloud of 65 536 points (uniform-grid KNN at level 0, tensor-core LFA kernels
+    at levels 1-3, tcgen05 per-point layers): eval logits against the oracle port on the CPU."""
+    modules, _, _ = mods
+    st = dict(n_classes=2, n_points=65536, n_features=0, n_neighbors=16, knn="kdtree")
+    sd = onet.synth_state_dict(st, 5)
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.from_numpy(make_input(1, 65536, 0, 5))
+    np.random.seed(1)
+    with torch.no_grad():
+        got = net(x.cuda()).cpu()
+    np.random.seed(1)
+    with torch.no_grad():
+        ref = onet.forward({k: v.clone() for k, v in sd.items()}, st, x, training=False)
+    assert rel_err(got, ref) < TOL
+    importlib.import_module("3d_recognizer_b200.ops").check_tc_status(torch.device("cuda"))
+
+
+def test_train_step_40960x2_vs_oracle_port(mods):
+    """BASELINE config 4's cloud size (40 960 points, two clouds): train-mode logits, loss and BatchNorm running
+    statistics at the strict bar, one run, no retries.  Gradients: every tensor within 1 % relative L2 and >= 99.9 % of
+    the 1.3 M entries within 3e-3 of their tensor's maximum — at this size ~130 pre-activations sit within fp32
+    round-off of a ReLU kink, a dozen of them end up on the other branch than in the oracle's own (not bit-reproducible)
+    run, and each such toggle moves whole tensors by 1e-4..1e-3; pinning them one oracle run at a time
+    (tests/test_kink_pinned_gpu.py does exactly that up to 16 384 points, where EVERY entry then agrees within 1e-4)
+    would take a quarter of an hour here."""
+    modules, _, _ = mods
+    N, B, seed = 40960, 2, 7
+    st = dict(n_classes=2, n_points=N, n_features=0, n_neighbors=16, knn="kdtree")
+    sd = onet.synth_state_dict(st, seed)
+    x = torch.from_numpy(make_input(B, N, 0, seed))
+    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, 2, (B, N)))
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    leaves = {}
+    for k, v in sd_ref.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            leaves[k] = v
+    np.random.seed(78)
+    ref_logits = onet.forward(sd_ref, st, x, training=True, dropout_p=0.0)
+    ref_loss = onet.dice_loss(ref_logits, labels)
+    ref_loss.backward()
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(sd)
+    net.train()
+    net.fc_end[2].p = 0.0
+    np.random.seed(78)
+    logits = net(x.cuda())
+    loss = onet.dice_loss(logits, labels.cuda())
+    loss.backward()
+    assert rel_err(logits.detach().cpu(), ref_logits.detach()) < TOL
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert torch.allclose(v.cpu(), sd_ref[k].detach(), rtol=1e-4, atol=1e-5), k
+    got = {k: p.grad for k, p in net.named_parameters()}
+    refg = {k: v.grad for k, v in leaves.items()}
+    worst_l2, wname = onet.grad_parity_l2(got, refg)
+    fracs = {t: onet.grad_parity_fraction(got, refg, t) for t in (1e-4, 3e-4, 1e-3, 3e-3)}
+    print(f"40960x2: worst tensor rel-L2 {worst_l2:.2e} ({wname}); fraction of entries within tol: {fracs}")
+    assert worst_l2 < 1e-2, (worst_l2, wname)
+    assert fracs[3e-3] >= 0.999, fracs
+    importlib.import_module("3d_recognizer_b200.ops").check_tc_status(torch.device("cuda"))
