@@ -88,6 +88,8 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "r3d_tversky_loss_bwd": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_confusion_counts": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
+                                     c_int, c_int, c_void_p, c_void_p]),
     "r3d_pointwise_bn": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int,
                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -110,20 +110,26 @@ class Model:
         if self.settings.upsampling == "none":
             prepostprocess = False
         dev = self._model.device
-        with torch.no_grad():
-            input_t = torch.from_numpy(np.ascontiguousarray(input, dtype=np.float32)).to(dev, non_blocking=True)
-            if prepostprocess:
-                # host RNG draw identical to the reference (preprocessing.py:35-62, consistent=True)
-                indices = sample_points(input.shape[1], self.settings.n_points, consistent=True)
-                idx_t = torch.from_numpy(indices).to(dev, non_blocking=True)
-                sampled = input_t.index_select(1, idx_t)
-                logits = self._model(sampled)
-                predictions = self.upsample(logits, sampled[:, :, :3], input_t[:, :, :3]).cpu().numpy()
-            else:
-                predictions = torch.softmax(self._model(input_t), dim=-2).cpu().numpy()
+        input_t = torch.from_numpy(np.ascontiguousarray(input, dtype=np.float32)).to(dev, non_blocking=True)
+        predictions = self.predict_device(input_t, prepostprocess).cpu().numpy()
         if not batched:
             predictions = predictions[0]
         return predictions
+
+    def predict_device(self, input_t: torch.Tensor, prepostprocess: bool = True) -> torch.Tensor:
+        """The device part of ``predict``: input_t (B,N,3+F) fp32 on the model's device -> class confidences (B,C,N) on
+        the device.  Pre-sampling indices come from the host RNG exactly as in the reference (preprocessing.py:35-62,
+        consistent=True); soft-max, the K=1 / K=8 neighbour search and the (weighted) gather back to the full cloud
+        (model.py:123-144, modules.py:328-456) run on the device."""
+        dev = self._model.device
+        with torch.no_grad():
+            if prepostprocess and self.settings.upsampling != "none":
+                indices = sample_points(input_t.shape[1], self.settings.n_points, consistent=True)
+                idx_t = torch.from_numpy(indices).to(dev, non_blocking=True)
+                sampled = input_t.index_select(1, idx_t)
+                logits = self._model(sampled)
+                return self.upsample(logits, sampled[:, :, :3], input_t[:, :, :3])
+            return torch.softmax(self._model(input_t), dim=-2)
 
     # ------------------------------------------------------------------ training step (trainer.py:107-119)
     def make_optimizer(self, learning_rate: float = 1e-2, capturable: bool = False,

@@ -281,7 +281,7 @@ def lfa_pool_tc(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.
         _lfa_tc_wide(0, f"lfa_cl_fwd{stage}", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1,
                      w_score.contiguous(), rmat=rmat, pooled=pooled)
         return pooled
-    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_pool{stage}_tc[N={N},d={d}]", flops=flops, bytes=nbytes):
+    with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_cl_fwd{stage}[N={N},d={d}]", flops=flops, bytes=nbytes):
         rc = _cabi.lib().r3d_lfa_pool_tc(stage, _cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.raw(feat), fs,
                                          _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1), _cabi.ptr(b_rpe1), _cabi.ptr(w_rpe2),
                                          _cabi.ptr(a_rpe2), _cabi.ptr(b_rpe2), _cabi.ptr(w_score), _cabi.ptr(pooled),

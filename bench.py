@@ -15,6 +15,8 @@ clouds.  Workloads (BASELINE.json `configs`):
   train2500   (configs[1]) the same step on 8 clouds x 2 500 points (train.py:50-56 cloud size) per GPU (weak)
   infer16k | infer64k | infer256k   (configs[2]) eval forward, global batch 32 split over the GPUs
   knn1m_k16 | knn1m_k32             (configs[4]) 1 M x 1 M exact KNN micro-benchmark (1 GPU)
+  predict160k                       (configs[0]'s call, on the GPU) Model.predict of one 160 998-point LiDAR-shaped frame
+                                    with the repo-default model: the UI's 250 ms budget (main.py:49)
 
 `value`  : points/sec (queries/sec for knn*) with the batch already resident in HBM.
 `e2e`    : the same through the public API (Model.train_step / Model.predict / ops.knn_host) with HOST
@@ -48,6 +50,9 @@ WORKLOADS = {
     "infer16k": dict(kind="infer", n=16384, k=16, global_batch=32, scaling="strong"),
     "infer64k": dict(kind="infer", n=65536, k=16, global_batch=32, scaling="strong"),
     "infer256k": dict(kind="infer", n=262144, k=16, global_batch=32, scaling="strong"),
+    # the UI's prediction call (main.py:49: one Model.predict every 250 ms on the Tk thread): one 160 998-point frame
+    # (the mock L515 frames' size), repo-default model (train.py:50-51: 2 500 points, K = 32), host array in and out
+    "predict160k": dict(kind="predict", n=160998, k=32, per_gpu_batch=1, scaling="weak"),
     "knn1m_k16": dict(kind="knn", n=1 << 20, k=16, per_gpu_batch=1, scaling="weak"),
     "knn1m_k32": dict(kind="knn", n=1 << 20, k=32, per_gpu_batch=1, scaling="weak"),
 }
@@ -62,8 +67,10 @@ def load_peaks():
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -234,7 +241,8 @@ def kernel_family(name):
     (lfa_pool_kernel<D,K,STAGE> / lfa_pool_bwd_kernel<D,K,NT,STAGE>)."""
     base = name.split("[")[0]
     for a, b in (("lfa_pool1_bwd", "lfa_pool_bwd"), ("lfa_pool2_bwd", "lfa_pool_bwd"), ("lfa_pool1", "lfa_pool"),
-                 ("lfa_pool2", "lfa_pool")):
+                 ("lfa_pool2", "lfa_pool"), ("lfa_cl_fwd1", "lfa_cl_fwd"), ("lfa_cl_fwd2", "lfa_cl_fwd"),
+                 ("lfa_cl_bwd1", "lfa_cl_bwd"), ("lfa_cl_bwd2", "lfa_cl_bwd")):
         if base == a:
             return b
     return base
@@ -261,6 +269,16 @@ def roofline_of(tab, peaks, fp32_peak):
     n = max(f["launches"], 1)
     t_hbm = f["bytes"] / (peaks["hbm_gbs"] * 1e9)
     t_fp32 = f["flops"] / (fp32_peak["ffma"] * 1e12)
+    if name.startswith("lfa_cl_"):
+        # tensor-core (tcgen05, split-fp16) kernels: the contraction runs on the tensor pipe.  achieved = ALGORITHMIC
+        # fp32-equivalent flops / time; each algorithmic product costs three fp16 MMAs, so 1/3 of the peak is the ceiling
+        tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        ach = f["flops"] / t_s * 1e-12
+        return dict(kernel=name, launches=f["launches"], ms_avg=f["ms"] / n, traffic=None, shapes=sorted(f["shapes"]),
+                    algorithmic_flops_per_launch=f["flops"] / n, algorithmic_bytes_per_launch=f["bytes"] / n,
+                    bound="tensor", achieved=ach, peak=tpeak, unit="TFLOP/s", frac=ach / tpeak,
+                    peak_source=peaks["source"] + ": dense bf16/fp16 tensor peak, sustained; fp32-accurate split-fp16 "
+                                "issues 3 MMAs per algorithmic product (attainable <= 1/3 of this peak)")
     common = dict(kernel=name, launches=f["launches"], ms_avg=f["ms"] / n, traffic=None, shapes=sorted(f["shapes"]),
                   algorithmic_flops_per_launch=f["flops"] / n, algorithmic_bytes_per_launch=f["bytes"] / n)
     if t_fp32 >= t_hbm:
@@ -281,6 +299,22 @@ def cpu_train_or_infer(kind, n, k, batch, budget_s, max_steps, seed=0):
     from oracle import network as onet
     syn = importlib.import_module("3d_recognizer_b200.synthetic")
     losses = importlib.import_module("3d_recognizer_b200.losses")
+    if kind == "predict":
+        # Model.predict of the reference on the CPU (oracle port: consistent pre-sampling to 2 500 points, eval forward,
+        # soft-max, 1-NN up-sampling back to the full frame), one frame per step
+        st = dict(SETTINGS, n_points=2500, n_neighbors=k)
+        sd = onet.synth_state_dict(st, seed)
+        frame = syn.fingertip_cloud(np.random.RandomState(seed), n)[0]
+        times = []
+        t_start = time.perf_counter()
+        for i in range(max_steps + 1):
+            t0 = time.perf_counter()
+            onet.predict(sd, st, frame)
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget_s and times:
+                break
+        return n / statistics.mean(times), len(times), 1, torch.get_num_threads()
     st = dict(SETTINGS, n_points=n, n_neighbors=k)
     sd = onet.synth_state_dict(st, seed)
     params = []
@@ -353,7 +387,8 @@ def run_reference(args, wl, name):
         kind = "port"
         sample = f"{nsteps} step(s) of batch {b} x {wl['n']} points after 1 warm-up"
         unit = "points/s"
-        metric = "train_step_points_per_sec" if wl["kind"] == "train" else "forward_points_per_sec"
+        metric = {"train": "train_step_points_per_sec", "predict": "predict_points_per_sec"}.get(
+            wl["kind"], "forward_points_per_sec")
         ms = 1e3 * b * wl["n"] / v
         cfg = dict(workload=name, n_points=wl["n"], k=wl["k"], global_batch=gb, layer_sizes=SETTINGS["layer_sizes"])
     line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps,
@@ -488,19 +523,36 @@ def main():
 
         h2d, d2h = 2 * batch * n * 12, batch * n * k * 12
     else:
-        st = modules.RandLANetSettings(**dict(SETTINGS, n_points=n, n_neighbors=k))
-        torch.manual_seed(0)
-        model = model_mod.Model(st, device=dev)
-        parallel.broadcast_parameters(model.module)
+        if wl["kind"] != "predict":
+            st = modules.RandLANetSettings(**dict(SETTINGS, n_points=n, n_neighbors=k))
+            torch.manual_seed(0)
+            model = model_mod.Model(st, device=dev)
+            parallel.broadcast_parameters(model.module)
         pool = 4
-        data = [syn.fingertip_batch(1000 * rank + j, batch, n, n_raw=max(150_000, 2 * n)) for j in range(pool)]
-        x_h = [torch.from_numpy(x).pin_memory() for x, _ in data]
-        y_h = [torch.from_numpy(y).pin_memory() for _, y in data]
-        x_d = [x.to(dev) for x in x_h]
-        y_d = [y.to(dev) for y in y_h]
+        if wl["kind"] != "predict":
+            data = [syn.fingertip_batch(1000 * rank + j, batch, n, n_raw=max(150_000, 2 * n)) for j in range(pool)]
+            x_h = [torch.from_numpy(x).pin_memory() for x, _ in data]
+            y_h = [torch.from_numpy(y).pin_memory() for _, y in data]
+            x_d = [x.to(dev) for x in x_h]
+            y_d = [y.to(dev) for y in y_h]
         units_per_step = batch * n
         unit = "points/s"
-        if wl["kind"] == "train":
+        if wl["kind"] == "predict":
+            metric = "predict_points_per_sec"
+            st = modules.RandLANetSettings(**dict(SETTINGS, n_points=2500, n_neighbors=k))
+            torch.manual_seed(0)
+            model = model_mod.Model(st, device=dev)
+            frames = [syn.fingertip_cloud(np.random.RandomState(100 * rank + j), n)[0] for j in range(pool)]
+            x_d = [torch.from_numpy(f[None]).to(dev) for f in frames]
+
+            def dev_step(i):
+                model.predict_device(x_d[i % pool])
+
+            def e2e_step(i):
+                model.predict(frames[i % pool])          # numpy in, numpy out: H2D, forward, up-sampling, D2H
+
+            h2d, d2h = n * 12, n * 2 * 4
+        elif wl["kind"] == "train":
             metric = "train_step_points_per_sec"
             opt = model.make_optimizer(1e-2, capturable=not args.no_graph)
             flat = parallel.FlatGradients(model.module) if world > 1 else None

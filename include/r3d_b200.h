@@ -266,6 +266,13 @@ int r3d_tversky_loss_fwd(const float* logits, long long sb, long long sc, long l
 int r3d_tversky_loss_bwd(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
                          int C, int N, const float* coef, const float* gout, float* dlogits, r3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------ training metrics
+ * randlanet/utils/metrics.py:8-59 (accuracy, iou) per batch, trainer.py:121-131: counts (C,C) int64 +=
+ * [label][prediction] with prediction = arg max over classes (lowest index on ties); overall / per-class accuracy and
+ * IoU follow on the host from the matrix.  One launch, no host synchronisation; logits strided like the loss; C <= 16. */
+int r3d_confusion_counts(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
+                         int C, int N, long long* counts, r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,

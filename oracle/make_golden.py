@@ -217,7 +217,9 @@ def gen_predict(rmod):
         p = Path(tmp) / "ckpt"
         model.save(p)
         data = p.read_bytes()
-    # too large for a fixture in full (5.3 MB of weights): keep only the config + key list
+    # the archive itself (written by the reference's Model.save, 5 MB): the product's Model.load must read it as is
+    with open(os.path.join(GOLD, "ref_checkpoint.zip"), "wb") as f:
+        f.write(data)
     import zipfile, io, json
     z = zipfile.ZipFile(io.BytesIO(data))
     out["ckpt_config_json"] = np.frombuffer(z.read("config"), dtype=np.uint8)
@@ -233,12 +235,18 @@ def gen_loss():
     (trainer.py:245-269) on seeded logits: loss value and d loss / d logits; also pins oracle.network.dice_loss."""
     import_reference()
     from randlanet.utils.losses import FocalTverskyLoss
+    from randlanet.utils.metrics import accuracy, iou
     out = {}
     rng = np.random.RandomState(77)
     for cname, (B, C, N) in {"b2c2n300": (2, 2, 300), "b3c3n257": (3, 3, 257), "b1c5n64": (1, 5, 64)}.items():
         logits = (rng.randn(B, C, N) * 2.0).astype(np.float32)
         labels = rng.randint(0, C, (B, N)).astype(np.int64)
         out[f"{cname}/logits"], out[f"{cname}/labels"] = logits, labels
+        # metrics.py:8-59 on the same batch (also with a class that never occurs: labels capped at C - 2)
+        for tag, lab in (("", labels), ("absent/", np.minimum(labels, max(C - 2, 0)))):
+            oa, pca = accuracy(torch.from_numpy(logits), torch.from_numpy(lab))
+            miou, pci = iou(torch.from_numpy(logits), torch.from_numpy(lab))
+            out[f"{cname}/{tag}metrics"] = np.array([oa, miou] + list(pca) + list(pci), dtype=np.float64)
         for name, (alpha, gamma) in LOSS_PARAMS.items():
             x = torch.from_numpy(logits).requires_grad_(True)
             loss = FocalTverskyLoss(alpha=alpha, gamma=gamma, neglect_background=True)(x, torch.from_numpy(labels))

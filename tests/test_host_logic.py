@@ -297,3 +297,23 @@ def test_bench_line_is_short_and_round_trips():
     assert {"value", "unit", "cores", "kind"} <= set(d["cpu_baseline"])
     assert "kernels" not in d and len(side["kernels"]) == 240 and side["roofline"]["shapes"]
     assert json.loads(json.dumps(side))["extras"] == {"a": 1}
+
+
+def test_reference_written_checkpoint_matches_the_schema():
+    """tests/golden/ref_checkpoint.zip (written by the reference's Model.save): archive members, config keys and every
+    tensor name / shape / dtype equal the schema the product's RandLANet builds (no GPU needed)."""
+    import io
+    import json
+    import zipfile
+    from oracle import network as onet
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+    with zipfile.ZipFile(os.path.join(GOLDEN, "ref_checkpoint.zip")) as z:
+        assert sorted(z.namelist()) == ["config", "model"]
+        config = json.loads(z.read("config"))
+        sd = torch.load(io.BytesIO(z.read("model")), map_location="cpu")
+    st = modules.RandLANetSettings(**config)
+    assert st.n_points == 2500 and st.n_neighbors == 32 and st.layer_sizes == [16, 64, 128, 256]
+    schema = onet.state_dict_schema(config)
+    assert list(sd) == list(schema)
+    for k, (shape, dtype) in schema.items():
+        assert tuple(sd[k].shape) == shape and sd[k].dtype == dtype, k
