@@ -60,6 +60,9 @@ _SIDE_STREAMS = {}
 OVERLAP_WEIGHT_GRADS = os.environ.get("R3D_NO_OVERLAP") is None
 
 
+SERIALIZE_FORKS = False      # bench.py's instrumented pass: every fork runs inline, so per-kernel events time one kernel
+
+
 class _fork:
     """Runs the enclosed launches on a side stream of the current device, ordered after everything queued on the
     current stream so far; ``join()`` makes the current stream wait for them.  The per-point layers of a small cloud
@@ -79,17 +82,22 @@ class _fork:
         self.ctx = None
 
     def __enter__(self):
+        self.inline = SERIALIZE_FORKS
+        if self.inline:
+            return self
         self.side.wait_stream(self.cur)
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
         return self
 
     def __exit__(self, *exc):
-        self.ctx.__exit__(*exc)
+        if not self.inline:
+            self.ctx.__exit__(*exc)
         return False
 
     def join(self):
-        self.cur.wait_stream(self.side)
+        if not self.inline:
+            self.cur.wait_stream(self.side)
 
 
 def _once(ctx, what: str) -> None:

@@ -5,7 +5,7 @@ ReLU / LeakyReLU kink, and two correct fp32 evaluations may take different branc
 explains why the other gradient tests set a few outliers aside or repeat a step).  This test removes the ambiguity
 instead of tolerating it:
 
-  1. an fp64 run of the oracle enumerates the AMBIGUOUS elements: |pre-activation| <= 2e-6 x rms of its tensor
+  1. an fp64 run of the oracle enumerates the AMBIGUOUS elements: |pre-activation| <= 4e-6 x rms of its tensor
      (fp32 evaluations of this network differ by ~1e-6 relative; nothing farther from the kink can flip), with their
      exact branches.  Every fp32 oracle run below pins ALL of them (the port's own threaded reductions are not
      bit-reproducible, so an unpinned run may itself flip one of them);
@@ -27,7 +27,7 @@ from test_forward_gpu import make_input
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-BAND = 2e-6
+BAND = 4e-6
 
 
 def _pins(candidates, state):
@@ -106,13 +106,13 @@ def _fit_branches(A: torch.Tensor, d: torch.Tensor):
     return on
 
 
-@pytest.mark.parametrize("N,B,seed", [(1024, 2, 11), (2500, 2, 12), (16384, 1, 41)])
-def test_every_gradient_entry_with_pinned_branches(N, B, seed):
+@pytest.mark.parametrize("N,B,seed,extra", [(1024, 2, 11, {}), (2500, 2, 12, {}), (16384, 1, 41, {})])
+def test_every_gradient_entry_with_pinned_branches(N, B, seed, extra):
     modules = importlib.import_module("3d_recognizer_b200.modules")
-    st = dict(n_classes=2, n_points=N, n_features=0, n_neighbors=16, knn="kdtree")
+    st = dict(dict(n_classes=2, n_points=N, n_features=0, n_neighbors=16, knn="kdtree"), **extra)
     sd = onet.synth_state_dict(st, seed)
-    x = torch.from_numpy(make_input(B, N, 0, seed))
-    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, 2, (B, N)))
+    x = torch.from_numpy(make_input(B, N, st["n_features"], seed))
+    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, st["n_classes"], (B, N)))
 
     # 1. ambiguous elements and their exact branches, from fp64 pre-activations
     _, _, _, k64 = _oracle_step(sd, st, x, labels, 78, dtype=torch.float64, threshold=BAND)
@@ -159,9 +159,18 @@ def test_every_gradient_entry_with_pinned_branches(N, B, seed):
                 break
     pinned = [c for c, a, b in zip(candidates, state, exact) if a != b]
     worst = float(d.abs().max())
+    if worst >= TOL:                                  # name the tensors for the failure message
+        off, bad = 0, []
+        for name in ref:
+            n = ref[name].numel()
+            w = float(d[off:off + n].abs().max())
+            if w >= TOL:
+                bad.append((name, round(w, 6), int((d[off:off + n].abs() >= TOL).sum())))
+            off += n
+        print("tensors beyond tolerance:", bad)
     assert worst < TOL, (f"{int((d.abs() >= TOL).sum())} of {d.numel()} gradient entries beyond 1e-4 (worst {worst:.2e}) "
                          f"with {len(pinned)} of {len(candidates)} ambiguous branches off their exact side")
     assert float((logits - ref_logits).abs().max() / ref_logits.abs().max()) < TOL
     assert abs(loss - float(ref_loss)) < 1e-5
-    print(f"N={N}: {d.numel()} gradient entries within {worst:.1e}; {len(pinned)} of {len(candidates)} ambiguous "
+    print(f"N={N} K={st['n_neighbors']}: {d.numel()} gradient entries within {worst:.1e}; {len(pinned)} of {len(candidates)} ambiguous "
           "branches off their exact side")
