@@ -71,7 +71,8 @@ struct LfaClBwdSmem {
     static constexpr int OFF_GROUPS = OFF_W2 + (HAS_W2 ? 2 * kClW2Bytes : 0);
     static constexpr int GROUP_BYTES = (HAS_DS ? 4 : 2) * C::OP_BYTES + C::RINFO_FLOATS * 4;
     static constexpr int OFF_BARS = OFF_GROUPS + NG * GROUP_BYTES;
-    static constexpr size_t BYTES = (size_t)OFF_BARS + 2 * NG * 8 + 16 + 34 * 4 + 16;
+    static constexpr int OFF_EXTRA = OFF_BARS + 2 * NG * 8 + 16 + 34 * 4 + 16;      // MODE 4: centre[64] f32, S'[64] f64, n[8] f64
+    static constexpr size_t BYTES = (size_t)OFF_EXTRA + (MODE == 4 ? 64 * 4 + 64 * 8 + 8 * 8 : 0);
     // TMEM columns: per group a working accumulator (R) and a first-level sum accumulator (ACC1), one shared second level
     static constexpr int ACC1 = MODE <= 2 ? 128 : 64;
     static constexpr int COL_ACC2 = NG * (C::R + ACC1);
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + NG);
     int* lock = reinterpret_cast<int*>(tmem_slot + 1);
     float* red = reinterpret_cast<float*>(tmem_slot + 4);
+    float* centre = reinterpret_cast<float*>(smem + S::OFF_EXTRA);            // MODE 4: per virtual r lane
+    double* csum = reinterpret_cast<double*>(smem + S::OFF_EXTRA + 64 * 4);   //         sum of centred r1 per lane
+    double* cnum = csum + 64;                                                 //         valid rows per sub-tile
 
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -115,6 +119,12 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
         }
         *lock = 0;
         mbar_fence_init();
+    }
+    if (MODE == 4 && tid < 64) {
+        if (tid < 8) red[tid] = 0.f;
+        centre[tid] = 0.f;
+        csum[tid] = 0.0;
+        if (tid < 8) cnum[tid] = 0.0;
     }
     if (warp == NG * 4) tmem_alloc_warp(tmem_slot, S::TMEM_COLS);
     float sw = 1.f, sw2 = 1.f;
@@ -255,6 +265,40 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
         named_bar_sync(15, NG * kClLanes);
         tc_fence_after_sync();
 
+        // MODE 4: the moments are taken of CENTRED values r1 - c (c = this CTA's estimate of the channel mean from its
+        // first tile) and converted back in fp64 at the end: M = M' + c S'^T + S' c^T + n c c^T.  The tensor core's
+        // accumulate truncation is a systematic relative bias of the accumulated matrix; on raw second moments it is
+        // amplified by E[z^2] / var(z) in the BatchNorm variance that is formed from them, on centred ones it is not.
+        float cme = 0.f;
+        double nvalid = 0.0;
+        if (MODE == 4) {
+            if (g == 0 && (long long)blockIdx.x < a.ntiles) {
+                cl_row_info<D, K>(rinfo, a.xyz, a.xyz_bstride, a.idx, a.feat_bstride, a.dfeat_bstride, a.N, a.npts,
+                                  (long long)blockIdx.x, l);
+                named_bar_sync(1, kClLanes);
+                float sum = 0.f, cnt = 0.f;
+                for (int j = 0; j < 32; ++j) {
+                    const float4* q = reinterpret_cast<const float4*>(ri + (hh * 32 + j) * kClRinfo);
+                    const float4 q2 = q[2];
+                    if (__float_as_uint(q2.w) != 0xffffffffu) {
+                        sum += cl_mlp1(w1, a1s, b1s, q[0], q[1], q2);
+                        cnt += 1.f;
+                    }
+                }
+                atomicAdd(&centre[lr], sum);                    // both row halves of the lane
+                if (rc == 0) atomicAdd(&red[ln.sub], cnt);      // rows of the sub-tile (red[0..7] is free by now)
+            }
+            if (g == 0) {
+                named_bar_sync(1, kClLanes);
+                if (l < 64) {
+                    const float n = red[l / H];
+                    centre[l] = n > 0.f ? centre[l] / n : 0.f;  // still scaled by sx, like the operand values
+                }
+            }
+            named_bar_sync(15, NG * kClLanes);
+            cme = centre[lr];
+        }
+
         auto fold = [&]() {
             // acc2 += acc1 under the CTA lock (all 128 lanes of the group; its MMAs have completed)
             if (l == 0) {
@@ -307,10 +351,15 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                         const float4* q = reinterpret_cast<const float4*>(ri + (ng * 8 + j) * kClRinfo);
                         const float4 q2 = q[2];
                         v[j] = cl_mlp1(w1, a1s, b1s, q[0], q[1], q2);
-                        if (MODE == 4 && __float_as_uint(q2.w) == 0xffffffffu) v[j] = 0.f;     // padding rows count for nothing
+                        if (MODE == 4) {
+                            const bool valid = __float_as_uint(q2.w) != 0xffffffffu;
+                            v[j] = valid ? v[j] - cme : 0.f;                  // centred; padding rows count for nothing
+                            nvalid += valid ? 1.0 : 0.0;
+                        }
                         rs += v[j];
                     }
-                    amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                    amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                                             fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7])))));
                     cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
                 }
                 if (MODE == 4) gacc[10] += (double)(rs * inv_sx);
@@ -613,7 +662,9 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
             for (int o = 16; o > 0; o >>= 1) du2max = fmaxf(du2max, __shfl_xor_sync(0xffffffffu, du2max, o));
             if ((l & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(a.scal + 1), __float_as_uint(du2max));
         } else {
-            atomicAdd(a.s_r1 + rc * 16 + 10, gacc[10]);
+            // centred sums of this CTA per virtual lane, valid rows per sub-tile (shared-memory fp64 atomics: a few hundred)
+            atomicAdd(&csum[lr], gacc[10]);
+            if (rc == 0) atomicAdd(&cnum[ln.sub], nvalid);
         }
 
         // ---- second-level accumulator -> global (group 0, after every group's last fold)
@@ -639,6 +690,10 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
             } else if (ln.part == 0) {
                 const float unscale = (MODE == 3) ? 1.0f / (sg * kClSx) : 1.0f / (kClSx * kClSx);
                 double* out = (MODE == 3 ? a.dw2 : a.m_r1) + (size_t)rc * H;
+                // MODE 4: back from centred to raw moments in fp64 (values below are true-scale: centre and sums / sx)
+                const double ci = (MODE == 4) ? (double)centre[l] / kClSx : 0.0, si = (MODE == 4) ? csum[l] : 0.0;
+                const double nsub = (MODE == 4) ? cnum[ln.sub] : 0.0;
+                if (MODE == 4) atomicAdd(a.s_r1 + rc * 16 + 10, si + nsub * ci);
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 16) {
                     uint32_t u[16];
@@ -646,7 +701,14 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if ((c0 + j) / H == ln.sub) atomicAdd(out + (c0 + j) % H, (double)(__uint_as_float(u[j]) * unscale));
+                        if ((c0 + j) / H == ln.sub) {
+                            double v = (double)(__uint_as_float(u[j]) * unscale);
+                            if (MODE == 4) {
+                                const double cj = (double)centre[c0 + j] / kClSx, sj = csum[c0 + j];
+                                v += ci * sj + si * cj + nsub * ci * cj;
+                            }
+                            atomicAdd(out + (c0 + j) % H, v);
+                        }
                 }
             }
         }

@@ -185,10 +185,10 @@ def _rows_view(x: torch.Tensor):
 USE_TENSOR_CORES = True
 TC_WIDTHS, TC_NEIGHBORS = (64, 128, 256), (16, 32)     # forward: widths where the tensor-core kernel is the faster one
 TC_BWD_WIDTHS = (64, 128, 256)                         # backward (d = 256: stage-1 backward and pass 1 of stage 2)
-# r1 moments on the tensor cores: built and tested (1e-5 relative), but OFF — the moments feed BatchNorm statistics
-# (var = E[z^2] - E[z]^2 cancels), and the systematic accumulate-truncation bias of the tensor core (~1e-6) shows up as
-# 1e-4-level deviations in the encoding-MLP gradients (tests/test_kink_pinned_gpu.py, K = 32 case)
-TC_MOM_WIDTHS = ()
+# r1 moments on the tensor cores, taken of CENTRED values and converted back in fp64 (csrc/lfa_cl_bwd.cu MODE 4): the
+# moments feed BatchNorm statistics (var = E[z^2] - E[z]^2 cancels), where the tensor core's systematic accumulate
+# truncation on raw second moments showed up as 1e-4-level deviations in the encoding-MLP gradients
+TC_MOM_WIDTHS = (16, 64, 128)
 TC_ALL_WIDTHS = (16, 32, 64, 128, 256)                 # what the kernels are built for (tests run all of them)
 if os.environ.get("R3D_TC_WIDTHS"):                   # tuning override: "fwd widths;bwd widths", e.g. "64,128;16,64,128"
     _f, _, _b = os.environ["R3D_TC_WIDTHS"].partition(";")
