@@ -456,24 +456,28 @@ __global__ void __launch_bounds__(128) lfa_r1_rows_kernel(const float* __restric
     }
 }
 
-// du2 (layout of r3d_lfa_bn2_bwd: [b][tile][h][P*K], P points per tile) = part[0] + part[1], part [half][row][h]
+// du2 (layout of r3d_lfa_bn2_bwd: [b][tile][h][P*K], P points per tile) = part[0] + part[1], part [half][row][h].
+// One CTA per (cloud, tile): its P*K rows are read row by row (coalesced along the channels), summed, transposed
+// through shared memory and written channel by channel (coalesced along the rows).
 __global__ void __launch_bounds__(256) lfa_du2_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int B,
                                                               int N, int K, int h, int P, long long rows) {
+    extern __shared__ float tile[];                    // [P*K][h + 1]
     const int T = (N + P - 1) / P;
-    const long long total = (long long)B * T * h * P * K;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const int p = (int)((i / K) % P);
-        const int c = (int)((i / ((long long)K * P)) % h);
-        const long long bt = i / ((long long)K * P * h);
-        const int tile = (int)(bt % T), b = (int)(bt / T);
-        const int n = tile * P + p;
+    const int b = blockIdx.x / T, t = blockIdx.x % T;
+    const int PK = P * K, ld = h + 1;
+    const long long row0 = ((long long)b * N + (long long)t * P) * K;
+    const int nrows = min(PK, (N - t * P) * K);        // rows of this tile that exist
+    for (int i = threadIdx.x; i < PK * h; i += 256) {
+        const int r = i / h, c = i % h;
         float v = 0.f;
-        if (n < N) {
-            const long long row = ((long long)b * N + n) * K + k;
-            v = part[row * h + c] + part[(rows + row) * h + c];
-        }
-        out[i] = v;
+        if (r < nrows) v = part[(row0 + r) * h + c] + part[(rows + row0 + r) * h + c];
+        tile[r * ld + c] = v;
+    }
+    __syncthreads();
+    float* o = out + (size_t)blockIdx.x * h * PK;
+    for (int i = threadIdx.x; i < PK * h; i += 256) {
+        const int c = i / PK, r = i % PK;
+        o[i] = tile[r * ld + c];
     }
 }
 
@@ -500,8 +504,12 @@ extern "C" int r3d_lfa_du2_combine(const float* part, float* out, int B, int N, 
     if (B < 0 || N < 0 || K <= 0 || h <= 0 || tile_points <= 0) return R3D_EINVAL;
     if (B == 0 || N == 0) return R3D_OK;
     if (!part || !out) return R3D_EINVAL;
-    lfa_du2_combine_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(part, out, B, N, K, h, tile_points,
-                                                                                      (long long)B * N * K);
+    const int T = (N + tile_points - 1) / tile_points;
+    const size_t smem = (size_t)tile_points * K * (h + 1) * sizeof(float);
+    if (smem > 200 * 1024) return R3D_EUNSUPPORTED;
+    R3D_CUDA_TRY(cudaFuncSetAttribute(lfa_du2_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lfa_du2_combine_kernel<<<(unsigned)(B * T), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        part, out, B, N, K, h, tile_points, (long long)B * N * K);
     R3D_LAUNCH_CHECK("lfa_du2_combine_kernel");
     return R3D_OK;
 }

@@ -410,6 +410,107 @@ __global__ void __launch_bounds__(256) rowreduce_gemm_big_kernel(const float* __
         }
 }
 
+// Narrow variant (both channel counts <= 64 and multiples of 4, at least one of them <= 32): the 64 x 64 tile of the
+// kernel above would spend 4-16x its FMAs and half its load slots on padding.  Here the output tile is TA x TB, a
+// thread still owns a 4 x 4 block, and the 256 threads form NS = 256 / ((TA/4)(TB/4)) row SLICES: slice s takes rows
+// s, s + NS, ... of every 64-row chunk.  Chunks are double-buffered in shared memory by float4 loads that carry no
+// padding; the slices are summed through shared memory at the end (one atomic per element and CTA).  HBM-streaming:
+// 2.6 M rows of a 16 x 16 layer in ~0.1 ms instead of 0.57 ms.
+constexpr int kRrNarrowRows = 64;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) rowreduce_gemm_narrow_kernel(const float* __restrict__ A, int Ca,
+                                                                    const float* __restrict__ Bm, int Cb, long long M,
+                                                                    long long rows_per_cta, float* __restrict__ out,
+                                                                    int ld_out) {
+    constexpr int NTT = (TA / 4) * (TB / 4);          // threads per row slice
+    constexpr int NS = 256 / NTT;                     // row slices
+    constexpr int FA = TA / 4, FB = TB / 4;           // float4 per row
+    constexpr int ROWS = (FA + FB > 16) ? kRrNarrowRows / 2 : kRrNarrowRows;   // rows per chunk (48 KB static limit)
+    constexpr int F4 = ROWS * (FA + FB);              // float4 per chunk
+    constexpr int LPT = (F4 + 255) / 256;             // loads per thread and chunk
+    __shared__ __align__(16) float4 buf[2][F4];       // [row][FA | FB]
+    __shared__ float red[TA * TB];
+    const int tid = threadIdx.x;
+    const int slice = tid / NTT, tt = tid % NTT;
+    const int ta = tt / FB, tb = tt % FB;
+    const long long r_lo = (long long)blockIdx.x * rows_per_cta;
+    const long long r_hi = min(M, r_lo + rows_per_cta);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 rg[LPT];
+    auto load = [&](long long r0) {
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const int i = tid + k * 256;
+            const int row = i / (FA + FB), c = i % (FA + FB);
+            const long long r = r0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < F4 && r < r_hi) {
+                if (c < FA) {
+                    if (c * 4 < Ca) v = *reinterpret_cast<const float4*>(A + r * Ca + c * 4);
+                } else if ((c - FA) * 4 < Cb) {
+                    v = *reinterpret_cast<const float4*>(Bm + r * Cb + (c - FA) * 4);
+                }
+            }
+            rg[k] = v;
+        }
+    };
+    auto store = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const int i = tid + k * 256;
+            if (i < F4) buf[b][i] = rg[k];
+        }
+    };
+    for (int i = tid; i < TA * TB; i += 256) red[i] = 0.f;
+    load(r_lo);
+    store(0);
+    __syncthreads();
+    int b = 0;
+    for (long long r0 = r_lo; r0 < r_hi; r0 += ROWS, b ^= 1) {
+        const bool more = r0 + ROWS < r_hi;
+        if (more) load(r0 + ROWS);
+#pragma unroll
+        for (int k = slice; k < ROWS; k += NS) {
+            const float4 av = buf[b][k * (FA + FB) + ta];
+            const float4 bv = buf[b][k * (FA + FB) + FA + tb];
+            const float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+        }
+        if (more) store(b ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&red[(ta * 4 + i) * TB + tb * 4 + j], acc[i][j]);
+    __syncthreads();
+    for (int i = tid; i < TA * TB; i += 256) {
+        const int ca = i / TB, cb = i % TB;
+        if (ca < Ca && cb < Cb) atomicAdd(out + (size_t)ca * ld_out + cb, red[i]);
+    }
+}
+
+template <int TA, int TB>
+static void launch_rr_narrow(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
+                             cudaStream_t st) {
+    long long ctas = (long long)kNumSMs * 4;
+    const long long max_ctas = (M + 4 * kRrNarrowRows - 1) / (4 * kRrNarrowRows);     // at least 256 rows per CTA
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    long long rows_per_cta = (M + ctas - 1) / ctas;
+    rows_per_cta = (rows_per_cta + kRrNarrowRows - 1) / kRrNarrowRows * kRrNarrowRows;
+    ctas = (M + rows_per_cta - 1) / rows_per_cta;
+    rowreduce_gemm_narrow_kernel<TA, TB><<<(unsigned)ctas, 256, 0, st>>>(A, Ca, Bm, Cb, M, rows_per_cta, out, ld_out);
+}
+
 // Thin variant (one side <= 8 channels, the other <= 32: fc_start's 8x3, the class logits' 2x32): HBM-streaming.
 // A lane owns one channel of the wide side, loops over the narrow side; rows are strided over all warps of the grid;
 // one shared-memory reduction per CTA, then one atomic per element and CTA.
@@ -569,6 +670,20 @@ extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int C
         return R3D_OK;
     }
     const bool vec = (Ca % 4) == 0 && (Cb % 4) == 0 && is_aligned(A, 16) && is_aligned(Bm, 16);
+    if (vec && Ca <= 64 && Cb <= 64 && (Ca <= 32 || Cb <= 32) && M >= 4096) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int ta = Ca <= 16 ? 16 : (Ca <= 32 ? 32 : 64), tb = Cb <= 16 ? 16 : (Cb <= 32 ? 32 : 64);
+        if (ta == 16 && tb == 16) launch_rr_narrow<16, 16>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 16 && tb == 32) launch_rr_narrow<16, 32>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 32 && tb == 16) launch_rr_narrow<32, 16>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 32 && tb == 32) launch_rr_narrow<32, 32>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 16 && tb == 64) launch_rr_narrow<16, 64>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 64 && tb == 16) launch_rr_narrow<64, 16>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else if (ta == 32 && tb == 64) launch_rr_narrow<32, 64>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        else launch_rr_narrow<64, 32>(A, Ca, Bm, Cb, M, out, ld_out, st);
+        R3D_LAUNCH_CHECK("rowreduce_gemm_narrow_kernel");
+        return R3D_OK;
+    }
     const bool big = vec && Ca >= 128 && Cb >= 128;
     const int tile = big ? kRrBig : kRrTile;
     const int ga = ceil_div(Ca, tile), gb = ceil_div(Cb, tile);

@@ -243,3 +243,18 @@ def test_train_step_vs_reference_golden(mods, name):
             return
         history.append(fails)
     raise AssertionError(history)
+
+
+@pytest.mark.parametrize("M,Ca,Cb", [(100000, 16, 16), (50000, 32, 16), (8192, 16, 64), (70001, 64, 32), (4097, 12, 20),
+                                     (300000, 32, 32), (65536, 64, 16), (5000, 40, 24)])
+def test_rowreduce_gemm_narrow_tiles(mods, M, Ca, Cb):
+    """Weight-gradient row reduction A^T B for narrow layers (the level-0 layers of a large batch): the narrow-tile
+    kernel (row slices inside the CTA, no padding work) against an fp64 product."""
+    _, _, ops = mods
+    g = torch.Generator(device="cuda").manual_seed(M + Ca + Cb)
+    a = torch.randn(M, Ca, device="cuda", generator=g)
+    b = torch.randn(M, Cb, device="cuda", generator=g)
+    got = ops.rowreduce_gemm(a, b)
+    ref = a.double().t() @ b.double()
+    assert got.shape == (Ca, Cb)
+    assert rel_err(got.double(), ref) < 2e-5
