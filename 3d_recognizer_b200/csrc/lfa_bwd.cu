@@ -477,6 +477,68 @@ __global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : (FINE ? 2 : 
     }
 }
 
+
+// Moments of the position encoding (r3d_lfa_moments mode 0) as an HBM-streaming kernel: they depend on the coordinates
+// and the neighbour lists only, any width.  A thread walks rows with the grid stride, accumulates the 66 distinct
+// products of e = [rpe(10), 1] over at most 16 rows in fp32, then the warp reduces them in fp64 and adds them to the
+// CTA's fp64 shared-memory matrix; one global fp64 atomic per entry and CTA at the end.  (The tile kernel above rebuilt
+// a channel-major shared-memory tile and ran a 16 x 16 reduce_gemm over it: 2.0 ms for 42 M rows; this: ~0.3 ms.)
+__global__ void __launch_bounds__(256) lfa_rpe_moments_kernel(const float* __restrict__ xyz, long long xyz_bstride,
+                                                              const int32_t* __restrict__ idx, double* __restrict__ m_rpe,
+                                                              int N, int K, long long rows) {
+    __shared__ double acc64[66];
+    if (threadIdx.x < 66) acc64[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // every thread of a warp runs the same number of batches (the warp reduction below is collective)
+    const long long warp_first = row - lane;
+    for (long long base = warp_first; base < rows; base += 16 * stride) {
+        float p[66];
+#pragma unroll
+        for (int i = 0; i < 66; ++i) p[i] = 0.f;
+        for (int it = 0; it < 16; ++it) {
+            const long long r = base + lane + (long long)it * stride;
+            if (r < rows) {
+                const long long gp = r / K;
+                const int b = (int)(gp / N), pi = (int)(gp - (long long)b * N);
+                float e[11];
+                float rpe[10];
+                rpe_of_row(xyz + (size_t)b * xyz_bstride, pi, idx[r], rpe);
+#pragma unroll
+                for (int q = 0; q < 10; ++q) e[q] = rpe[q];
+                e[10] = 1.f;
+                int o = 0;
+#pragma unroll
+                for (int i = 0; i < 11; ++i)
+#pragma unroll
+                    for (int j = i; j < 11; ++j) p[o] = fmaf(e[i], e[j], p[o]), ++o;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 66; ++i) {
+            double v = (double)p[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == (i & 31)) atomicAdd(&acc64[i], v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 66) {
+        // entry t of the upper triangle -> (i, j), i <= j
+        int t = threadIdx.x, i = 0;
+        while (t >= 11 - i) {
+            t -= 11 - i;
+            ++i;
+        }
+        const int j = i + t;
+        const double v = acc64[threadIdx.x];
+        atomicAdd(m_rpe + i * kRpeRows + j, v);
+        if (i != j) atomicAdd(m_rpe + j * kRpeRows + i, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------- launchers
 template <int D, int K, int NT, int STAGE, int FINE = 0>
 static int launch_bwd(const LfaBwdArgs& a, cudaStream_t st) {
@@ -656,7 +718,14 @@ extern "C" int r3d_lfa_moments(int mode, const float* xyz, long long xyz_bstride
     LfaMomArgs a{xyz, xyz_bstride, idx, w_rpe1, a_rpe1, b_rpe1, m_rpe, m_r1, s_r1, gsym, gsum, g1,
                  nullptr, nullptr, nullptr, nullptr, nullptr, B, N};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mode == 0) return dispatch_mom<0>(d, K, a, st);
+    if (mode == 0) {
+        const long long rows = (long long)B * N * K;
+        long long blocks = (rows + 256 * 16 - 1) / (256 * 16);
+        if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+        lfa_rpe_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(xyz, xyz_bstride, idx, m_rpe, N, K, rows);
+        R3D_LAUNCH_CHECK("lfa_rpe_moments_kernel");
+        return R3D_OK;
+    }
     if (mode == 1) return dispatch_mom<1>(d, K, a, st);
     return dispatch_mom<2>(d, K, a, st);
 }

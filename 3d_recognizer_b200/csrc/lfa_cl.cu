@@ -169,15 +169,16 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_fwd_kernel(LfaClA
                 float fv[32];
                 const float* fb = a.feat + rc;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) fv[j] = fb[__float_as_uint(ri[(hh * 32 + j) * kClRinfo + 10])];
+                for (int j = 0; j < 32; ++j) fv[j] = fb[cl_feat_off(ri, hh * 32 + j)];
 #pragma unroll 1
                 for (int u = 0; u < 4; ++u) {
                     const int ng = hh * 4 + u;
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4* q = reinterpret_cast<const float4*>(ri + (ng * 8 + j) * kClRinfo);
-                        v[j] = cl_mlp1(w1, a1s, b1s, q[0], q[1], q[2]);
+                        float4 q0, q1, q2;
+                        cl_rpe_row<D, K>(ri, ng * 8 + j, q0, q1, q2);
+                        v[j] = cl_mlp1(w1, a1s, b1s, q0, q1, q2);
                     }
                     amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
                     cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
@@ -317,8 +318,8 @@ extern "C" int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstrid
         a.ntiles = (a.npts + ClCfg<DD, KK>::TPTS - 1) / ClCfg<DD, KK>::TPTS;                \
         return stage == 1 ? launch_cl_fwd<DD, KK, 1, NG1>(a, st) : launch_cl_fwd<DD, KK, 2, NG2>(a, st); \
     }
-    R3D_CL_CASE(128, 16, 4, 4) R3D_CL_CASE(64, 16, 4, 3) R3D_CL_CASE(32, 16, 3, 2) R3D_CL_CASE(16, 16, 2, 2)
-    R3D_CL_CASE(128, 32, 4, 4) R3D_CL_CASE(64, 32, 4, 3) R3D_CL_CASE(32, 32, 3, 2) R3D_CL_CASE(16, 32, 2, 2)
+    R3D_CL_CASE(128, 16, 4, 4) R3D_CL_CASE(64, 16, 4, 4) R3D_CL_CASE(32, 16, 4, 3) R3D_CL_CASE(16, 16, 3, 3)
+    R3D_CL_CASE(128, 32, 4, 4) R3D_CL_CASE(64, 32, 4, 4) R3D_CL_CASE(32, 32, 4, 3) R3D_CL_CASE(16, 32, 3, 3)
 #undef R3D_CL_CASE
     return R3D_EUNSUPPORTED;
 }

@@ -65,7 +65,11 @@ template <int D, int K, int MODE, int NG>
 struct LfaClBwdSmem {
     using C = ClCfg<D, K>;
     static constexpr bool HAS_W = MODE <= 2;
-    static constexpr bool HAS_W2 = MODE == 2 || MODE == 3;
+    // mlp_rpe2 inside pass 1 (MODE 2): an MMA against the W2 image for d >= 64; for the narrow levels (h <= 16) the
+    // h x h product runs on the CUDA cores from an fp32 staging copy of r1 (no image, no extra MMA round, and the
+    // shared memory it saves is what lets two worker groups fit at d = 16)
+    static constexpr bool U2_MMA = (MODE == 2 && D > 32) || MODE == 3;
+    static constexpr bool HAS_W2 = U2_MMA;
     static constexpr bool HAS_DS = MODE <= 3;
     static constexpr int OFF_W2 = HAS_W ? 2 * C::W_BYTES : 0;
     static constexpr int OFF_GROUPS = OFF_W2 + (HAS_W2 ? 2 * kClW2Bytes : 0);
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
     if (warp == NG * 4) {
         // ============================================================ MMA issuer
         if ((tid & 31) == 0) {
-            constexpr int NR = (MODE == 1) ? 2 : (MODE == 2 ? 3 : (MODE == 3 ? 2 : 1));     // MMA rounds per tile
+            constexpr int NR = (MODE == 1) ? 2 : (MODE == 2 ? (S::U2_MMA ? 3 : 2) : (MODE == 3 ? 2 : 1));     // MMA rounds per tile
             int left[NG], step[NG];
             uint32_t ph[NG];
             int total = 0;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                         const bool fresh = (tile_no % kClFlush) == 0;                          // first tile after a fold
                         const uint32_t w2h = smem_u32(W2hi), w2l = smem_u32(W2lo);
                         if (MODE == 1 || MODE == 2) {
-                            if (MODE == 2 && round == 0) {
+                            if (MODE == 2 && S::U2_MMA && round == 0) {
                                 cl_mma_3x(acc, w2h, w2l, kClW2Is, 128, xhi, xlo, C::OP_CS, 128, id_fwd, 4, false);      // U2
                             } else if (round == NR - 2) {
                                 cl_mma_3x(acc, smem_u32(Whi), smem_u32(Wlo), C::W_IS, 128, xhi, xlo, C::OP_CS, 128, id_fwd, 8,
@@ -228,9 +232,14 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
         for (int q = 0; q < 10; ++q) w1[q] = a.w_rpe1[rc * 10 + q];
         const float a1s = a.a_rpe1[rc] * kClSx, b1s = a.b_rpe1[rc] * kClSx;
         float a2s = 0.f, b2s = 0.f;
+        float w2r[S::U2_MMA ? 1 : H];                 // CUDA-core mlp_rpe2 (narrow levels): this channel's weight row
         if (MODE == 2) {
-            a2s = a.a_rpe2[rc] / sw2;
+            a2s = S::U2_MMA ? a.a_rpe2[rc] / sw2 : a.a_rpe2[rc];     // staging holds r1 * sx, so does the result
             b2s = a.b_rpe2[rc] * kClSx;
+            if (!S::U2_MMA) {
+#pragma unroll
+                for (int i = 0; i < H; ++i) w2r[i] = a.w_rpe2[rc * H + i];
+            }
         }
         float bn_a2 = 0.f, bn_mean = 0.f, bn_rstd = 0.f, bn_m1 = 0.f, bn_m2 = 0.f;
         if (MODE == 3) {
@@ -278,10 +287,10 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                 named_bar_sync(1, kClLanes);
                 float sum = 0.f, cnt = 0.f;
                 for (int j = 0; j < 32; ++j) {
-                    const float4* q = reinterpret_cast<const float4*>(ri + (hh * 32 + j) * kClRinfo);
-                    const float4 q2 = q[2];
-                    if (__float_as_uint(q2.w) != 0xffffffffu) {
-                        sum += cl_mlp1(w1, a1s, b1s, q[0], q[1], q2);
+                    if (cl_grad_off(ri, hh * 32 + j) != 0xffffffffu) {
+                        float4 q0, q1, q2;
+                        cl_rpe_row<D, K>(ri, hh * 32 + j, q0, q1, q2);
+                        sum += cl_mlp1(w1, a1s, b1s, q0, q1, q2);
                         cnt += 1.f;
                     }
                 }
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                 if (MODE <= 2) {
                     const float* fb = a.feat + rc;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) fv[j] = fb[__float_as_uint(ri[(hh * 32 + j) * kClRinfo + 10])];
+                    for (int j = 0; j < 32; ++j) fv[j] = fb[cl_feat_off(ri, hh * 32 + j)];
                 }
                 float rs = 0.f;
 #pragma unroll 1
@@ -348,11 +357,11 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4* q = reinterpret_cast<const float4*>(ri + (ng * 8 + j) * kClRinfo);
-                        const float4 q2 = q[2];
-                        v[j] = cl_mlp1(w1, a1s, b1s, q[0], q[1], q2);
+                        float4 q0, q1, q2;
+                        cl_rpe_row<D, K>(ri, ng * 8 + j, q0, q1, q2);
+                        v[j] = cl_mlp1(w1, a1s, b1s, q0, q1, q2);
                         if (MODE == 4) {
-                            const bool valid = __float_as_uint(q2.w) != 0xffffffffu;
+                            const bool valid = cl_grad_off(ri, ng * 8 + j) != 0xffffffffu;
                             v[j] = valid ? v[j] - cme : 0.f;                  // centred; padding rows count for nothing
                             nvalid += valid ? 1.0 : 0.0;
                         }
@@ -360,7 +369,14 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     }
                     amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
                                              fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7])))));
-                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
+                    if (MODE == 2 && !S::U2_MMA) {
+                        // r1 (x sx) of this channel -> fp32 staging [sub][row][h] in the (still unused) dS planes
+                        float* stg = reinterpret_cast<float*>(Shi) + ((size_t)ln.sub * R + ng * 8) * H + rc;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) stg[j * H] = v[j];
+                    } else {
+                        cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
+                    }
                 }
                 if (MODE == 4) gacc[10] += (double)(rs * inv_sx);
                 if (MODE <= 2) {
@@ -376,12 +392,40 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     }
                 }
             }
+            if (MODE == 2 && !S::U2_MMA) {
+                // ---- B': r2 = relu(a2 (W2 r1) + c2) on the CUDA cores: every thread reads the h staged r1 values of
+                // its rows (broadcast among the lanes of a sub-tile) and writes its channel's units of X^T
+                named_bar_sync(1 + g, kClLanes);
+                const float* stg = reinterpret_cast<const float*>(Shi) + (size_t)ln.sub * R * H;
+#pragma unroll 1
+                for (int u = 0; u < 4; ++u) {
+                    const int ng = hh * 4 + u;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4* rr = reinterpret_cast<const float4*>(stg + (size_t)(ng * 8 + j) * H);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i4 = 0; i4 < H / 4; ++i4) {
+                            const float4 t = rr[i4];
+                            acc = fmaf(w2r[i4 * 4 + 0], t.x, acc);
+                            acc = fmaf(w2r[i4 * 4 + 1], t.y, acc);
+                            acc = fmaf(w2r[i4 * 4 + 2], t.z, acc);
+                            acc = fmaf(w2r[i4 * 4 + 3], t.w, acc);
+                        }
+                        v[j] = fmaxf(fmaf(acc, a2s, b2s), 0.f);
+                        amax = fmaxf(amax, v[j]);
+                    }
+                    cl_store_unit(Xhi, Xlo, cl_unit_off<D, K>(lr, ng), v);
+                }
+                named_bar_sync(1 + g, kClLanes);          // staging is read: the dS planes may be written again (epilogue C)
+            }
             fence_async_smem();
             tc_fence_before_sync();
             named_bar_sync(1 + g, kClLanes);
             if (l == 0) mbar_arrive(&full[g]);
 
-            if (MODE == 2) {
+            if (MODE == 2 && S::U2_MMA) {
                 // ---- B2: r2 = relu(a2 (W2 r1) + c2) over the r half of X^T (TMEM lanes 0..63 = warps 0, 1 of the group)
                 mbar_wait(&done[g], done_phase);
                 done_phase ^= 1u;
@@ -508,7 +552,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                         if (c0 + 16 < R) tmem_ld16_nowait(tacc + (uint32_t)(c0 + 16), un);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const uint32_t off = __float_as_uint(ri[(c0 + j) * kClRinfo + 11]);
+                            const uint32_t off = cl_grad_off(ri, c0 + j);
                             if (off != 0xffffffffu) red_add_f32(df + off, __uint_as_float(u[j]) * inv2);
                         }
                         if (c0 + 16 < R) tmem_ld_wait();
@@ -535,8 +579,8 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                             if (MODE == 1) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    const float4* q = reinterpret_cast<const float4*>(ri + (c0 + hlf * 8 + j) * kClRinfo);
-                                    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                                    float4 q0, q1, q2;
+                                    cl_rpe_row<D, K>(ri, c0 + hlf * 8 + j, q0, q1, q2);
                                     part[0] = fmaf(du[j], q0.x, part[0]); part[1] = fmaf(du[j], q0.y, part[1]);
                                     part[2] = fmaf(du[j], q0.z, part[2]); part[3] = fmaf(du[j], q0.w, part[3]);
                                     part[4] = fmaf(du[j], q1.x, part[4]); part[5] = fmaf(du[j], q1.y, part[5]);
@@ -585,7 +629,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float zh = (__uint_as_float(u[hlf * 8 + j]) * iu - bn_mean) * bn_rstd;
-                                const bool valid = __float_as_uint(ri[(c0 + hlf * 8 + j) * kClRinfo + 11]) != 0xffffffffu;
+                                const bool valid = cl_grad_off(ri, c0 + hlf * 8 + j) != 0xffffffffu;
                                 t[j] = valid ? bn_a2 * (dv[j] - bn_m1 - zh * bn_m2) * sg : 0.f;
                             }
                             cl_store_unit(Shi, Slo, cl_unit_off<D, K>(l, c0 / 8 + hlf), t);
@@ -617,8 +661,8 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float du = (xr[j] > 0.f) ? __uint_as_float(u[hlf * 8 + j]) * inv2 : 0.f;
-                                const float4* q = reinterpret_cast<const float4*>(ri + (c0 + hlf * 8 + j) * kClRinfo);
-                                const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                                float4 q0, q1, q2;
+                                cl_rpe_row<D, K>(ri, c0 + hlf * 8 + j, q0, q1, q2);
                                 part[0] = fmaf(du, q0.x, part[0]); part[1] = fmaf(du, q0.y, part[1]);
                                 part[2] = fmaf(du, q0.z, part[2]); part[3] = fmaf(du, q0.w, part[3]);
                                 part[4] = fmaf(du, q1.x, part[4]); part[5] = fmaf(du, q1.y, part[5]);
@@ -747,7 +791,7 @@ static int launch_cl_bwd(const LfaClBwdArgs& a, cudaStream_t st) {
 }
 
 // worker groups per CTA by mode and width (shared-memory budget: weight images + per-group operand planes + row info)
-constexpr int cl_bwd_groups(int mode, int d) { return mode <= 2 ? (d >= 64 ? 2 : 1) : (mode == 3 ? (d >= 64 ? 3 : 2) : 3); }
+constexpr int cl_bwd_groups(int mode, int d) { return mode <= 2 ? 2 : (mode == 3 ? (d >= 64 ? 3 : 2) : 3); }
 
 template <int MODE>
 static int dispatch_cl_bwd(LfaClBwdArgs& a, int K, int d, cudaStream_t st) {

@@ -30,7 +30,7 @@ namespace r3d {
 constexpr int kClLanes = 128;       // virtual channels = TMEM lanes = threads of a worker group
 constexpr int kClR = 64;            // row slots per sub-tile = MMA N = TMEM columns of an accumulator
 constexpr float kClSx = 16.0f;      // fixed scale of activation operands: |x| < 4094 (status bit 0 reports a violation)
-constexpr int kClRinfo = 12;        // floats per row of the row-info table: rpe[10], neighbour offset, spare
+constexpr int kClRinfo = 8;         // floats per row of the row-info table: p_j (3), |p_i - p_j|, two neighbour offsets, 2 spare
 
 template <int D, int K>
 struct ClCfg {
@@ -42,7 +42,7 @@ struct ClCfg {
     static constexpr int PTS = R / K;                 // points per sub-tile
     static constexpr int TPTS = SUB * PTS;            // points per tile
     static constexpr int ROWS = SUB * R;              // (point, neighbour) rows per tile
-    static constexpr int SUB_RI = R * kClRinfo + 4;   // floats between the row-info blocks of two sub-tiles (bank skew)
+    static constexpr int SUB_RI = R * kClRinfo + PTS * 4 + 4;   // floats per sub-tile: rows, then p_i of its points (+ bank skew)
     static constexpr int RINFO_FLOATS = SUB * SUB_RI;
     static constexpr int OP_BYTES = kClLanes * R * 2; // one fp16 plane (hi or lo) of a row operand: 16 KB
     static constexpr int OP_CS = (R / 8) * 128;       // byte stride between channel groups (8 channels) of a row operand
@@ -137,8 +137,10 @@ __device__ __forceinline__ void cl_build_w2_image(const float* __restrict__ w, f
 }
 
 // ---------------------------------------------------------------------------------------------- row info
-// rinfo[sub][n] = {rpe[10], feature offset of the neighbour (uint32 bits), gradient offset of the neighbour (uint32
-// bits; 0xffffffff marks a padding row past the last point)}
+// Row-info table of a tile, per sub-tile: R rows of {p_j.xyz, |p_i - p_j|, feature offset of the neighbour (uint32 bits),
+// gradient offset of the neighbour (uint32 bits; 0xffffffff marks a padding row past the last point), -, -} followed by
+// the PTS points' {p_i.xyz, -}.  The relative position p_i - p_j is re-formed by the readers with the same single
+// rounded subtraction as rpe_of_row, so the encoding stays bit-identical to the KNN's distances.
 template <int D, int K>
 __device__ __forceinline__ void cl_row_info(float* __restrict__ rinfo, const float* __restrict__ xyz, long long xyz_bstride,
                                             const int32_t* __restrict__ idx, long long feat_bstride,
@@ -155,14 +157,29 @@ __device__ __forceinline__ void cl_row_info(float* __restrict__ rinfo, const flo
         const int pj = idx[gp * K + k];
         float rpe[10];
         rpe_of_row(xyz + (size_t)b * xyz_bstride, pi, pj, rpe);
-        float4* dst = reinterpret_cast<float4*>(rinfo + sub * C::SUB_RI + n * kClRinfo);
-        dst[0] = make_float4(rpe[0], rpe[1], rpe[2], rpe[3]);
-        dst[1] = make_float4(rpe[4], rpe[5], rpe[6], rpe[7]);
+        float* base = rinfo + sub * C::SUB_RI;
         const uint32_t off = (uint32_t)((long long)b * feat_bstride + (long long)pj * C::H);
         const uint32_t doff = valid ? (uint32_t)((long long)b * dfeat_bstride + (long long)pj * C::H) : 0xffffffffu;
-        dst[2] = make_float4(rpe[8], rpe[9], __uint_as_float(off), __uint_as_float(doff));
+        float4* dst = reinterpret_cast<float4*>(base + n * kClRinfo);
+        dst[0] = make_float4(rpe[3], rpe[4], rpe[5], rpe[9]);
+        dst[1] = make_float4(__uint_as_float(off), __uint_as_float(doff), 0.f, 0.f);
+        if (k == 0) *reinterpret_cast<float4*>(base + C::R * kClRinfo + p * 4) = make_float4(rpe[0], rpe[1], rpe[2], 0.f);
     }
 }
+
+// the ten encoding channels of row n of a sub-tile, in the register layout cl_mlp1 takes
+template <int D, int K>
+__device__ __forceinline__ void cl_rpe_row(const float* __restrict__ ri, int n, float4& q0, float4& q1, float4& q2) {
+    using C = ClCfg<D, K>;
+    const float4 pt = *reinterpret_cast<const float4*>(ri + C::R * kClRinfo + (n / K) * 4);
+    const float4 rw = *reinterpret_cast<const float4*>(ri + n * kClRinfo);
+    q0 = make_float4(pt.x, pt.y, pt.z, rw.x);
+    q1 = make_float4(rw.y, rw.z, __fsub_rn(pt.x, rw.x), __fsub_rn(pt.y, rw.y));
+    q2 = make_float4(__fsub_rn(pt.z, rw.z), rw.w, 0.f, 0.f);
+}
+// neighbour offsets of row n: feature row (element offset), gradient row (0xffffffff: padding row)
+__device__ __forceinline__ uint32_t cl_feat_off(const float* __restrict__ ri, int n) { return __float_as_uint(ri[n * kClRinfo + 4]); }
+__device__ __forceinline__ uint32_t cl_grad_off(const float* __restrict__ ri, int n) { return __float_as_uint(ri[n * kClRinfo + 5]); }
 
 // r1 = relu(a1 (W1 . rpe) + b1) for one row, W1 row in registers (same FMA order as rpe_mlp1 of lfa_common.cuh)
 __device__ __forceinline__ float cl_mlp1(const float (&w)[10], float a1, float b1, const float4& q0, const float4& q1,

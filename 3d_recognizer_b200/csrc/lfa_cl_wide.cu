@@ -27,7 +27,8 @@ constexpr int kWXBytes = kWD * kWR * 2;                 // one plane of X^T: 16 
 constexpr int kWSBytes = kWH * kWR * 2;                 // one plane of dS^T: 8 KB
 constexpr int kWWBytes = kWH * kWD * 2;                 // one plane of the weight image: 64 KB
 constexpr int kWWIs = 16 * 128;                         // byte stride between input-channel groups of the weight image
-constexpr int kWRinfo = kWR * kClRinfo;                 // floats
+constexpr int kWRow = 12;                                // floats per row of this kernel's row table: rpe[10], two offsets
+constexpr int kWRinfo = kWR * kWRow;                    // floats
 constexpr int kWideFlush = 32;
 
 struct LfaWideArgs {
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_wide_kernel(LfaWi
                 const int pj = a.idx[gp * K + k];
                 float rpe[10];
                 rpe_of_row(a.xyz + (size_t)b * a.xyz_bstride, pi, pj, rpe);
-                float4* dst = reinterpret_cast<float4*>(ri + l * kClRinfo);
+                float4* dst = reinterpret_cast<float4*>(ri + l * kWRow);
                 dst[0] = make_float4(rpe[0], rpe[1], rpe[2], rpe[3]);
                 dst[1] = make_float4(rpe[4], rpe[5], rpe[6], rpe[7]);
                 const uint32_t off = (uint32_t)((long long)b * a.feat_bstride + (long long)pj * kWH);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_wide_kernel(LfaWi
                 float fv[R], rv[R];
                 const float* fb = a.feat + l;
 #pragma unroll
-                for (int j = 0; j < R; ++j) fv[j] = fb[__float_as_uint(ri[j * kClRinfo + 10])];
+                for (int j = 0; j < R; ++j) fv[j] = fb[__float_as_uint(ri[j * kWRow + 10])];
                 if (a.rmat != nullptr) {
                     const float* rb = a.rmat + (size_t)tile * R * kWH + l;
                     const long long rows_left = a.npts * K - tile * R;          // rows of this tile that exist
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_wide_kernel(LfaWi
                 } else {
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        const float4* q = reinterpret_cast<const float4*>(ri + j * kClRinfo);
+                        const float4* q = reinterpret_cast<const float4*>(ri + j * kWRow);
                         rv[j] = cl_mlp1(w1, a1s, b1s, q[0], q[1], q[2]);
                     }
                 }
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_wide_kernel(LfaWi
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int n = c0 + hlf * 8 + j;
-                            const float4* q = reinterpret_cast<const float4*>(ri + n * kClRinfo);
+                            const float4* q = reinterpret_cast<const float4*>(ri + n * kWRow);
                             const float4 q2 = q[2];
                             const uint32_t doff = __float_as_uint(q2.w);
                             if (doff != 0xffffffffu) red_add_f32_w(df + doff, __uint_as_float(u1[hlf * 8 + j]) * inv2);

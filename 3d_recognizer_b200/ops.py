@@ -184,7 +184,7 @@ def _rows_view(x: torch.Tensor):
 # FP32 CUDA-core kernels (its 256 x 256 weight image does not fit shared memory next to the row operands).
 USE_TENSOR_CORES = True
 TC_WIDTHS, TC_NEIGHBORS = (64, 128, 256), (16, 32)     # forward: widths where the tensor-core kernel is the faster one
-TC_BWD_WIDTHS = (64, 128, 256)                         # backward (d = 256: stage-1 backward and pass 1 of stage 2)
+TC_BWD_WIDTHS = (16, 64, 128, 256)                     # backward (d = 256: stage-1 backward and pass 1 of stage 2)
 # r1 moments on the tensor cores, taken of CENTRED values and converted back in fp64 (csrc/lfa_cl_bwd.cu MODE 4): the
 # moments feed BatchNorm statistics (var = E[z^2] - E[z]^2 cancels), where the tensor core's systematic accumulate
 # truncation on raw second moments showed up as 1e-4-level deviations in the encoding-MLP gradients
