@@ -318,8 +318,8 @@ extern "C" int r3d_lfa_pool_tc(int stage, const float* xyz, long long xyz_bstrid
         a.ntiles = (a.npts + ClCfg<DD, KK>::TPTS - 1) / ClCfg<DD, KK>::TPTS;                \
         return stage == 1 ? launch_cl_fwd<DD, KK, 1, NG1>(a, st) : launch_cl_fwd<DD, KK, 2, NG2>(a, st); \
     }
-    R3D_CL_CASE(128, 16, 4, 4) R3D_CL_CASE(64, 16, 4, 4) R3D_CL_CASE(32, 16, 4, 3) R3D_CL_CASE(16, 16, 3, 3)
-    R3D_CL_CASE(128, 32, 4, 4) R3D_CL_CASE(64, 32, 4, 4) R3D_CL_CASE(32, 32, 4, 3) R3D_CL_CASE(16, 32, 3, 3)
+    R3D_CL_CASE(128, 16, 4, 4) R3D_CL_CASE(64, 16, 4, 3) R3D_CL_CASE(32, 16, 4, 3) R3D_CL_CASE(16, 16, 3, 3)
+    R3D_CL_CASE(128, 32, 4, 4) R3D_CL_CASE(64, 32, 4, 3) R3D_CL_CASE(32, 32, 4, 3) R3D_CL_CASE(16, 32, 3, 3)
 #undef R3D_CL_CASE
     return R3D_EUNSUPPORTED;
 }

@@ -613,6 +613,142 @@ extern "C" int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca
                                    float* y, long long y_bstride, int y_ld, int cout, int B, int n, int transpose_out,
                                    double* stats, int w_out_in, r3d_stream_t stream);
 
+
+// ------------------------------------------------------------------------------------ streaming rows kernel
+// Dense narrow layers on many rows (the level-0 layers of a large batch: 2.6 M rows of 8..64 channels): HBM-streaming.
+// The GEMM kernels above stage 16-channel chunks behind barriers and the one-thread-per-row kernel reads rows with a
+// 32..256-byte stride between lanes; both sit at 1.2-1.5 TB/s on these shapes.  Here a CTA of 128 threads takes blocks of
+// 128 rows: the block is read with fully coalesced float4 loads into a padded shared-memory tile, thread t computes row
+// t from the tile (own row: conflict-free LDS.128; weights: broadcast LDS.128), the outputs go back through a second
+// tile and leave with coalesced float4 stores; the batch statistics of a train-mode BatchNorm are column sums of that
+// tile, kept per channel in fp64 registers across the CTA's blocks and flushed with one atomic per channel and CTA.
+template <int CIN, int COUT>
+struct PwRowsSmem {
+    static constexpr int XLD = CIN + 4, YLD = COUT + 4;
+    static constexpr size_t BYTES = (size_t)(128 * XLD + 128 * YLD + CIN * COUT + 2 * COUT) * sizeof(float);
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128) pw_rows_kernel(PwArgs a) {
+    using S = PwRowsSmem<CIN, COUT>;
+    extern __shared__ __align__(16) float sm[];
+    float* Xs = sm;                              // [128][XLD]
+    float* Ys = Xs + 128 * S::XLD;               // [128][YLD]
+    float* Ws = Ys + 128 * S::YLD;               // [CIN][COUT]
+    float* Sc = Ws + CIN * COUT;                 // scale, shift
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * COUT; i += 128)
+        Ws[i] = a.w_out_in ? a.wT[(size_t)(i % COUT) * CIN + i / COUT] : a.wT[i];
+    for (int i = tid; i < COUT; i += 128) {
+        Sc[i] = a.scale ? a.scale[i] : 1.f;
+        Sc[COUT + i] = a.shift ? a.shift[i] : 0.f;
+    }
+    __syncthreads();
+    const long long M = (long long)a.B * a.n;
+    const long long nblk = (M + 127) / 128;
+    double s1 = 0.0, s2 = 0.0;                   // thread c < COUT: statistics of channel c
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long m0 = blk * 128;
+        const int rows = (int)((M - m0 < 128) ? (M - m0) : 128);
+        // ---- coalesced load of the block
+        const float4* src = reinterpret_cast<const float4*>(a.xa + m0 * CIN);
+#pragma unroll
+        for (int k = 0; k < CIN / 4; ++k) {
+            const int i = tid + k * 128;
+            const int r = i / (CIN / 4), c4 = i % (CIN / 4);
+            const float4 v = (r < rows) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(Xs + r * S::XLD + c4 * 4) = v;
+        }
+        __syncthreads();
+        // ---- row tid
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+        const float* xr = Xs + tid * S::XLD;
+#pragma unroll
+        for (int c = 0; c < CIN; c += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + c);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < COUT; j += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(Ws + (c + u) * COUT + j);
+                    acc[j] = fmaf(xv[u], w.x, acc[j]);
+                    acc[j + 1] = fmaf(xv[u], w.y, acc[j + 1]);
+                    acc[j + 2] = fmaf(xv[u], w.z, acc[j + 2]);
+                    acc[j + 3] = fmaf(xv[u], w.w, acc[j + 3]);
+                }
+        }
+        float* yr = Ys + tid * S::YLD;
+#pragma unroll
+        for (int j = 0; j < COUT; j += 4) {
+            float4 o;
+            o.x = apply_act(fmaf(acc[j], Sc[j], Sc[COUT + j]), a.act, a.slope);
+            o.y = apply_act(fmaf(acc[j + 1], Sc[j + 1], Sc[COUT + j + 1]), a.act, a.slope);
+            o.z = apply_act(fmaf(acc[j + 2], Sc[j + 2], Sc[COUT + j + 2]), a.act, a.slope);
+            o.w = apply_act(fmaf(acc[j + 3], Sc[j + 3], Sc[COUT + j + 3]), a.act, a.slope);
+            if (tid >= rows) o = make_float4(0.f, 0.f, 0.f, 0.f);          // rows past the end count for nothing
+            *reinterpret_cast<float4*>(yr + j) = o;
+        }
+        __syncthreads();
+        // ---- coalesced store, column sums
+        float4* dst = reinterpret_cast<float4*>(a.y + m0 * COUT);
+#pragma unroll
+        for (int k = 0; k < COUT / 4; ++k) {
+            const int i = tid + k * 128;
+            const int r = i / (COUT / 4), c4 = i % (COUT / 4);
+            if (r < rows) dst[i] = *reinterpret_cast<const float4*>(Ys + r * S::YLD + c4 * 4);
+        }
+        if (a.stats && tid < COUT) {
+            float p1 = 0.f, p2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 128; ++r) {
+                const float v = Ys[r * S::YLD + tid];
+                p1 += v;
+                p2 = fmaf(v, v, p2);
+            }
+            s1 += (double)p1;
+            s2 += (double)p2;
+        }
+        __syncthreads();
+    }
+    if (a.stats && tid < COUT) {
+        atomicAdd(a.stats + tid, s1);
+        atomicAdd(a.stats + COUT + tid, s2);
+    }
+}
+
+static bool pw_rows_eligible(const PwArgs& a) {
+    const long long M = (long long)a.B * a.n;
+    auto ok = [](int c) { return c == 8 || c == 16 || c == 32 || c == 64; };
+    return M >= 131072 && a.cb == 0 && !a.gidx && !a.transpose_out && !a.bn.y && ok(a.ca) && ok(a.cout) &&
+           a.ca * a.cout <= 2048 && a.y_ld == a.cout && a.xa_bstride == (long long)a.n * a.ca &&
+           a.y_bstride == (long long)a.n * a.cout;
+}
+
+template <int CIN, int COUT>
+static int pw_rows_launch(const PwArgs& a, cudaStream_t st) {
+    auto kern = pw_rows_kernel<CIN, COUT>;
+    constexpr size_t smem = PwRowsSmem<CIN, COUT>::BYTES;
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nblk = ((long long)a.B * a.n + 127) / 128;
+    const long long grid = nblk < (long long)kNumSMs * 4 ? nblk : (long long)kNumSMs * 4;
+    kern<<<(unsigned)grid, 128, smem, st>>>(a);
+    R3D_LAUNCH_CHECK("pw_rows_kernel");
+    return R3D_OK;
+}
+
+static int pw_rows_run(const PwArgs& a, cudaStream_t st) {
+#define R3D_ROWS(CI, CO) \
+    if (a.ca == CI && a.cout == CO) return pw_rows_launch<CI, CO>(a, st);
+    R3D_ROWS(8, 8) R3D_ROWS(8, 16) R3D_ROWS(8, 32) R3D_ROWS(8, 64) R3D_ROWS(16, 8) R3D_ROWS(16, 16) R3D_ROWS(16, 32)
+    R3D_ROWS(16, 64) R3D_ROWS(32, 8) R3D_ROWS(32, 16) R3D_ROWS(32, 32) R3D_ROWS(32, 64) R3D_ROWS(64, 8) R3D_ROWS(64, 16)
+    R3D_ROWS(64, 32)
+#undef R3D_ROWS
+    return R3D_EUNSUPPORTED;
+}
+
 // ------------------------------------------------------------------------------------- launch helpers
 // Launches a per-point kernel.  When the fused BatchNorm tail is wanted (a.bn.y) the launch must be cooperative (grid
 // barrier) and the whole grid co-resident; otherwise a.bn.y is cleared and the caller runs r3d_bn_apply afterwards.
@@ -657,6 +793,7 @@ static int pw_run(PwArgs a, cudaStream_t st, bool* fused) {
     const int ca = a.ca, cb = a.cb, cout = a.cout;
     const long long M = (long long)a.B * a.n;
     if (fused) *fused = false;
+    if (pw_rows_eligible(a)) return pw_rows_run(a, st);
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
         int rc = pw_launch(pw_small_kernel, dim3((unsigned)((M + 255) / 256)), 256, a, st, fused);
         if (rc != R3D_OK) return rc;
@@ -776,6 +913,19 @@ extern "C" int r3d_pointwise_bn(const float* x, long long M, int cin, const floa
 // shared memory), 1 pw_gemm_kernel (channel counts not multiples of 4), 2 pw_gemm_fast_kernel (pipelined FP32 GEMM,
 // any tile shape), 3 pw_tc_kernel (tcgen05 3xTF32).  Dense layout assumed (y_ld = cout).
 extern "C" int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int transpose_out) {
+    {
+        PwArgs r{};
+        r.ca = ca;
+        r.cb = cb;
+        r.cout = cout;
+        r.B = 1;
+        r.n = (int)(rows > 0x7fffffffLL ? 0x7fffffffLL : rows);
+        r.transpose_out = transpose_out;
+        r.y_ld = cout;
+        r.xa_bstride = (long long)r.n * ca;
+        r.y_bstride = (long long)r.n * cout;
+        if (pw_rows_eligible(r)) return 4;
+    }
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) return 0;
     PwArgs a{};
     a.ca = ca;

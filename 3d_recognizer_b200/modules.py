@@ -168,6 +168,10 @@ class UpSampler(torch.nn.Module):
         return y.transpose(1, 2).unsqueeze(-1)
 
 
+SUPPORTED_LAYER_SIZES = (16, 32, 64, 128, 256)
+SUPPORTED_NEIGHBORS = (16, 32)
+
+
 class RandLANet(torch.nn.Module):
     """RandLA-Net (modules.py:459-611): forward((B,N,3+F)) -> logits (B,C,N)."""
 
@@ -180,6 +184,12 @@ class RandLANet(torch.nn.Module):
         self._device = device
         sizes = settings.layer_sizes
         L = len(sizes)
+        # the fused LocSE + pooling kernels are instantiated for these widths / neighbour counts (csrc/lfa*.cu); anything
+        # else fails here, at construction, not at the first forward (there is no tensor-op fallback back-end)
+        bad = [d for d in sizes if d not in SUPPORTED_LAYER_SIZES]
+        if bad or k not in SUPPORTED_NEIGHBORS:
+            raise ValueError(f"3d_recognizer_b200 builds its fused LFA kernels for layer_sizes in {SUPPORTED_LAYER_SIZES} "
+                             f"and n_neighbors in {SUPPORTED_NEIGHBORS}; got layer_sizes={list(sizes)}, n_neighbors={k}")
         # (1) K points must survive down to the last encoder level; (2) >= 2 points at the bottleneck
         self._min_n_points = max(k * settings.decimation ** (L - 1), 2 * settings.decimation ** L)
 

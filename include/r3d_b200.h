@@ -305,7 +305,7 @@ int r3d_pointwise_stats(const float* xa, long long xa_bstride, int ca, const int
  * (>= 4096 rows; tests, benchmarks).  Returns the previous value. */
 int r3d_pointwise_set_tensor_cores(int on);
 /* the kernel r3d_pointwise runs for a dense layer under the current settings: 0 pw_small_kernel, 1 pw_gemm_kernel,
- * 2 pw_gemm_fast_kernel, 3 pw_tc_kernel (tcgen05) */
+ * 2 pw_gemm_fast_kernel, 3 pw_tc_kernel (tcgen05), 4 pw_rows_kernel (HBM-streaming: dense narrow layers, >= 131072 rows) */
 int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int transpose_out);
 
 /* ------------------------------------------------------------- train-mode BatchNorm of a per-point layer

@@ -229,3 +229,29 @@ def test_lfa_pool_tensor_core_vs_cuda_core(mods, d, K, stage, B, N):
                           b1 if s2 else None, ws)
     assert rel_err(got, ref) < 1e-5
     ops.check_tc_status(xyz.device)
+
+
+@pytest.mark.parametrize("ca,cout", [(8, 8), (8, 64), (16, 32), (32, 64), (64, 32), (64, 8), (32, 16), (16, 16)])
+@pytest.mark.parametrize("w_out_in,act", [(False, "relu"), (True, None)])
+def test_pointwise_streaming_rows_kernel(mods, ca, cout, w_out_in, act):
+    """pw_rows_kernel (dense narrow layers on >= 131072 rows: the level-0 layers of a large batch): values, the
+    batch statistics of the train-mode epilogue, a row count that is not a multiple of the 128-row block."""
+    _, _, ops = mods
+    L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+    B, n = 2, 100003
+    assert L.r3d_pointwise_plan(ca, 0, cout, B * n, 0) == 4
+    g = torch.Generator(device="cuda").manual_seed(ca * 100 + cout)
+    x = torch.randn(B, n, ca, device="cuda", generator=g)
+    shape = (cout, ca) if w_out_in else (ca, cout)
+    w = torch.randn(*shape, device="cuda", generator=g) / ca ** 0.5
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    sh = torch.randn(cout, device="cuda", generator=g)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    got = ops.pointwise(x, w, sc, sh, act, 0.0, stats=stats, w_out_in=w_out_in)
+    wm = w.double().t() if w_out_in else w.double()
+    ref = (x.double() @ wm) * sc.double() + sh.double()
+    ref = F.relu(ref) if act == "relu" else ref
+    assert rel_err(got.double(), ref) < 2e-6
+    flat = ref.reshape(-1, cout)
+    assert rel_err(stats[:cout], flat.sum(0)) < 1e-5 * max(1.0, float(flat.abs().sum(0).max() / flat.sum(0).abs().max()))
+    assert rel_err(stats[cout:], (flat * flat).sum(0)) < 1e-5
