@@ -261,7 +261,7 @@ class _LfaPoolFn(torch.autograd.Function):
     def forward(ctx, stage, xyz, idx32, feat, ws, w1, a1, c1, w2, a2, c2, w1f, a1f, c1f, w2f, a2f, c2f):
         w2T = w2f.t().contiguous() if stage == 2 else None
         wsT = ws.t().contiguous()
-        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2], idx32.shape[0] * idx32.shape[1]):
             pooled = ops.lfa_pool_tc(stage, xyz, idx32, feat, w1f, a1f, c1f, w2f if stage == 2 else None,
                                      a2f if stage == 2 else None, c2f if stage == 2 else None, ws.contiguous())
         else:
@@ -303,7 +303,7 @@ class _LfaPool1TrainFn(torch.autograd.Function):
     def forward(ctx, xyz, idx32, feat, ws, w1, gamma1, beta1, w2, gamma2, beta2, w1f, a1f, c1f, m, save1, g1, count,
                 shared):
         wsT = shared["wT"][0] if "wT" in shared else ws.t().contiguous()
-        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2], idx32.shape[0] * idx32.shape[1]):
             pooled = ops.lfa_pool_tc(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, ws.contiguous())
         else:
             pooled = ops.lfa_pool(1, xyz, idx32, feat, w1f, a1f, c1f, None, None, None, wsT)
@@ -346,7 +346,7 @@ class _LfaPool2TrainFn(torch.autograd.Function):
         else:
             w2T = w2f.t().contiguous()
             wsT = ws.t().contiguous()
-        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2]):
+        if ops.lfa_pool_tc_supported(ws.shape[0], idx32.shape[2], idx32.shape[0] * idx32.shape[1]):
             ctx.tc_cache = {}           # d = 256: the r2 rows the forward materialised, reused by pass 1 of the backward
             pooled = ops.lfa_pool_tc(2, xyz, idx32, feat, w1f, a1f, c1f, w2f.contiguous(), a2f, c2f, ws.contiguous(),
                                      cache=ctx.tc_cache)
@@ -684,7 +684,7 @@ def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Te
         f = ops.pointwise(x, w, sc, sh, "lrelu", 0.2)
         w1, a1, b1 = e["rpe1"]
         w2T, a2, b2 = e["rpe2"]
-        tc = ops.lfa_pool_tc_supported(2 * w1.shape[0], k)
+        tc = ops.lfa_pool_tc_supported(2 * w1.shape[0], k, idx.shape[0] * idx.shape[1])
         pooled = (ops.lfa_pool_tc(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1_oi"]) if tc else
                   ops.lfa_pool(1, xyz_l, idx, f, w1, a1, b1, None, None, None, e["score1"]))
         w, sc, sh = e["pool1"]

@@ -190,6 +190,8 @@ TC_BWD_WIDTHS = (16, 64, 128, 256)                     # backward (d = 256: stag
 # truncation on raw second moments showed up as 1e-4-level deviations in the encoding-MLP gradients
 TC_MOM_WIDTHS = (16, 64, 128)
 TC_ALL_WIDTHS = (16, 32, 64, 128, 256)                 # what the kernels are built for (tests run all of them)
+if os.environ.get("R3D_TC_OFF"):                      # tuning override: FP32 CUDA-core LFA kernels everywhere
+    USE_TENSOR_CORES = False
 if os.environ.get("R3D_TC_WIDTHS"):                   # tuning override: "fwd widths;bwd widths", e.g. "64,128;16,64,128"
     _f, _, _b = os.environ["R3D_TC_WIDTHS"].partition(";")
     TC_WIDTHS = tuple(int(v) for v in _f.split(",") if v)
@@ -197,16 +199,31 @@ if os.environ.get("R3D_TC_WIDTHS"):                   # tuning override: "fwd wi
 _TC_STATUS = {}
 
 
-def lfa_pool_tc_supported(d: int, k: int) -> bool:
-    return USE_TENSOR_CORES and d in TC_WIDTHS and k in TC_NEIGHBORS
+# Launches too small to amortise a tensor-core kernel's fixed cost (weight image, TMEM folds, the final d x d atomics of
+# up to 148 CTAs: ~20 us forward, ~90 us backward) stay on the FP32 kernels.  Thresholds in POINTS (B*N) per launch,
+# from the 8 x 2 500-point step (profiles/r02_tc_vs_fp32_train2500.txt): forward pays from ~1 k points at d = 64/128,
+# the backward family from ~16 k (d = 16: ~130 k), d = 256 backward always.  TC_MIN_POINTS = 0 forces (tests).
+TC_MIN_POINTS = {"fwd": {64: 1024, 128: 512, 256: 1024, 16: 1 << 30, 32: 1 << 30},
+                 "bwd": {16: 131072, 32: 32768, 64: 16384, 128: 4096, 256: 0},
+                 "mom": {16: 131072, 32: 32768, 64: 16384, 128: 4096}}
+TC_FORCE = False
 
 
-def lfa_bwd_tc_supported(d: int, k: int) -> bool:
-    return USE_TENSOR_CORES and d in TC_BWD_WIDTHS and k in TC_NEIGHBORS
+def _tc_big_enough(kind: str, d: int, points) -> bool:
+    return TC_FORCE or points is None or points >= TC_MIN_POINTS[kind].get(d, 0)
 
 
-def lfa_mom_tc_supported(d: int, k: int) -> bool:
-    return USE_TENSOR_CORES and d in TC_MOM_WIDTHS and d <= 128 and k in TC_NEIGHBORS
+def lfa_pool_tc_supported(d: int, k: int, points=None) -> bool:
+    return USE_TENSOR_CORES and d in TC_WIDTHS and k in TC_NEIGHBORS and _tc_big_enough("fwd", d, points)
+
+
+def lfa_bwd_tc_supported(d: int, k: int, points=None) -> bool:
+    return USE_TENSOR_CORES and d in TC_BWD_WIDTHS and k in TC_NEIGHBORS and _tc_big_enough("bwd", d, points)
+
+
+def lfa_mom_tc_supported(d: int, k: int, points=None) -> bool:
+    return (USE_TENSOR_CORES and d in TC_MOM_WIDTHS and d <= 128 and k in TC_NEIGHBORS
+            and _tc_big_enough("mom", d, points))
 
 
 def _lfa_tc_wide(mode: int, name: str, flops: float, nbytes: float, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1,
@@ -504,13 +521,13 @@ def lfa_pool_bwd(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, 
         g2c = acc64[h * 16 + h * h:].view(h, 16)
     flops = float(B) * N * (2 * K * (10 * h + 3 * d * d + d + (3 * h * h if stage == 2 else 0)))
     nbytes = float(B) * N * (12 + 4 * K + 4 * h + 4 * d + 4 * K * h)
-    if stage == 1 and d == 256 and lfa_bwd_tc_supported(d, K):
+    if stage == 1 and d == 256 and lfa_bwd_tc_supported(d, K, B * N):
         scal = zeros(2, torch.float32, dev)
         _absmax_into(dpooled, scal)
         _lfa_tc_wide(1, "lfa_cl_bwd1", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1, w_score,
                      dpooled=dpooled, dfeat=dfeat, dws=dws, g1=g1, scal=scal)
         return dfeat, dws, g1, g2m, g2c
-    if stage == 1 and lfa_bwd_tc_supported(d, K):
+    if stage == 1 and lfa_bwd_tc_supported(d, K, B * N):
         scal = zeros(2, torch.float32, dev)
         _absmax_into(dpooled, scal)
         _lfa_tc_bwd(1, "lfa_cl_bwd1", flops, nbytes, xyz, xs, idx32, feat, fs, w_rpe1, a_rpe1, b_rpe1, w_score=w_score,
@@ -543,7 +560,7 @@ def lfa_moments(mode: int, xyz, idx32, d: int, w_rpe1=None, a_rpe1=None, b_rpe1=
         g1 = zeros((h, 16), torch.float64, dev)
     flops = float(B) * N * K * 2 * (256 if mode == 0 else 10 * h + h * h + (16 * h if mode == 2 else 0))
     nbytes = float(B) * N * (12 + 4 * K)
-    if mode == 1 and lfa_mom_tc_supported(d, K):
+    if mode == 1 and lfa_mom_tc_supported(d, K, B * N):
         _lfa_tc_bwd(4, "lfa_cl_mom", flops, nbytes, xyz, xs, idx32, None, 0, w_rpe1, a_rpe1, b_rpe1, m_r1=m_r1, s_r1=s_r1)
         return m_r1, s_r1
     with torch.cuda.device(dev), _cabi.kernel_timer(f"lfa_moments{mode}[N={N},d={d}]", flops=flops, bytes=nbytes):
@@ -614,7 +631,7 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
     d = 2 * h
     dev = xyz.device
     L = _cabi.lib()
-    if d == 256 and lfa_bwd_tc_supported(d, K):
+    if d == 256 and lfa_bwd_tc_supported(d, K, B * N):
         if w_rpe2 is None:
             w_rpe2 = w_rpe2T.t().contiguous()
         rmat = cache.pop("r2", None) if cache is not None else None
@@ -638,7 +655,7 @@ def lfa_pool2_bwd_train(xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe
             rc = L.r3d_lfa_du2_combine(_cabi.ptr(part), _cabi.ptr(du2), B, N, K, h, pts, _cabi.stream_ptr(dev))
         _cabi.check(rc, "r3d_lfa_du2_combine")
         return dfeat, dws, du2, sums
-    if lfa_bwd_tc_supported(d, K):
+    if lfa_bwd_tc_supported(d, K, B * N):
         if w_rpe2 is None:
             w_rpe2 = w_rpe2T.t().contiguous()
         dpooled = dpooled.contiguous()

@@ -106,9 +106,27 @@ def _fit_branches(A: torch.Tensor, d: torch.Tensor):
     return on
 
 
-@pytest.mark.parametrize("N,B,seed,extra", [(1024, 2, 11, {}), (2500, 2, 12, {}), (16384, 1, 41, {})])
+@pytest.mark.parametrize("N,B,seed,extra", [(1024, 2, 11, {}), (2500, 2, 12, {}), (16384, 1, 41, {}),
+                                            (2500, 2, 12, dict(force_tc=True))])
 def test_every_gradient_entry_with_pinned_branches(N, B, seed, extra):
+    """Last case: the tensor-core LFA kernels forced at every level (the dispatcher would keep launches this small on
+    the FP32 kernels), so that the whole-network bar also covers them end to end."""
     modules = importlib.import_module("3d_recognizer_b200.modules")
+    ops = importlib.import_module("3d_recognizer_b200.ops")
+    extra = dict(extra)
+    saved = (ops.TC_FORCE, ops.TC_WIDTHS, ops.TC_BWD_WIDTHS, ops.TC_MOM_WIDTHS)
+    if extra.pop("force_tc", False):
+        ops.TC_FORCE = True
+        ops.TC_WIDTHS = ops.TC_BWD_WIDTHS = ops.TC_ALL_WIDTHS
+        ops.TC_MOM_WIDTHS = (16, 32, 64, 128)
+    try:
+        _pinned_case(modules, N, B, seed, extra)
+    finally:
+        ops.TC_FORCE, ops.TC_WIDTHS, ops.TC_BWD_WIDTHS, ops.TC_MOM_WIDTHS = saved
+        ops.check_tc_status(torch.device("cuda"))
+
+
+def _pinned_case(modules, N, B, seed, extra):
     st = dict(dict(n_classes=2, n_points=N, n_features=0, n_neighbors=16, knn="kdtree"), **extra)
     sd = onet.synth_state_dict(st, seed)
     x = torch.from_numpy(make_input(B, N, st["n_features"], seed))

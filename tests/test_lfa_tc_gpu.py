@@ -27,13 +27,14 @@ class _force:
 
     def __enter__(self):
         o = self.ops
-        self.saved = (o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS)
+        self.saved = (o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS, o.TC_FORCE)
         o.USE_TENSOR_CORES = self.on
+        o.TC_FORCE = True                                  # also below the size thresholds of the dispatcher
         o.TC_BWD_WIDTHS = o.TC_WIDTHS = o.TC_MOM_WIDTHS = o.TC_ALL_WIDTHS
 
     def __exit__(self, *exc):
         o = self.ops
-        o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS = self.saved
+        o.USE_TENSOR_CORES, o.TC_BWD_WIDTHS, o.TC_WIDTHS, o.TC_MOM_WIDTHS, o.TC_FORCE = self.saved
         return False
 
 
