@@ -90,6 +90,16 @@ SIGNATURES = {
                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_confusion_counts": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
                                      c_int, c_int, c_void_p, c_void_p]),
+    "r3d_upsample": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                             ctypes.c_float, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, ctypes.c_longlong,
+                             c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_upsample_bwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                 ctypes.c_float, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, ctypes.c_longlong,
+                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_feed_batch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                               ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_void_p,
+                               c_int, c_void_p]),
+    "r3d_sample_subset": (c_int, [c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_int, c_void_p]),
     "r3d_pointwise_bn": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int,
                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -228,21 +228,58 @@ def lfa_block(lfa, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + shared_mlp(lfa.shortcut, feat), 0.01)
 
 
+class _UpsampleFn(torch.autograd.Function):
+    """ops.upsample (gather at the K nearest coarse points, weighted sum, optional concat with the decoder skip) with
+    its scatter-add backward (ops.upsample_bwd): one launch each way."""
+
+    @staticmethod
+    def forward(ctx, approach, feat, idx, dist, skip):
+        ctx.approach, ctx.n_coarse, ctx.n_feat = approach, feat.shape[1], feat.shape[2]
+        ctx.save_for_backward(idx, dist)
+        return ops.upsample(approach, feat, idx, dist, skip)
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, dist = ctx.saved_tensors
+        need_skip = ctx.needs_input_grad[4]
+        dfeat, dskip = ops.upsample_bwd(ctx.approach, dout, idx, dist, ctx.n_coarse, ctx.n_feat, need_skip)
+        return None, dfeat if ctx.needs_input_grad[1] else None, None, None, dskip
+
+
 def upsample(approach: str, feat: torch.Tensor, xyz: torch.Tensor, xyz_up: torch.Tensor,
-             idx: torch.Tensor = None) -> torch.Tensor:
-    """UpSampler (modules.py:343-456) on point-major features: feat (B,N1,F) -> (B,N2,F).  ``idx``: the 1-NN indices
-    (B,N2,1) int64 when the caller has searched already."""
+             idx: torch.Tensor = None, skip: torch.Tensor = None, channel_major: bool = False) -> torch.Tensor:
+    """UpSampler (modules.py:343-456) on point-major features: feat (B,N1,F) -> (B,N2,F) [(B,N2,F+Fs) with the decoder
+    skip (B,N2,Fs) concatenated, modules.py:600-602; (B,F,N2) with ``channel_major``].  ``idx``: the 1-NN indices
+    (B,N2,1) when the caller has searched already.  One neighbour search and one gather launch; differentiable in
+    ``feat`` and ``skip``."""
+    if approach not in ops.UP_WEIGHTING:
+        raise ValueError(f"Upsampling approach {approach} not understood!")
+    dist = None
+    if not (feat.is_cuda and feat.dtype == torch.float32):
+        # fp64 arbiters and the CPU host-logic tests (forward() itself refuses non-CUDA inputs): the same math as
+        # differentiable tensor ops, like shared_mlp
+        if approach == "nni":
+            if idx is None:
+                idx = ops.knn(xyz, xyz_up, 1, idx64=True, dist=False)["idx64"]
+            up = gather_points(feat, idx[:, :, :1]).squeeze(2)
+        else:
+            nn_ = ops.knn(xyz, xyz_up, 8, idx64=True, dist=True)
+            w = (1.0 + 1e-7) / (nn_["dist"] ** ops.UP_WEIGHTING[approach][1] + 1e-7)
+            w = w / w.sum(dim=-1, keepdim=True)
+            up = (w.unsqueeze(-1) * gather_points(feat, nn_["idx64"])).sum(dim=2)
+        up = up if skip is None else torch.cat((up, skip), dim=-1)
+        return up.transpose(1, 2) if channel_major else up
     if approach == "nni":
         if idx is None:
-            idx = ops.knn(xyz, xyz_up, 1, idx64=True, dist=False)["idx64"]
-        return gather_points(feat, idx).squeeze(2)
-    # "nna" reaches the inverse-distance branch too (default argument, modules.py:372 / :435)
-    power = 2.0 if approach == "isdw" else 1.0
-    nn_ = ops.knn(xyz, xyz_up, 8, idx64=True, dist=True)
-    eps = 1e-7
-    w = (1.0 + eps) / (nn_["dist"] ** power + eps)
-    w = w / w.sum(dim=-1, keepdim=True)
-    return (w.unsqueeze(-1) * gather_points(feat, nn_["idx64"])).sum(dim=2)
+            idx = ops.knn(xyz, xyz_up, 1, idx64=False, idx32=True, dist=False)["idx32"]
+    else:
+        # "nna" reaches the inverse-distance branch too (default argument, modules.py:372 / :435)
+        nn_ = ops.knn(xyz, xyz_up, 8, idx64=False, idx32=True, dist=True)
+        idx, dist = nn_["idx32"], nn_["dist"]
+    if torch.is_grad_enabled() and (feat.requires_grad or (skip is not None and skip.requires_grad)):
+        out = _UpsampleFn.apply(approach, feat, idx, dist, skip)
+        return out.transpose(1, 2) if channel_major else out
+    return ops.upsample(approach, feat, idx, dist, skip, channel_major)
 
 
 # ------------------------------------------------------------- training path: fused LFA with autograd
@@ -549,8 +586,8 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
                 K = net.encoder[lvl]._n_neighbors
                 enc_idx[lvl] = ops.knn(xyz[:, :n_k], xyz[:, :n_k], K, idx64=False, idx32=True, dist=False)["idx32"]
             for lvl in range(L):                     # decoder stage lvl: sizes[L - lvl] -> sizes[L - lvl - 1] points
-                dec_idx[lvl] = ops.knn(xyz[:, :sizes[L - lvl]], xyz[:, :sizes[L - lvl - 1]], 1, idx64=True,
-                                       dist=False)["idx64"]
+                dec_idx[lvl] = ops.knn(xyz[:, :sizes[L - lvl]], xyz[:, :sizes[L - lvl - 1]], 1, idx64=False, idx32=True,
+                                       dist=False)["idx32"]
 
     skips: List[torch.Tensor] = []
     n_l = N
@@ -568,8 +605,8 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     cur = shared_mlp(net.mlp, cur)
     for lvl, stage in enumerate(net.decoder):
         n_up = skips[-1].shape[1]          # N // dec^(l-1): the encoder level this stage returns to
-        up = upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up], dec_idx.get(lvl))
-        cur = shared_mlp(stage, torch.cat((up, skips.pop()), dim=-1))
+        # 1-NN up-sampling + skip concat (modules.py:596-602): one gather launch, one scatter launch in the backward
+        cur = shared_mlp(stage, upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up], dec_idx.get(lvl), skip=skips.pop()))
         n_l = n_up
     inv = torch.empty_like(perm)                  # inverse permutation by scatter (argsort is a 30 us radix sort)
     inv.scatter_(0, perm, torch.arange(perm.numel(), device=perm.device))

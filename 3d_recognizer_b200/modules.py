@@ -164,8 +164,9 @@ class UpSampler(torch.nn.Module):
         if ap not in ("nni", "nna", "idw", "isdw"):
             raise ValueError(f"Upsampling approach {ap} not understood!")
         dev = self._device
-        y = engine.upsample(ap, features.to(dev).squeeze(-1).transpose(1, 2), xyz.to(dev), xyz_upsampled.to(dev))
-        return y.transpose(1, 2).unsqueeze(-1)
+        y = engine.upsample(ap, features.to(dev).squeeze(-1).transpose(1, 2), xyz.to(dev), xyz_upsampled.to(dev),
+                            channel_major=True)
+        return y.unsqueeze(-1)
 
 
 SUPPORTED_LAYER_SIZES = (16, 32, 64, 128, 256)

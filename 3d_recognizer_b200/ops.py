@@ -380,6 +380,72 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
     return out
 
 
+UP_WEIGHTING = {"nni": (0, 1.0), "nna": (1, 1.0), "idw": (1, 1.0), "isdw": (1, 2.0), "mean": (2, 1.0)}
+
+
+def _up_args(approach: str, idx: torch.Tensor, dist: Optional[torch.Tensor]):
+    if approach not in UP_WEIGHTING:
+        raise ValueError(f"Upsampling approach {approach} not understood!")
+    weighting, power = UP_WEIGHTING[approach]
+    if idx.dtype not in (torch.int32, torch.int64) or idx.dim() != 3:
+        raise ValueError("idx must be an int32 / int64 tensor of shape (B, N2, K)")
+    idx = idx.contiguous()
+    if weighting == 1:
+        if dist is None or dist.shape != idx.shape:
+            raise ValueError("the inverse-distance approaches need dist (B, N2, K)")
+        dist = dist.float().contiguous()
+    return weighting, power, idx, dist
+
+
+def upsample(approach: str, feat: torch.Tensor, idx: torch.Tensor, dist: Optional[torch.Tensor] = None,
+             skip: Optional[torch.Tensor] = None, channel_major: bool = False) -> torch.Tensor:
+    """UpSampler gather (modules.py:343-414) [+ decoder skip concat, :600-602] in one launch (C ABI ``r3d_upsample``).
+    feat (B,N1,F), idx (B,N2,K) neighbours of the fine points among the coarse ones, dist (B,N2,K) for nna/idw/isdw,
+    skip (B,N2,Fs) -> (B,N2,F+Fs), or (B,F,N2) with ``channel_major``."""
+    _cabi.require_cuda(feat, "feat")
+    weighting, power, idx, dist = _up_args(approach, idx, dist)
+    feat, fbs = _rows_view(feat.detach())
+    B, N1, F = feat.shape
+    N2, K = idx.shape[1], idx.shape[2]
+    Fs, sbs = 0, 0
+    if skip is not None:
+        skip, sbs = _rows_view(skip.detach())
+        Fs = skip.shape[2]
+        assert skip.shape[1] >= N2
+    dev = feat.device
+    out = torch.empty((B, F, N2) if channel_major else (B, N2, F + Fs), dtype=torch.float32, device=dev)
+    kk = 1 if weighting == 0 else K
+    with torch.cuda.device(dev), _cabi.kernel_timer("upsample", flops=2.0 * B * N2 * F * kk,
+                                                    bytes=4.0 * B * N2 * (F * (kk + 1) + 2 * Fs + 2 * kk)):
+        rc = _cabi.lib().r3d_upsample(_cabi.raw(feat), fbs, F, F, _cabi.ptr(idx), int(idx.dtype == torch.int64),
+                                      _cabi.ptr(dist), K, weighting, power, _cabi.raw(skip), sbs, Fs, Fs, _cabi.ptr(out),
+                                      0, 0, 1 if channel_major else 0, B, N1, N2, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_upsample")
+    return out
+
+
+def upsample_bwd(approach: str, dout: torch.Tensor, idx: torch.Tensor, dist: Optional[torch.Tensor], n_coarse: int,
+                 n_feat: int, need_skip: bool = True):
+    """Backward of ``upsample``: dout (B,N2,F+Fs) -> (dfeat (B,N1,F) scatter-added, dskip (B,N2,Fs) or None)
+    (C ABI ``r3d_upsample_bwd``)."""
+    _cabi.require_cuda(dout, "dout")
+    weighting, power, idx, dist = _up_args(approach, idx, dist)
+    dout, dbs = _rows_view(dout.detach())
+    B, N2, C = dout.shape
+    F, Fs, K = n_feat, C - n_feat, idx.shape[2]
+    dev = dout.device
+    dfeat = zeros((B, n_coarse, F), torch.float32, dev)
+    dskip = torch.empty((B, N2, Fs), dtype=torch.float32, device=dev) if (need_skip and Fs) else None
+    kk = 1 if weighting == 0 else K
+    with torch.cuda.device(dev), _cabi.kernel_timer("upsample_bwd", flops=2.0 * B * N2 * F * kk,
+                                                    bytes=4.0 * B * N2 * (F * (kk + 1) + 2 * Fs + 2 * kk)):
+        rc = _cabi.lib().r3d_upsample_bwd(_cabi.raw(dout), dbs, C, _cabi.ptr(idx), int(idx.dtype == torch.int64),
+                                          _cabi.ptr(dist), K, weighting, power, _cabi.ptr(dfeat), 0, 0, F,
+                                          _cabi.ptr(dskip), 0, 0, Fs, B, n_coarse, N2, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_upsample_bwd")
+    return dfeat, dskip
+
+
 def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bias: Optional[torch.Tensor], act,
              slope: float = 0.0):
     """Train-mode BatchNorm + activation of a per-point layer (C ABI ``r3d_bn_apply``): z (M,C) conv output without

@@ -273,6 +273,45 @@ int r3d_tversky_loss_bwd(const float* logits, long long sb, long long sc, long l
 int r3d_confusion_counts(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
                          int C, int N, long long* counts, r3d_stream_t stream);
 
+/* --------------------------------------------------------------------------------- feature up-sampling
+ * randlanet/utils/modules.py:343-414 (UpSampler.nearest_neighbor_interpolation / nearest_neighbors_averaging) fused
+ * with the decoder's skip concat (:600-602):
+ *   out[b,q,0:F] = sum_k w[b,q,k] feat[b, idx[b,q,k], :],   out[b,q,F:F+Fs] = skip[b,q,:]   (skip nullable, Fs = 0)
+ * weighting 0: the first neighbour only (nni, K = 1); 1: w = (1+1e-7)/(dist^power + 1e-7) normalised over K (nna / idw
+ * power 1, isdw power 2; dist = Euclidean distances (B,N2,K), not squared); 2: plain mean over K.
+ * idx (B,N2,K) int32 or int64 (idx64 = 1) from r3d_knn; K <= 16.  feat (B,N1,F), skip (B,N2,Fs), out (B,N2,F+Fs) rows
+ * with leading dimensions *_ld and cloud strides *_bstride in floats (0 = dense).  channel_major = 1 writes (B,F,N2)
+ * instead (the layout Model.upsample returns, model.py:123-144; Fs must be 0).
+ * _bwd: dfeat (B,N1,F) += scattered w * dout[:, :, 0:F] (caller zero-fills), dskip (nullable) = dout[:, :, F:]. */
+int r3d_upsample(const float* feat, long long feat_bstride, int feat_ld, int F, const void* idx, int idx64,
+                 const float* dist, int K, int weighting, float power, const float* skip, long long skip_bstride,
+                 int skip_ld, int Fs, float* out, long long out_bstride, int out_ld, int channel_major, int B, int N1,
+                 int N2, r3d_stream_t stream);
+int r3d_upsample_bwd(const float* dout, long long dout_bstride, int dout_ld, const void* idx, int idx64,
+                     const float* dist, int K, int weighting, float power, float* dfeat, long long dfeat_bstride,
+                     int dfeat_ld, int F, float* dskip, long long dskip_bstride, int dskip_ld, int Fs, int B, int N1,
+                     int N2, r3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------- data feeding
+ * randlanet/utils/dataset.py:61-97 (PointCloudPreprocessor.preprocess) + augmentation.py:24-167, one launch per batch
+ * over clouds cached in device memory:
+ *   points (rows, ld = 3+F) fp32 and labels (rows) int64: all clouds of the dataset back to back; row_start (B) int64 =
+ *   first row of each cloud of THIS batch; sample_idx (B,n) int32 = rows within the cloud (preprocessing.py:35-62, or
+ *   r3d_sample_subset).  normalization 0 none, 1 mean, 2 max, 3 stdev, 4 centre only (dataset.py:81-92).
+ *   aug (B,7) fp32 nullable = per cloud [scale, angle_x, angle_y, angle_z, shift_x, shift_y, shift_z] as the reference
+ *   draws them (augmentation.py:73, :99-102, :154); null: no augmentation.  noise (B,n,3) fp32 nullable = standard
+ *   normals of the jitter (augmentation.py:48-52); null: Philox4x32-10 keyed by (seed, counter, cloud, point).
+ *   jitter_sigma / jitter_limit = AugmentationSettings.jitter_variance / jitter_limit.
+ *   out (B,n,ld) fp32 = [augmented xyz, features]; labels_out (B,n) int64 nullable.
+ * r3d_sample_subset: sizes (B) int32 device = points per cloud -> out (B,n) int32: a uniform random subset of n points
+ * in ascending order (N > n), or every point once followed by n - N uniform draws with replacement (N <= n). */
+int r3d_feed_batch(const float* points, int ld, const int64_t* labels, const int64_t* row_start,
+                   const int32_t* sample_idx, int n, int normalization, const float* aug, const float* noise,
+                   float jitter_sigma, float jitter_limit, unsigned long long seed, unsigned long long counter,
+                   float* out, int64_t* labels_out, int B, r3d_stream_t stream);
+int r3d_sample_subset(const int32_t* sizes, int n, unsigned long long seed, unsigned long long counter, int32_t* out,
+                      int B, r3d_stream_t stream);
+
 /* ----------------------------------------------------------------------------- per-point MLP layer
  * y[b,n,:] = act(scale * (W [xa[b, g(n), :] ; xb[b,n,:]]) + shift)
  * Replaces SharedMLP / Linear on single points (modules.py:60-104; call sites :314, :325, :253, :565-566,

@@ -262,6 +262,36 @@ def gen_loss():
     print("loss golden:", len(out), "arrays; oracle.network.dice_loss pinned against the reference's FocalTverskyLoss")
 
 
+def gen_feed():
+    """The reference's PointCloudPreprocessor (utils/dataset.py:11-97) + perturbate_point_cloud on a seeded numpy stream,
+    consistent and non-consistent sampling: every item's (input, labels); also pins oracle.feeding."""
+    import_reference()
+    from randlanet.utils.augmentation import AugmentationSettings
+    from randlanet.utils.dataset import PointCloudPreprocessor
+    from . import feeding
+    data, n = feeding.feed_dataset(), feeding.FEED_N
+    out = {}
+    for name, (norm, aug) in feeding.FEED_CASES.items():
+        for consistent in (True, False):
+            s = AugmentationSettings() if aug else None
+            pre = PointCloudPreprocessor(data, n, consistent_sampling=consistent, augmentation_settings=s,
+                                         normalization=norm)
+            np.random.seed(feeding.FEED_SEED)
+            ref = [pre[i] for i in range(len(data))]
+            np.random.seed(feeding.FEED_SEED)
+            for i, (inp, lab, idx) in enumerate(ref):
+                x, f, l2 = feeding.preprocess(*data[i], n, consistent, s, norm)
+                mine = np.concatenate((x, f), axis=1).astype(np.float32)
+                assert idx == i and np.array_equal(l2, lab.numpy())
+                assert np.abs(mine - inp.numpy()).max() < 1e-6 * np.abs(inp.numpy()).max(), (name, consistent, i)
+                out[f"{name}/{int(consistent)}/{i}/input"] = inp.numpy()
+                out[f"{name}/{int(consistent)}/{i}/labels"] = lab.numpy()
+    # (broaden_annotation lives in the top-level dataset.py, which does not import under numpy >= 1.24 — np.bool,
+    # SURVEY F11; oracle.feeding restates its ten lines and has no fixture)
+    np.savez_compressed(os.path.join(GOLD, "feed_golden.npz"), **out)
+    print("feed golden:", len(out), "arrays; oracle.feeding pinned against the reference's PointCloudPreprocessor")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     build(ref=True)
@@ -272,6 +302,7 @@ def main():
     gen_e2e(rmod)
     gen_predict(rmod)
     gen_loss()
+    gen_feed()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 
