@@ -100,12 +100,20 @@ SIGNATURES = {
                                ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_void_p,
                                c_int, c_void_p]),
     "r3d_sample_subset": (c_int, [c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_int, c_void_p]),
+    "r3d_pc_gemm_supported": (c_int, [c_int, c_int, ctypes.c_longlong]),
+    "r3d_pc_gemm": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p,
+                            ctypes.c_longlong, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
+    "r3d_pc_wgrad_supported": (c_int, [c_int, c_int, ctypes.c_longlong]),
+    "r3d_pc_wgrad": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_int,
+                             c_void_p]),
     "r3d_pointwise_bn": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int,
                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_bn_set_fused": (c_int, [c_int]),
     "r3d_bn_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, ctypes.c_float,
                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "r3d_bn_bwd_absmax": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, ctypes.c_float,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "r3d_rowreduce_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p]),
     "r3d_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_tc16_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float,

@@ -153,7 +153,7 @@ struct BnDzSmem {
 __device__ __forceinline__ void bn_bwd_dz_body(const float* __restrict__ dy, const float* __restrict__ z, long long M,
                                                int C, const float* __restrict__ save, const float* __restrict__ beta,
                                                int act, float slope, const double* stats2, float* __restrict__ dz,
-                                               float* __restrict__ dgb, BnDzSmem& S) {
+                                               float* __restrict__ dgb, BnDzSmem& S, float* absmax = nullptr) {
     float *sa = S.sa, *sm = S.sm, *sr = S.sr, *sc = S.sc, *m1 = S.m1, *m2 = S.m2;
     if (dgb && blockIdx.x == 0)
         for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) dgb[c] = (float)stats2[c];
@@ -168,6 +168,7 @@ __device__ __forceinline__ void bn_bwd_dz_body(const float* __restrict__ dy, con
     __syncthreads();
     const long long total4 = M * C / 4;
     const int c4 = C / 4;
+    float mx = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4) * 4;
         const float4 g = reinterpret_cast<const float4*>(dy)[i];
@@ -179,8 +180,14 @@ __device__ __forceinline__ void bn_bwd_dz_body(const float* __restrict__ dy, con
             const float du = gv[j] * act_grad(fmaf(zv[j], sa[c + j], sc[c + j]), act, slope);
             const float zh = (zv[j] - sm[c + j]) * sr[c + j];
             o[j] = sa[c + j] * (du - m1[c + j] - zh * m2[c + j]);
+            mx = fmaxf(mx, fabsf(o[j]));
         }
         reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (absmax) {        // max |dz|: the operand scale of the tensor-core weight-gradient kernel (r3d_pc_wgrad)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
     }
 }
 
@@ -188,9 +195,9 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const float* __restrict_
                                                         long long M, int C, const float* __restrict__ save,
                                                         const float* __restrict__ beta, int act, float slope,
                                                         const double* __restrict__ stats2, float* __restrict__ dz,
-                                                        float* __restrict__ dgb) {
+                                                        float* __restrict__ dgb, float* __restrict__ absmax) {
     __shared__ BnDzSmem S;
-    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S);
+    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S, absmax);
 }
 
 // Both passes in ONE cooperative launch with a grid barrier between them: for the layers of a small cloud each pass
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const float* __restri
                                                            long long M, int C, const float* __restrict__ save,
                                                            const float* __restrict__ beta, int act, float slope,
                                                            double* stats2, float* __restrict__ dz,
-                                                           float* __restrict__ dgb) {
+                                                           float* __restrict__ dgb, float* __restrict__ absmax) {
     __shared__ union {
         float red[2][kBnMaxC];
         BnDzSmem dzs;
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const float* __restri
     bn_bwd_reduce_body(dy, z, M, C, save, beta, act, slope, stats2, S.red);
     __threadfence();
     cooperative_groups::this_grid().sync();
-    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S.dzs);
+    bn_bwd_dz_body(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, S.dzs, absmax);
 }
 
 // ------------------------------------------------------------------------------------ rowreduce_gemm
@@ -590,17 +597,23 @@ extern "C" int r3d_bn_bwd_reduce(const float* dy, const float* z, long long M, i
     return R3D_OK;
 }
 
-extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
-                             int act, float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
+static int bn_bwd_dz_launch(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                            int act, float slope, const double* stats2, float* dz, float* dgb, float* absmax,
+                            r3d_stream_t stream) {
     if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
     if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
     if (M == 0) return R3D_OK;
     if (!dy || !z || !save || !beta || !stats2 || !dz) return R3D_EINVAL;
     if (!is_aligned(dy, 16) || !is_aligned(z, 16) || !is_aligned(dz, 16)) return R3D_EALIGN;
     bn_bwd_dz_kernel<<<grid_for(M * C / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, z, M, C, save, beta, act,
-                                                                                             slope, stats2, dz, dgb);
+                                                                                             slope, stats2, dz, dgb, absmax);
     R3D_LAUNCH_CHECK("bn_bwd_dz_kernel");
     return R3D_OK;
+}
+
+extern "C" int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                             int act, float slope, const double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
+    return bn_bwd_dz_launch(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, nullptr, stream);
 }
 
 // Single-launch (cooperative, grid barrier) variants of the train-mode BatchNorm: bit 0 forward (r3d_pointwise_bn),
@@ -615,8 +628,10 @@ extern "C" int r3d_bn_set_fused(int mask) {
     return g_bn_fused.exchange(mask);
 }
 
-extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
-                          int act, float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
+// r3d_bn_bwd + absmax_dz (nullable; caller-zeroed device scalar) = atomic max with max |dz|
+extern "C" int r3d_bn_bwd_absmax(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                                 int act, float slope, double* stats2, float* dz, float* dgb, float* absmax_dz,
+                                 r3d_stream_t stream) {
     if (M < 0 || C <= 0 || act < 0 || act > 2) return R3D_EINVAL;
     if (C > kBnMaxC || (C % 4) != 0) return R3D_EUNSUPPORTED;
     if (M == 0) return R3D_OK;
@@ -645,13 +660,18 @@ extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, c
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel, dy, z, M, C, save, beta, act, slope, stats2, dz, dgb));
+        R3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel, dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, absmax_dz));
         R3D_LAUNCH_CHECK("bn_bwd_fused_kernel");
         return R3D_OK;
     }
     int rc = r3d_bn_bwd_reduce(dy, z, M, C, save, beta, act, slope, stats2, stream);
     if (rc != R3D_OK) return rc;
-    return r3d_bn_bwd_dz(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, stream);
+    return bn_bwd_dz_launch(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, absmax_dz, stream);
+}
+
+extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta,
+                          int act, float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream) {
+    return r3d_bn_bwd_absmax(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, nullptr, stream);
 }
 
 extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,

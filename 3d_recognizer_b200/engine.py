@@ -116,10 +116,20 @@ class _SharedMLPTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, gamma, beta, bn, act, slope):
         x = x.contiguous()
-        cout = w.shape[0]
+        cout, cin = w.shape
+        M = x.shape[0]
         scratch = ops.zeros(4 * cout, torch.float64, x.device)   # forward stats | backward stats
         stats = scratch[:2 * cout]
-        z, y, save = ops.pointwise_bn(x, w.contiguous(), stats, bn, bias, act, slope)
+        # operand scales of the tensor-core weight-gradient kernel: [0] max |x| (written by the forward GEMM when it
+        # runs on the tensor cores), [1] max |dz| (written by the BatchNorm backward)
+        ctx.absmax = ops.zeros((2,), torch.float32, x.device) if ops.pc_wgrad_ok(M, cout, cin) else None
+        if ops.pc_gemm_ok(M, cin, cout):
+            ctx.absmax_x_known = ctx.absmax is not None
+            z = ops.pc_gemm(x, w.contiguous(), stats=stats, absmax_out=None if ctx.absmax is None else ctx.absmax[0:1])
+            y, save = ops.bn_apply(z, stats, bn, bias, act, slope)
+        else:
+            ctx.absmax_x_known = False
+            z, y, save = ops.pointwise_bn(x, w.contiguous(), stats, bn, bias, act, slope)
         ctx.act, ctx.slope = act, slope
         ctx.save_for_backward(x, w, z, save, beta, scratch)
         return y
@@ -128,16 +138,30 @@ class _SharedMLPTrainFn(torch.autograd.Function):
     def backward(ctx, dy):
         _once(ctx, "SharedMLP")
         x, w, z, save, beta, scratch = ctx.saved_tensors
-        cout = w.shape[0]
-        dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope, stats2=scratch[2 * cout:])
+        cout, cin = w.shape
+        M = x.shape[0]
+        am = ctx.absmax
+        dz, dgamma, dbeta = ops.bn_backward(dy, z, save, beta, ctx.act, ctx.slope, stats2=scratch[2 * cout:],
+                                            absmax_out=None if am is None else am[1:2])
+
+        def weight_grad():
+            if am is None:
+                return ops.rowreduce_gemm(dz, x)
+            return ops.pc_wgrad(dz, x, am[1:2], am[0:1] if ctx.absmax_x_known else None)
+
+        def input_grad():
+            if ops.pc_gemm_ok(M, cout, cin):
+                return ops.pc_gemm(dz, w.contiguous(), transposed=True)
+            return ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0)
+
         if OVERLAP_WEIGHT_GRADS and ctx.needs_input_grad[0]:
             with _fork(dz.device) as f:
-                dw = ops.rowreduce_gemm(dz, x)
-            dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0)
+                dw = weight_grad()
+            dx = input_grad()
             f.join()
         else:
-            dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
-            dw = ops.rowreduce_gemm(dz, x)
+            dx = input_grad() if ctx.needs_input_grad[0] else None
+            dw = weight_grad()
         # the conv bias cancels against the batch mean: its gradient is exactly zero and is reported as None (the
         # optimiser then leaves the parameter alone, which is what a zero gradient does)
         return dx, dw, None, dgamma, dbeta, None, None, None

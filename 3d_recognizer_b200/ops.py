@@ -380,6 +380,70 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
     return out
 
 
+# Per-point layers on the tensor cores (csrc/pw_cl.cu).  Measured against the FP32 kernels on the train40960 shapes
+# (tools/pw_cl_bench.py): ahead wherever both widths reach 32 (1.5x at 2.6 M rows x 32<->64, 2-3.5x on the mid-width layers
+# of levels 1-3 and the decoder); narrower layers are bound by memory traffic and stay on pw_rows / rowreduce_gemm_narrow.
+PC_MIN_ROWS = 8192
+
+
+def pc_gemm_ok(M: int, cin: int, cout: int) -> bool:
+    return (USE_TENSOR_CORES and M >= PC_MIN_ROWS and cin % 16 == 0 and 32 <= cin <= 128 and cout >= 32
+            and cin + cout >= 96)
+
+
+def pc_wgrad_ok(M: int, ca: int, cb: int) -> bool:
+    return (USE_TENSOR_CORES and M >= PC_MIN_ROWS and ca % 8 == 0 and cb % 8 == 0 and max(ca, cb) >= 64
+            and min(ca, cb) >= 32)
+
+
+def pc_gemm(x: torch.Tensor, w: torch.Tensor, transposed: bool = False, scale=None, shift=None, act=None,
+            slope: float = 0.0, stats: Optional[torch.Tensor] = None, absmax_out: Optional[torch.Tensor] = None
+            ) -> torch.Tensor:
+    """Per-point layer on the tensor cores (C ABI ``r3d_pc_gemm``): x (M,cin) dense rows, w the layer's (cout,cin)
+    weight -> act(scale * (x w^T) + shift) (M,cout); ``transposed``: the input gradient x (M,cout) -> x w (M,cin).
+    ``stats`` (2*channels fp64, zero-filled) += batch sums of x w^T and its square; ``absmax_out`` (1,) fp32 zero-filled
+    receives max |x| (the weight-gradient kernel's operand scale)."""
+    _cabi.require_cuda(x, "x")
+    assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous()
+    M, cin = x.shape
+    cout = w.shape[1] if transposed else w.shape[0]
+    assert (w.shape[0] if transposed else w.shape[1]) == cin
+    so, si = (1, w.shape[1]) if transposed else (w.shape[1], 1)
+    y = torch.empty((M, cout), dtype=torch.float32, device=x.device)
+    name = f"pc_gemm[M={M},{cin}->{cout}]" if _cabi.TIMER_SHAPES else "pc_gemm"
+    with torch.cuda.device(x.device), _cabi.kernel_timer(name, flops=2.0 * M * cin * cout, bytes=4.0 * M * (cin + cout)):
+        rc = _cabi.lib().r3d_pc_gemm(_cabi.raw(x.detach()), x.stride(0), _cabi.ptr(w.detach()), so, si, _cabi.ptr(scale),
+                                     _cabi.ptr(shift), _ACT[act], float(slope), _cabi.ptr(y), cout, _cabi.ptr(stats),
+                                     _cabi.ptr(absmax_out), M, cin, cout, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "r3d_pc_gemm")
+    return y
+
+
+def pc_wgrad(a: torch.Tensor, b: torch.Tensor, absmax_a: Optional[torch.Tensor] = None,
+             absmax_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a (M,Ca), b (M,Cb) dense rows -> a^T b (Ca,Cb) on the tensor cores (C ABI ``r3d_pc_wgrad``).  absmax_*: (1,) fp32
+    device bounds of |a|, |b|; computed here (``r3d_absmax``) when not supplied by the tensors' producers."""
+    _cabi.require_cuda(a, "a")
+    a, b = a.contiguous(), b.contiguous()
+    M, Ca = a.shape
+    Cb = b.shape[1]
+    if absmax_a is None or absmax_b is None:
+        slots = zeros((2,), torch.float32, a.device)
+        if absmax_a is None:
+            absmax_a = slots[0:1]
+            _absmax_into(a, absmax_a)
+        if absmax_b is None:
+            absmax_b = slots[1:2]
+            _absmax_into(b, absmax_b)
+    out = zeros((Ca, Cb), torch.float32, a.device)
+    name = f"pc_wgrad[M={M},{Ca}x{Cb}]" if _cabi.TIMER_SHAPES else "pc_wgrad"
+    with torch.cuda.device(a.device), _cabi.kernel_timer(name, flops=2.0 * M * Ca * Cb, bytes=4.0 * M * (Ca + Cb)):
+        rc = _cabi.lib().r3d_pc_wgrad(_cabi.ptr(a), Ca, Ca, _cabi.ptr(b), Cb, Cb, M, _cabi.raw(absmax_a), _cabi.raw(absmax_b),
+                                      _cabi.ptr(out), Cb, _cabi.stream_ptr(a.device))
+    _cabi.check(rc, "r3d_pc_wgrad")
+    return out
+
+
 UP_WEIGHTING = {"nni": (0, 1.0), "nna": (1, 1.0), "idw": (1, 1.0), "isdw": (1, 2.0), "mean": (2, 1.0)}
 
 
@@ -503,11 +567,12 @@ def pointwise_bn(x: torch.Tensor, w: torch.Tensor, stats: torch.Tensor, bn: torc
 
 
 def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0,
-                stats2: Optional[torch.Tensor] = None):
-    """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd``: the reduce and dz passes, one
+                stats2: Optional[torch.Tensor] = None, absmax_out: Optional[torch.Tensor] = None):
+    """BatchNorm(+activation) backward with batch statistics (C ABI ``r3d_bn_bwd_absmax``: the reduce and dz passes, one
     cooperative launch for small tensors).
     ``stats2``: optional zero-filled (2C) fp64 scratch (the forward allocates it together with its own statistics
-    buffer: one fill instead of two).  Returns (dz (M,C), dgamma (C), dbeta (C))."""
+    buffer: one fill instead of two); ``absmax_out``: optional zero-filled (1,) fp32 that receives max |dz|.
+    Returns (dz (M,C), dgamma (C), dbeta (C))."""
     M, C = z.shape
     dy = dy.contiguous()
     if stats2 is None:
@@ -516,8 +581,9 @@ def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: tor
     s2 = torch.empty(2 * C, dtype=torch.float32, device=z.device)
     L = _cabi.lib()
     with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_backward[M={M},C={C}]", flops=12.0 * M * C, bytes=20.0 * M * C):
-        rc = L.r3d_bn_bwd(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act], float(slope),
-                          _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.ptr(s2), _cabi.stream_ptr(z.device))
+        rc = L.r3d_bn_bwd_absmax(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act],
+                                 float(slope), _cabi.ptr(stats2), _cabi.ptr(dz), _cabi.ptr(s2), _cabi.raw(absmax_out),
+                                 _cabi.stream_ptr(z.device))
     _cabi.check(rc, "r3d_bn_bwd")
     return dz, s2[C:], s2[:C]
 

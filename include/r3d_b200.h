@@ -273,6 +273,25 @@ int r3d_tversky_loss_bwd(const float* logits, long long sb, long long sc, long l
 int r3d_confusion_counts(const float* logits, long long sb, long long sc, long long sn, const int64_t* labels, int B,
                          int C, int N, long long* counts, r3d_stream_t stream);
 
+/* ------------------------------------------------------- per-point layers on the tensor cores (training)
+ * SharedMLP's 1x1 convolution (randlanet/utils/modules.py:60-104) on dense rows, tcgen05 with split-fp16 operands
+ * (fp32-accurate: ~1e-6 relative), for the mid-width layers of the training step:
+ *   r3d_pc_gemm    y (M,cout; ldy) = act(scale * (x W^T) + shift), x (M,cin; ldx), element (o,i) of W at
+ *                  w[o*w_so + i*w_si] (forward: the (cout,cin) weight, strides (cin,1); input gradient: the same
+ *                  array with strides (1,cout_layer)); stats (2 cout fp64, nullable, caller-zeroed) += per-channel sums
+ *                  of x W^T and of its square; absmax_x (nullable) = atomic max with max |x|.  cin % 16 == 0, cin <= 128.
+ *   r3d_pc_wgrad   out (ca,cb; ld_out; caller-zeroed) += A^T B, A (M,ca; lda), B (M,cb; ldb) like r3d_rowreduce_gemm;
+ *                  absmax_a / absmax_b: device scalars that bound |A|, |B| (r3d_absmax, or absmax_x of r3d_pc_gemm).
+ *                  ca, cb multiples of 8.
+ * *_supported return 1 when the shape is served (else the calls return R3D_EUNSUPPORTED). */
+int r3d_pc_gemm_supported(int cin, int cout, long long M);
+int r3d_pc_gemm(const float* x, long long ldx, const float* w, long long w_so, long long w_si, const float* scale,
+                const float* shift, int act, float slope, float* y, long long ldy, double* stats, float* absmax_x,
+                long long M, int cin, int cout, r3d_stream_t stream);
+int r3d_pc_wgrad_supported(int ca, int cb, long long M);
+int r3d_pc_wgrad(const float* A, long long lda, int ca, const float* Bm, long long ldb, int cb, long long M,
+                 const float* absmax_a, const float* absmax_b, float* out, int ld_out, r3d_stream_t stream);
+
 /* --------------------------------------------------------------------------------- feature up-sampling
  * randlanet/utils/modules.py:343-414 (UpSampler.nearest_neighbor_interpolation / nearest_neighbors_averaging) fused
  * with the decoder's skip concat (:600-602):
@@ -376,6 +395,10 @@ int r3d_bn_bwd_dz(const float* dy, const float* z, long long M, int C, const flo
  * barrier between the passes while the tensor is small (M*C <= 4 Mi elements).  Same arguments and results. */
 int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
                float slope, double* stats2, float* dz, float* dgb, r3d_stream_t stream);
+/* r3d_bn_bwd that also reports max |dz|: absmax_dz (nullable, caller-zeroed device scalar) = atomic max.  The operand
+ * scale of r3d_pc_wgrad. */
+int r3d_bn_bwd_absmax(const float* dy, const float* z, long long M, int C, const float* save, const float* beta, int act,
+                      float slope, double* stats2, float* dz, float* dgb, float* absmax_dz, r3d_stream_t stream);
 /* Weight gradient of a per-point layer: out (Ca,Cb; ld_out, caller-zeroed) += A^T B for A (M,Ca), B (M,Cb). */
 int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
                        r3d_stream_t stream);
