@@ -68,6 +68,7 @@ struct PcGemmArgs {
     long long ldy;
     double* stats;           // (2 cout) += sum y, sum y^2 (before scale / shift / act: the conv output), nullable
     float* absmax_x;         // += max |x| (atomic max), nullable
+    int accumulate;          // 1: y holds the partial sum of earlier input-channel blocks; add it before the epilogue
     long long M;
     int cin, cout;
     long long nstages;       // ceil(M / 64)
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(NSETS * kPcLoaders + 32, NSETS == 1 ? 2 : 1) p
                 const long long row = row0 + j;
                 float v = __uint_as_float(j < 16 ? r0[j & 15] : r1[j & 15]) * (inv_row[j] * inv_sw);
                 if (row < a.M && oc_ok) {
+                    if (a.accumulate) v += a.y[row * a.ldy + oc];
                     ps1 += v;
                     ps2 = fmaf(v, v, ps2);
                     v = fmaf(v, e_scale, e_shift);
@@ -461,9 +463,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_wgrad_kernel(PcWgradArgs a) 
 using namespace r3d;
 
 extern "C" int r3d_pc_gemm_supported(int cin, int cout, long long M) {
-    return cin >= 16 && cin <= 128 && cin % 16 == 0 && cout >= 8 && M >= 1;
+    return cin >= 16 && cin <= 4096 && cin % 16 == 0 && cout >= 8 && M >= 1;
 }
 
+// one launch per block of <= 128 input channels (the weight image of a block stays in shared memory); later blocks add
+// to the partial sums in y, the last one applies statistics / affine / activation
 extern "C" int r3d_pc_gemm(const float* x, long long ldx, const float* w, long long w_so, long long w_si, const float* scale,
                            const float* shift, int act, float slope, float* y, long long ldy, double* stats,
                            float* absmax_x, long long M, int cin, int cout, r3d_stream_t stream) {
@@ -474,22 +478,27 @@ extern "C" int r3d_pc_gemm(const float* x, long long ldx, const float* w, long l
     if (ldx == 0) ldx = cin;
     if (ldy == 0) ldy = cout;
     if (!is_aligned(x, 16) || ldx % 4 != 0) return R3D_EALIGN;
-    PcGemmArgs a{x, ldx, w, w_so, w_si, scale, shift, act, slope, y, ldy, stats, absmax_x, M, cin, cout,
-                 (M + kPcRows - 1) / kPcRows};
     const int tiles_o = (cout + 127) / 128;
-    const int per_sm = PcGemmSmem(cin).bytes <= 110 * 1024 ? 2 : 1;      // two CTAs of 8 loader warps, or one of 16
-    long long gx = (long long)per_sm * kNumSMs / tiles_o;
-    if (gx < 1) gx = 1;
-    if (gx > a.nstages) gx = a.nstages;
-    const PcGemmSmem L(cin);
-    if (per_sm == 2) {
-        R3D_CUDA_TRY(cudaFuncSetAttribute(pc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcGemmSmem(128).bytes));
-        pc_gemm_kernel<1><<<dim3((unsigned)gx, (unsigned)tiles_o), kPcLoaders + 32, L.bytes, static_cast<cudaStream_t>(stream)>>>(a);
-    } else {
-        R3D_CUDA_TRY(cudaFuncSetAttribute(pc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcGemmSmem(128).bytes));
-        pc_gemm_kernel<2><<<dim3((unsigned)gx, (unsigned)tiles_o), 2 * kPcLoaders + 32, L.bytes, static_cast<cudaStream_t>(stream)>>>(a);
+    for (int k0 = 0; k0 < cin; k0 += 128) {
+        const int kc = cin - k0 < 128 ? cin - k0 : 128;
+        const bool last = k0 + kc >= cin;
+        PcGemmArgs a{x + k0, ldx, w + (long long)k0 * w_si, w_so, w_si, last ? scale : nullptr, last ? shift : nullptr,
+                     last ? act : 0, slope, y, ldy, last ? stats : nullptr, absmax_x, k0 > 0 ? 1 : 0, M, kc, cout,
+                     (M + kPcRows - 1) / kPcRows};
+        const PcGemmSmem L(kc);
+        const int per_sm = L.bytes <= 110 * 1024 ? 2 : 1;      // two CTAs of 8 loader warps, or one of 16
+        long long gx = (long long)per_sm * kNumSMs / tiles_o;
+        if (gx < 1) gx = 1;
+        if (gx > a.nstages) gx = a.nstages;
+        if (per_sm == 2) {
+            R3D_CUDA_TRY(cudaFuncSetAttribute(pc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcGemmSmem(128).bytes));
+            pc_gemm_kernel<1><<<dim3((unsigned)gx, (unsigned)tiles_o), kPcLoaders + 32, L.bytes, static_cast<cudaStream_t>(stream)>>>(a);
+        } else {
+            R3D_CUDA_TRY(cudaFuncSetAttribute(pc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcGemmSmem(128).bytes));
+            pc_gemm_kernel<2><<<dim3((unsigned)gx, (unsigned)tiles_o), 2 * kPcLoaders + 32, L.bytes, static_cast<cudaStream_t>(stream)>>>(a);
+        }
+        R3D_LAUNCH_CHECK("pc_gemm_kernel");
     }
-    R3D_LAUNCH_CHECK("pc_gemm_kernel");
     return R3D_OK;
 }
 

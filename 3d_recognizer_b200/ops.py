@@ -253,6 +253,8 @@ def lfa_r2_rows(xyz, xs, idx32, w_rpe1, a_rpe1, b_rpe1, w_rpe2, a_rpe2, b_rpe2) 
         rc = _cabi.lib().r3d_lfa_r1_rows(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(w_rpe1), _cabi.ptr(a_rpe1),
                                          _cabi.ptr(b_rpe1), _cabi.ptr(r1), B, N, K, h, _cabi.stream_ptr(dev))
     _cabi.check(rc, "r3d_lfa_r1_rows")
+    if pc_gemm_ok(rows, h, h):
+        return pc_gemm(r1, w_rpe2.contiguous(), scale=a_rpe2, shift=b_rpe2, act="relu")
     return pointwise(r1.unsqueeze(0), w_rpe2.contiguous(), a_rpe2, b_rpe2, act="relu", w_out_in=True).squeeze(0)
 
 
@@ -383,6 +385,8 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
 # Per-point layers on the tensor cores (csrc/pw_cl.cu).  Measured against the FP32 kernels on the train40960 shapes
 # (tools/pw_cl_bench.py): ahead wherever both widths reach 32 (1.5x at 2.6 M rows x 32<->64, 2-3.5x on the mid-width layers
 # of levels 1-3 and the decoder); narrower layers are bound by memory traffic and stay on pw_rows / rowreduce_gemm_narrow.
+# C_in > 128 runs as one pass per 128-channel block with read-modify-write of y: correct (tested) but slower than pw_tc
+# on the decoder's 256...1024-channel inputs, so the dispatch stops at 128.
 PC_MIN_ROWS = 8192
 
 

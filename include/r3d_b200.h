@@ -279,7 +279,8 @@ int r3d_confusion_counts(const float* logits, long long sb, long long sc, long l
  *   r3d_pc_gemm    y (M,cout; ldy) = act(scale * (x W^T) + shift), x (M,cin; ldx), element (o,i) of W at
  *                  w[o*w_so + i*w_si] (forward: the (cout,cin) weight, strides (cin,1); input gradient: the same
  *                  array with strides (1,cout_layer)); stats (2 cout fp64, nullable, caller-zeroed) += per-channel sums
- *                  of x W^T and of its square; absmax_x (nullable) = atomic max with max |x|.  cin % 16 == 0, cin <= 128.
+ *                  of x W^T and of its square; absmax_x (nullable) = atomic max with max |x|.  cin % 16 == 0; one launch per block
+ *                  of 128 input channels (later blocks add to the partial sums in y).
  *   r3d_pc_wgrad   out (ca,cb; ld_out; caller-zeroed) += A^T B, A (M,ca; lda), B (M,cb; ldb) like r3d_rowreduce_gemm;
  *                  absmax_a / absmax_b: device scalars that bound |A|, |B| (r3d_absmax, or absmax_x of r3d_pc_gemm).
  *                  ca, cb multiples of 8.

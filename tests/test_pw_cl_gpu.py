@@ -20,7 +20,8 @@ def _err(got, ref):
 
 
 @pytest.mark.parametrize("M,cin,cout", [(655360, 64, 128), (163840, 128, 256), (40960, 128, 512), (70001, 32, 64),
-                                        (130, 48, 40), (64, 16, 8), (20000, 128, 32), (9999, 96, 200)])
+                                        (130, 48, 40), (64, 16, 8), (20000, 128, 32), (9999, 96, 200),
+                                        (40960, 1024, 256), (40960, 256, 512), (163840, 512, 128), (5000, 272, 72)])
 @pytest.mark.parametrize("transposed", [False, True])
 def test_pc_gemm_vs_fp64(ops, M, cin, cout, transposed):
     g = torch.Generator(device="cuda").manual_seed(M + cin)

@@ -25,7 +25,8 @@ def timeit(fn, n=10):
 
 GEMM = [(655360, 32, 128), (655360, 64, 64), (655360, 64, 128), (655360, 128, 128), (655360, 128, 64), (655360, 32, 256),
         (163840, 128, 256), (163840, 128, 512), (163840, 128, 128), (163840, 64, 128), (40960, 128, 256),
-        (2621440, 32, 64), (2621440, 64, 32), (2621440, 16, 32)]
+        (2621440, 32, 64), (2621440, 64, 32), (2621440, 16, 32), (40960, 256, 512), (40960, 1024, 256), (655360, 256, 32),
+        (163840, 512, 128), (40960, 512, 256), (40960, 256, 256), (163840, 256, 128), (40960, 256, 1024), (10240, 512, 512)]
 WGRAD = [(40960, 256, 1024), (163840, 256, 128), (40960, 512, 256), (163840, 128, 512), (655360, 32, 256),
          (655360, 128, 64), (655360, 128, 32), (40960, 128, 256), (10240, 512, 512), (163840, 128, 128),
          (655360, 64, 64), (2621440, 32, 64), (2621440, 8, 64), (2621440, 16, 16)]
