@@ -29,6 +29,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <math_constants.h>
 
 namespace r3d {
@@ -36,7 +37,7 @@ namespace r3d {
 constexpr int kKnnThreads = 256;
 constexpr int kTile = 1024;  // support points per smem stage (3 rows x 4 KB)
 
-static std::atomic<int> g_knn_variant{2};
+static std::atomic<int> g_knn_variant{3};   // 3 = dot-form prefilter + warp-cooperative admission (K = 16, 32), else 2
 static std::atomic<int> g_knn_algorithm{0};  // 0 auto, 1 tiled brute force, 2 uniform grid
 
 // knn_grid.cu
@@ -308,6 +309,215 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_kernel(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------ VARIANT 3: dot-form prefilter
+// The prefilter only has to be CONSERVATIVE, not accurate, so it can use the cheapest form there is:
+//     |q - s|^2 - |q|^2 = |s|^2 - 2 q.s            3 FMAs per pair (6 FP32-pipe operations in the difference form)
+// on coordinates taken relative to the cloud's first point (so that |q|, |s| are of the size of the cloud, not of its
+// distance from the origin).  The pack kernel stores (-2 s~, |s~|^2) as four rows; a thread compares the minimum over 4
+// points with  tq = thr (1 + 2^-20) + 2^-18 (|q~|^2 + max|s~|^2) - |q~|^2, which bounds every rounding error of the form
+// (centring 2^-24 relative per coordinate, |s~|^2, |q~|^2 and the FMA chain < 2^-19 (|q~|^2 + |s~|^2) together; derivation
+// in DESIGN.md §4.1).  Survivors are re-evaluated with the contract arithmetic on the ORIGINAL coordinates, so the
+// results are bit-identical to variant 0.
+// The admission itself is WARP-COOPERATIVE: a per-lane branch made the whole warp wait for one lane's insertion chain
+// (ncu: 21 of 32 lanes active on average).  Here the warp ballots the prefilter and serves the hit lanes one after the
+// other with all 32 lanes: lanes 0-3 evaluate the contract d2 of the group's four points, and the insertion into the hit
+// lane's list (row-major [query][K+1] in shared memory: conflict-free for both the owner and the warp) is one
+// compare + ballot + shifted store.
+__global__ void xyz_to_dot_kernel(const float* __restrict__ xyz, long long batch_stride, float* __restrict__ soa,
+                                  float* __restrict__ s2max, int N, int Np) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* cloud = xyz + (size_t)b * batch_stride;
+    const float cx = cloud[0], cy = cloud[1], cz = cloud[2];
+    float x = 0.f, y = 0.f, z = 0.f, w = CUDART_INF_F;
+    if (i < N) {
+        const float* p = cloud + (size_t)i * 3;
+        const float sx = p[0] - cx, sy = p[1] - cy, sz = p[2] - cz;
+        x = -2.f * sx, y = -2.f * sy, z = -2.f * sz;
+        w = fminf(fmaf(sz, sz, fmaf(sy, sy, sx * sx)), 3.0e38f);
+    }
+    if (i < Np) {
+        float* row = soa + (size_t)b * 4 * Np;
+        row[i] = x, row[Np + i] = y, row[2 * Np + i] = z, row[3 * Np + i] = w;
+    }
+    float m = i < N ? w : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(s2max + b), __float_as_int(m));
+}
+
+template <int Q, int KT, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
+    knn_dot_kernel(const float* __restrict__ soa, int Nsp, const float* __restrict__ s2max,
+                   const float* __restrict__ support, long long s_stride, const float* __restrict__ query,
+                   long long q_stride, int Ns, int Nq, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32,
+                   float* __restrict__ dist, float* __restrict__ dist_sq) {
+    constexpr int KP = KT + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);                         // [2][4][kTile]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * 4 * kTile * sizeof(float));
+    float* list_d = reinterpret_cast<float*>(smem_raw + 2 * 4 * kTile * sizeof(float) + 16);   // [Q][threads][KP]
+    int* list_i = reinterpret_cast<int*>(list_d + (size_t)KP * Q * NT);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.y;
+    const float* rows = soa + (size_t)b * 4 * Nsp;
+    const float* sup = support + (size_t)b * s_stride;
+    const int num_tiles = (Ns + kTile - 1) / kTile;
+    constexpr int stride = Q * NT;
+
+    auto issue = [&](int t) {
+        const int s = t & 1;
+        const int n = min(kTile, Ns - t * kTile);
+        const uint32_t bytes = (uint32_t)((n + 3) & ~3) * sizeof(float);
+        mbar_expect_tx(&bars[s], 4 * bytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            tma_bulk_g2s(tile + (s * 4 + c) * kTile, rows + (size_t)c * Nsp + (size_t)t * kTile, bytes, &bars[s]);
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (num_tiles > 1) issue(1);
+    }
+
+    const float cx = sup[0], cy = sup[1], cz = sup[2];
+    const float smax = s2max[b];
+    float qx[Q], qy[Q], qz[Q], thr[Q], tq[Q], off[Q];      // off = 2^-18 (|q~|^2 + max|s~|^2) - |q~|^2
+    uint64_t qxx[Q], qyy[Q], qzz[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        int qi = blockIdx.x * stride + q * NT + tid;
+        qi = min(qi, Nq - 1);
+        const float* p = query + (size_t)b * q_stride + (size_t)qi * 3;
+        qx[q] = p[0], qy[q] = p[1], qz[q] = p[2];
+        const float ux = qx[q] - cx, uy = qy[q] - cy, uz = qz[q] - cz;
+        const float q2 = fmaf(uz, uz, fmaf(uy, uy, ux * ux));
+        off[q] = fmaf(0x1p-18f, q2 + smax, -q2);
+        qxx[q] = pk2(ux, ux), qyy[q] = pk2(uy, uy), qzz[q] = pk2(uz, uz);
+        thr[q] = CUDART_INF_F;
+        tq[q] = CUDART_INF_F;
+        float* cd = list_d + (size_t)(q * NT + tid) * KP;
+        int* ci = list_i + (size_t)(q * NT + tid) * KP;
+        for (int k = 0; k < KT; ++k) cd[k] = CUDART_INF_F, ci[k] = -1;
+    }
+    __syncwarp();
+
+    for (int t = 0; t < num_tiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&bars[s], (t >> 1) & 1);
+        const float* xs = tile + (s * 4 + 0) * kTile;
+        const float* ys = tile + (s * 4 + 1) * kTile;
+        const float* zs = tile + (s * 4 + 2) * kTile;
+        const float* ws = tile + (s * 4 + 3) * kTile;
+        const int n = min(kTile, Ns - t * kTile);
+        const int n4 = (n + 3) & ~3;
+        const int base = t * kTile;
+
+        // G groups of 4 points x Q queries per iteration in ONE straight-line block — 2 G Q = 8 independent FMA chains —
+        // followed by a single warp vote: a vote + branch per group and query serialised the chains (measured: 40 % of
+        // the issue slots used, no faster than the difference form)
+        constexpr int G = Q == 1 ? 4 : 2;
+        for (int j = 0; j < n4; j += 4 * G) {
+            float m[Q][G];
+            bool any = false;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs + j + 4 * g);
+                const float4 y4 = *reinterpret_cast<const float4*>(ys + j + 4 * g);
+                const float4 z4 = *reinterpret_cast<const float4*>(zs + j + 4 * g);
+                float4 w4 = *reinterpret_cast<const float4*>(ws + j + 4 * g);
+                if (g >= 1 && j + 4 * g >= n4) w4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+                const uint64_t x01 = pk2(x4.x, x4.y), x23 = pk2(x4.z, x4.w), y01 = pk2(y4.x, y4.y), y23 = pk2(y4.z, y4.w);
+                const uint64_t z01 = pk2(z4.x, z4.y), z23 = pk2(z4.z, z4.w), w01 = pk2(w4.x, w4.y), w23 = pk2(w4.z, w4.w);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const uint64_t a01 = fma2(qzz[q], z01, fma2(qyy[q], y01, fma2(qxx[q], x01, w01)));
+                    const uint64_t a23 = fma2(qzz[q], z23, fma2(qyy[q], y23, fma2(qxx[q], x23, w23)));
+                    float a0, a1, a2, a3;
+                    upk2(a01, a0, a1);
+                    upk2(a23, a2, a3);
+                    m[q][g] = min3(fminf(a0, a1), a2, a3);
+                    any |= m[q][g] < tq[q];
+                }
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    unsigned hits = __ballot_sync(0xffffffffu, m[q][g] < tq[q]);
+                    if (!hits) continue;
+                    const int jg = j + 4 * g;
+                    // contract d2 of the group's four points, for whichever lane is being served: lanes 0-3 hold the points
+                    float px = 0.f, py = 0.f, pz = 0.f;
+                    const int cand = base + jg + (lane & 3);
+                    const bool cand_ok = cand < Ns;
+                    if (lane < 4 && cand_ok) {
+                        const float* p = sup + (size_t)cand * 3;
+                        px = p[0], py = p[1], pz = p[2];
+                    }
+                    while (hits) {
+                        const int L = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float lx = __shfl_sync(0xffffffffu, qx[q], L), ly = __shfl_sync(0xffffffffu, qy[q], L);
+                        const float lz = __shfl_sync(0xffffffffu, qz[q], L);
+                        float lthr = __shfl_sync(0xffffffffu, thr[q], L);
+                        const float dc = (lane < 4 && cand_ok) ? d2_contract(lx, ly, lz, px, py, pz) : CUDART_INF_F;
+                        float* cd = list_d + (size_t)(q * NT + (tid - lane + L)) * KP;
+                        int* ci = list_i + (size_t)(q * NT + (tid - lane + L)) * KP;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float d = __shfl_sync(0xffffffffu, dc, u);
+                            if (d < lthr) {                                   // warp-uniform
+                                const float vd = lane < KT ? cd[lane] : CUDART_INF_F;
+                                const int vi = lane < KT ? ci[lane] : -1;
+                                // the list is ascending: the entries <= d are a prefix (an equal d2 keeps the lower index first)
+                                const int pos = __popc(__ballot_sync(0xffffffffu, lane < KT && vd <= d));
+                                __syncwarp();
+                                if (lane >= pos && lane + 1 < KT) cd[lane + 1] = vd, ci[lane + 1] = vi;
+                                if (lane == pos) cd[pos] = d, ci[pos] = base + jg + u;
+                                const float prev = __shfl_sync(0xffffffffu, vd, KT >= 2 ? KT - 2 : 0);
+                                lthr = (pos == KT - 1) ? d : prev;
+                                __syncwarp();
+                            }
+                        }
+                        if (lane == L) {
+                            thr[q] = lthr;
+                            tq[q] = fmaf(lthr, 0x1p-20f, lthr) + off[q];
+                            if (!(tq[q] == tq[q])) tq[q] = CUDART_INF_F;   // inf - inf: keep everything on the exact path
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && t + 2 < num_tiles) issue(t + 2);
+    }
+
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int qi = blockIdx.x * stride + q * NT + tid;
+        if (qi >= Nq) continue;
+        const size_t o = ((size_t)b * Nq + qi) * KT;
+        const float* cd = list_d + (size_t)(q * NT + tid) * KP;
+        const int* ci = list_i + (size_t)(q * NT + tid) * KP;
+        for (int k = 0; k < KT; ++k) {
+            const float d = cd[k];
+            const int id = ci[k];
+            if (idx64) idx64[o + k] = id;
+            if (idx32) idx32[o + k] = id;
+            if (dist) dist[o + k] = __fsqrt_rn(d);
+            if (dist_sq) dist_sq[o + k] = d;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------- small clouds (Ns < 2048)
 // The down-sampled levels and the decoder of a 2 500-point cloud search 39..625 support points for a few thousand
 // queries: one thread per query leaves most SMs idle and every thread walks the whole support with a dependent
@@ -443,6 +653,20 @@ static int dispatch_q(int Q, bool k1, const float* sup_soa, int Nsp, const float
     return R3D_EINVAL;
 }
 
+template <int Q, int KT, int NT = kKnnThreads>
+static int launch_knn_dot(const float* soa, int Nsp, const float* s2max, const float* support, long long s_stride,
+                          const float* query, long long q_stride, int B, int Ns, int Nq, int64_t* idx64, int32_t* idx32,
+                          float* dist, float* dist_sq, cudaStream_t st) {
+    auto kern = knn_dot_kernel<Q, KT, NT>;
+    const size_t smem = 2 * 4 * kTile * sizeof(float) + 16 + (size_t)(KT + 1) * Q * NT * 8;
+    R3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(Nq, Q * NT), B);
+    kern<<<grid, NT, smem, st>>>(soa, Nsp, s2max, support, s_stride, query, q_stride, Ns, Nq, idx64, idx32, dist,
+                                          dist_sq);
+    R3D_LAUNCH_CHECK("knn_dot_kernel");
+    return R3D_OK;
+}
+
 static int pick_q(int B, int Nq, int K) {
     // two CTAs per SM (16 warps) hide the FP32-pipe and shared-memory latencies: K*Q*256*8 B of lists
     // + 24 KB of tiles must fit half of the 227 KB
@@ -463,13 +687,13 @@ extern "C" size_t r3d_knn_workspace_bytes(int B, int Ns, int Nq, int K) {
     (void)K;
     if (B <= 0 || Ns <= 0) return 256;
     const size_t Nsp = (size_t)((Ns + 3) & ~3);
-    const size_t brute = align_up((size_t)B * 3 * Nsp * sizeof(float), 256) + 256;
+    const size_t brute = align_up((size_t)B * 4 * Nsp * sizeof(float), 256) + align_up((size_t)B * sizeof(float), 256) + 256;
     const size_t grid = knn_grid_workspace_bytes(B, Ns, Nq > 0 ? Nq : 1) + 256;
     return brute > grid ? brute : grid;
 }
 
 extern "C" int r3d_knn_set_variant(int variant) {
-    if (variant < 0 || variant > 2) return g_knn_variant.load();
+    if (variant < 0 || variant > 3) return g_knn_variant.load();
     return g_knn_variant.exchange(variant);
 }
 
@@ -524,6 +748,24 @@ extern "C" int r3d_knn(const float* support, long long support_batch_stride, con
 
     const int Nsp = (Ns + 3) & ~3;
     float* soa = static_cast<float*>(workspace);
+    if (g_knn_variant.load() == 3 && (K == 16 || K == 32)) {
+        float* s2max = soa + align_up((size_t)B * 4 * Nsp * sizeof(float), 256) / sizeof(float);
+        R3D_CUDA_TRY(cudaMemsetAsync(s2max, 0, (size_t)B * sizeof(float), st));
+        dim3 grid(ceil_div(Nsp, 256), B);
+        xyz_to_dot_kernel<<<grid, 256, 0, st>>>(support, support_batch_stride, soa, s2max, Ns, Nsp);
+        R3D_LAUNCH_CHECK("xyz_to_dot_kernel");
+        int Q = pick_q(B, Nq, K);
+        if (const char* e = getenv("R3D_KNN_DOT_Q")) Q = atoi(e);       // tuning hook (tools/knn_bench.py)
+#define R3D_DOT_ARGS soa, Nsp, s2max, support, support_batch_stride, query, query_batch_stride, B, Ns, Nq, idx64, idx32, dist, dist_sq, st
+        if (K == 32) {
+            if (Q >= 2) return launch_knn_dot<2, 32>(R3D_DOT_ARGS);
+            return launch_knn_dot<1, 32>(R3D_DOT_ARGS);
+        }
+        if (Q >= 4) return launch_knn_dot<4, 16>(R3D_DOT_ARGS);
+        if (Q >= 2) return launch_knn_dot<2, 16>(R3D_DOT_ARGS);
+        return launch_knn_dot<1, 16>(R3D_DOT_ARGS);
+#undef R3D_DOT_ARGS
+    }
     {
         dim3 grid(ceil_div(Nsp, 256), B);
         xyz_to_soa_kernel<<<grid, 256, 0, st>>>(support, support_batch_stride, soa, Ns, Nsp);

@@ -11,9 +11,10 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-# (algorithm, variant): tiled brute force in its three arithmetic variants, and the uniform-grid search
-# (2 = one warp per query, 4 = one thread per query), and (0, 2) = the library's own choice (r3d_knn_plan)
-VARIANTS = [(1, 0), (1, 1), (1, 2), (2, 2), (4, 2), (0, 2)]
+# (algorithm, variant): tiled brute force in its four arithmetic variants (3 = dot-form prefilter + warp-cooperative
+# admission, the default), the uniform-grid search (2 = one warp per query, 4 = one thread per query), and
+# (0, 3) = the library's own choice (r3d_knn_plan)
+VARIANTS = [(1, 0), (1, 1), (1, 2), (1, 3), (2, 2), (4, 2), (0, 3)]
 
 
 class _mode:
@@ -158,3 +159,20 @@ def test_knn_large_properties(ops, algo, n):
     oi, od = knn_exact(s[0].cpu().numpy(), s[0, rows.cuda()].cpu().numpy(), 16)
     assert np.array_equal(idx[rows.cuda()].cpu().numpy(), oi)
     assert np.array_equal(d2[rows.cuda()].cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("K", [16, 32])
+@pytest.mark.parametrize("offset,scale", [(0.0, 1.0), (1000.0, 1.0), (-3.0e4, 50.0), (0.0, 1e-3), (5.0e6, 1.0e4)])
+def test_knn_dot_prefilter_far_from_origin(ops, oracle_built, K, offset, scale):
+    """Variant 3's prefilter works on coordinates relative to the cloud's first point: clouds far from the origin (fp32
+    coordinates with few bits left for the extent), tiny and huge extents stay bit-exact against the oracle."""
+    with _mode((1, 3)):
+        rng = np.random.RandomState(K)
+        s = (rng.rand(2, 3000, 3) * scale + offset).astype(np.float32)
+        q = (rng.rand(2, 700, 3) * scale * 1.1 + offset).astype(np.float32)
+        out = _run(ops, s, q, K)
+        oi, od = oracle_built.knn_exact(s, q, K)
+        assert np.array_equal(out["dist_sq"], od)
+        tie_free = np.all(np.diff(od, axis=-1) > 0, axis=-1)
+        assert np.array_equal(out["idx64"][tie_free], oi[tie_free])
+        assert np.array_equal(out["idx64"], oi)
