@@ -632,13 +632,16 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
         # 1-NN up-sampling + skip concat (modules.py:596-602): one gather launch, one scatter launch in the backward
         cur = shared_mlp(stage, upsample("nni", cur, xyz[:, :n_l], xyz[:, :n_up], dec_idx.get(lvl), skip=skips.pop()))
         n_l = n_up
-    inv = torch.empty_like(perm)                  # inverse permutation by scatter (argsort is a 30 us radix sort)
-    inv.scatter_(0, perm, torch.arange(perm.numel(), device=perm.device))
-    cur = cur.index_select(1, inv)
+    # The reference undoes the permutation before fc_end (modules.py:608).  fc_end acts per point (its BatchNorm batch
+    # statistics are sums over all points), so undoing it AFTER fc_end gives the same logits while the gather and its
+    # scatter-add backward move n_classes channels per point instead of 32.
     cur = shared_mlp(net.fc_end[0], cur)
     cur = shared_mlp(net.fc_end[1], cur)
     cur = F.dropout(cur, net.fc_end[2].p, net.fc_end[2].training)
-    return shared_mlp(net.fc_end[3], cur).transpose(1, 2)
+    cur = shared_mlp(net.fc_end[3], cur)
+    inv = torch.empty_like(perm)                  # inverse permutation by scatter (argsort is a 30 us radix sort)
+    inv.scatter_(0, perm, torch.arange(perm.numel(), device=perm.device))
+    return cur.index_select(1, inv).transpose(1, 2)
 
 
 def _require_cuda(t: torch.Tensor) -> None:
