@@ -789,11 +789,63 @@ static int pw_launch(Kern kern, dim3 grid, int threads, PwArgs& a, cudaStream_t 
     return R3D_OK;
 }
 
+// ------------------------------------------------------------------------------------------ pw_expand
+// C_in <= 4 into a wider layer over very many rows (the input gradient of the class-logits layer, 2 -> 32 at 2.6 M
+// rows): a write stream.  A thread owns 4 output channels of one row — the row's inputs are a broadcast load for the
+// cout / 4 adjacent threads, stores are 16 bytes and contiguous across the warp.  (The GEMM tile kernel ran this shape
+// at 0.85 TB/s.)
+__global__ void __launch_bounds__(256) pw_expand_kernel(PwArgs a) {
+    const int c4 = a.cout / 4;
+    const int cin = a.ca;
+    const long long total = (long long)a.B * a.n * c4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / c4;
+        const int c = (int)(t % c4) * 4;
+        const int b = (int)(row / a.n), n = (int)(row % a.n);
+        const float* x = a.xa + b * a.xa_bstride + (long long)n * cin;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < cin; ++i) {
+            const float v = x[i];
+            float4 w;
+            if (a.w_out_in)
+                w = make_float4(a.wT[(c + 0) * cin + i], a.wT[(c + 1) * cin + i], a.wT[(c + 2) * cin + i], a.wT[(c + 3) * cin + i]);
+            else
+                w = *reinterpret_cast<const float4*>(a.wT + (long long)i * a.cout + c);
+            acc.x = fmaf(v, w.x, acc.x), acc.y = fmaf(v, w.y, acc.y), acc.z = fmaf(v, w.z, acc.z), acc.w = fmaf(v, w.w, acc.w);
+        }
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = o[j];
+            if (a.scale) v *= a.scale[c + j];
+            if (a.shift) v += a.shift[c + j];
+            if (a.act == 1) v = fmaxf(v, 0.f);
+            if (a.act == 2) v = v > 0.f ? v : v * a.slope;
+            o[j] = v;
+        }
+        *reinterpret_cast<float4*>(a.y + b * a.y_bstride + (long long)n * a.y_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static bool pw_expand_eligible(const PwArgs& a) {
+    const long long M = (long long)a.B * a.n;
+    return M >= 131072 && a.ca <= 4 && a.cb == 0 && !a.gidx && !a.transpose_out && !a.stats && !a.bn.y && a.cout % 4 == 0 &&
+           a.cout > kPwSmallMaxCout && a.y_ld % 4 == 0 && a.y_bstride % 4 == 0 && is_aligned(a.y, 16) &&
+           is_aligned(a.wT, 16);
+}
+
 static int pw_run(PwArgs a, cudaStream_t st, bool* fused) {
     const int ca = a.ca, cb = a.cb, cout = a.cout;
     const long long M = (long long)a.B * a.n;
     if (fused) *fused = false;
     if (pw_rows_eligible(a)) return pw_rows_run(a, st);
+    if (pw_expand_eligible(a)) {
+        long long blocks = (M * (cout / 4) + 255) / 256;
+        if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+        pw_expand_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+        R3D_LAUNCH_CHECK("pw_expand_kernel");
+        return R3D_OK;
+    }
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) {
         int rc = pw_launch(pw_small_kernel, dim3((unsigned)((M + 255) / 256)), 256, a, st, fused);
         if (rc != R3D_OK) return rc;
@@ -925,6 +977,9 @@ extern "C" int r3d_pointwise_plan(int ca, int cb, int cout, long long rows, int 
         r.xa_bstride = (long long)r.n * ca;
         r.y_bstride = (long long)r.n * cout;
         if (pw_rows_eligible(r)) return 4;
+        r.y = reinterpret_cast<float*>(16);      // alignment checks only
+        r.wT = reinterpret_cast<const float*>(16);
+        if (pw_expand_eligible(r)) return 5;
     }
     if (cout <= kPwSmallMaxCout && (long long)(ca + cb) * cout <= kPwSmallMaxW) return 0;
     PwArgs a{};

@@ -10,6 +10,7 @@
 //             r3d_rowreduce_gemm   dW = dz^T x                       (row-reduction GEMM, split over row chunks)
 // All tensors are dense row-major (M, C); C is a multiple of 4 for the BatchNorm kernels.
 // Backward reference: autograd of modules.py:92-104 as driven by trainer.py:115-119.
+#include <cstdlib>
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -674,12 +675,89 @@ extern "C" int r3d_bn_bwd(const float* dy, const float* z, long long M, int C, c
     return r3d_bn_bwd_absmax(dy, z, M, C, save, beta, act, slope, stats2, dz, dgb, nullptr, stream);
 }
 
+// ------------------------------------------------------------------------------ rowreduce_gemm_rows8
+// Weight gradients of the narrowest layers over millions of rows (level 0 of a large batch: 8x8, 8x3, 2x32, 8x16, 32x8,
+// 64x8 at 2.6 M rows): pure streaming, a few FMAs per loaded float.  The thin kernel above puts one ROW on a warp (8 of
+// 32 lanes busy at 8 channels, 0.6-2.5 TB/s).  Here a thread owns an 8 x 8 tile of the output and walks rows: the
+// T = ceil(Ca/8) ceil(Cb/8) threads of a row are adjacent (a warp reads 32/T consecutive rows: contiguous memory), 64
+// accumulators in registers, a shuffle tree over the lanes that share a tile at the end, then shared-memory and global
+// atomics once per CTA.
+__global__ void __launch_bounds__(256) rowreduce_gemm_rows8_kernel(const float* __restrict__ A, int Ca,
+                                                                   const float* __restrict__ Bm, int Cb, long long M,
+                                                                   float* __restrict__ out, int ld_out, int na, int nb) {
+    const int T = na * nb;                                   // threads per row: a power of two <= 32
+    const int tile = threadIdx.x % T, ia = tile / nb, ib = tile % nb;
+    const int rows_per_block = 256 / T;
+    const int a0 = ia * 8, b0 = ib * 8;
+    const bool vec_a = (Ca % 4 == 0) && a0 + 8 <= Ca, vec_b = (Cb % 4 == 0) && b0 + 8 <= Cb;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (long long r = (long long)blockIdx.x * rows_per_block + threadIdx.x / T; r < M;
+         r += (long long)gridDim.x * rows_per_block) {
+        float a[8], b[8];
+        const float* ap = A + r * Ca + a0;
+        const float* bp = Bm + r * Cb + b0;
+        if (vec_a) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(ap)), v = __ldg(reinterpret_cast<const float4*>(ap + 4));
+            a[0] = u.x, a[1] = u.y, a[2] = u.z, a[3] = u.w, a[4] = v.x, a[5] = v.y, a[6] = v.z, a[7] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = a0 + i < Ca ? __ldg(ap + i) : 0.f;
+        }
+        if (vec_b) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(bp)), v = __ldg(reinterpret_cast<const float4*>(bp + 4));
+            b[0] = u.x, b[1] = u.y, b[2] = u.z, b[3] = u.w, b[4] = v.x, b[5] = v.y, b[6] = v.z, b[7] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = b0 + j < Cb ? __ldg(bp + j) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __shared__ float red[32][64];                            // [tile][8 x 8]
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[i][j];
+            for (int o = 16; o >= T; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // lanes with the same tile
+            if ((threadIdx.x & 31) < T) atomicAdd(&red[tile][i * 8 + j], v);
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * 64; e += 256) {
+        const int t = e / 64, i = (e % 64) / 8, j = e % 8;
+        const int ca = (t / nb) * 8 + i, cb = (t % nb) * 8 + j;
+        if (ca < Ca && cb < Cb) atomicAdd(out + (size_t)ca * ld_out + cb, red[t][i * 8 + j]);
+    }
+}
+
 extern "C" int r3d_rowreduce_gemm(const float* A, int Ca, const float* Bm, int Cb, long long M, float* out, int ld_out,
                                   r3d_stream_t stream) {
     if (M < 0 || Ca <= 0 || Cb <= 0) return R3D_EINVAL;
     if (M == 0) return R3D_OK;
     if (!A || !Bm || !out) return R3D_EINVAL;
     if (ld_out == 0) ld_out = Cb;
+    {
+        // a few channels each way over very many rows: thread-owned 8 x 8 output tiles (see rowreduce_gemm_rows8_kernel)
+        const int na = (Ca + 7) / 8, nb = (Cb + 7) / 8, T = na * nb;
+        static const bool rows8 = getenv("R3D_RR_ROWS8_OFF") == nullptr;       // tuning hook
+        if (rows8 && M >= 131072 && T <= 8 && (T & (T - 1)) == 0 && is_aligned(A, 16) && is_aligned(Bm, 16)) {
+            const int rows_per_block = 256 / T;
+            long long blocks = (M + (long long)rows_per_block * 16 - 1) / ((long long)rows_per_block * 16);
+            if (blocks > (long long)kNumSMs * 6) blocks = (long long)kNumSMs * 6;
+            rowreduce_gemm_rows8_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, Ca, Bm, Cb, M, out,
+                                                                                                       ld_out, na, nb);
+            R3D_LAUNCH_CHECK("rowreduce_gemm_rows8_kernel");
+            return R3D_OK;
+        }
+    }
     if ((Ca <= 8 && Cb <= 32) || (Cb <= 8 && Ca <= 32)) {
         long long blocks = (M + 8 * 8 - 1) / (8 * 8);             // >= 8 rows per warp: the row loop is latency-bound
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;

@@ -368,7 +368,7 @@ def pointwise(xa: torch.Tensor, wT: torch.Tensor, scale=None, shift=None, act=No
     nbytes = 4.0 * B * n * (ca + cb + cout)
     tname = "pointwise"
     if _cabi.KERNEL_TIMERS is not None:
-        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc", "pw_rows")[
+        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc", "pw_rows", "pw_expand")[
             _cabi.lib().r3d_pointwise_plan(ca, cb, cout, B * n, 1 if transpose_out else 0)]
         if _cabi.TIMER_SHAPES:
             tname += f"[M={B * n},{ca + cb}->{cout}]"
@@ -555,7 +555,7 @@ def pointwise_bn(x: torch.Tensor, w: torch.Tensor, stats: torch.Tensor, bn: torc
     track = bn.track_running_stats and bn.running_mean is not None
     tname = "pointwise_bn"
     if _cabi.KERNEL_TIMERS is not None:
-        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc", "pw_rows")[_cabi.lib().r3d_pointwise_plan(cin, 0, cout, M, 0)]
+        tname = ("pw_small", "pw_gemm", "pw_gemm_fast", "pw_tc", "pw_rows", "pw_expand")[_cabi.lib().r3d_pointwise_plan(cin, 0, cout, M, 0)]
         if _cabi.TIMER_SHAPES:
             tname += f"[M={M},{cin}->{cout},bn]"
     with torch.cuda.device(dev), _cabi.kernel_timer(tname, flops=2.0 * M * cin * cout + 4.0 * M * cout,

@@ -255,3 +255,22 @@ def test_pointwise_streaming_rows_kernel(mods, ca, cout, w_out_in, act):
     flat = ref.reshape(-1, cout)
     assert rel_err(stats[:cout], flat.sum(0)) < 1e-5 * max(1.0, float(flat.abs().sum(0).max() / flat.sum(0).abs().max()))
     assert rel_err(stats[cout:], (flat * flat).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("ca,cout", [(2, 32), (3, 64), (4, 20), (1, 32)])
+@pytest.mark.parametrize("w_out_in,act", [(False, None), (True, "lrelu")])
+def test_pointwise_expand_kernel(mods, ca, cout, w_out_in, act):
+    """pw_expand_kernel (C_in <= 4 into a wider layer on >= 131072 rows: the input gradient of the class-logits layer)."""
+    _, _, ops = mods
+    L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+    B, n = 2, 70001
+    assert L.r3d_pointwise_plan(ca, 0, cout, B * n, 0) == 5
+    g = torch.Generator(device="cuda").manual_seed(ca * 100 + cout)
+    x = torch.randn(B, n, ca, device="cuda", generator=g)
+    w = torch.randn(*((cout, ca) if w_out_in else (ca, cout)), device="cuda", generator=g)
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    sh = torch.randn(cout, device="cuda", generator=g)
+    got = ops.pointwise(x, w, sc, sh, act, 0.1, w_out_in=w_out_in)
+    ref = (x.double() @ (w.double().t() if w_out_in else w.double())) * sc.double() + sh.double()
+    ref = F.leaky_relu(ref, 0.1) if act == "lrelu" else ref
+    assert got.shape == (B, n, cout) and rel_err(got.double(), ref) < 1e-6

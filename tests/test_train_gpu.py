@@ -246,7 +246,10 @@ def test_train_step_vs_reference_golden(mods, name):
 
 
 @pytest.mark.parametrize("M,Ca,Cb", [(100000, 16, 16), (50000, 32, 16), (8192, 16, 64), (70001, 64, 32), (4097, 12, 20),
-                                     (300000, 32, 32), (65536, 64, 16), (5000, 40, 24)])
+                                     (300000, 32, 32), (65536, 64, 16), (5000, 40, 24),
+                                     # thread-owned 8 x 8 tiles (rowreduce_gemm_rows8_kernel): >= 131072 rows, <= 8 tiles
+                                     (2621440, 8, 8), (200001, 8, 3), (131072, 2, 32), (300000, 8, 16), (150000, 32, 8),
+                                     (140000, 64, 8), (262144, 8, 64), (131073, 3, 5), (200000, 12, 20), (150000, 32, 16)])
 def test_rowreduce_gemm_narrow_tiles(mods, M, Ca, Cb):
     """Weight-gradient row reduction A^T B for narrow layers (the level-0 layers of a large batch): the narrow-tile
     kernel (row slices inside the CTA, no padding work) against an fp64 product."""
