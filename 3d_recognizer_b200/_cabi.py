@@ -59,6 +59,14 @@ SIGNATURES = {
     "r3d_lfa_bn2_bwd": (c_int, [c_void_p, ctypes.c_longlong] + [c_void_p] * 10 + [c_int, c_int, c_int, c_int, c_void_p]),
     "r3d_lfa_moments": (c_int, [c_int, c_void_p, ctypes.c_longlong] + [c_void_p] * 10 +
                         [c_int, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_rpe_rows": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "r3d_lfa_gather_concat": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
+    "r3d_lfa_gather_concat_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int,
+                                          c_int, c_int, c_void_p]),
+    "r3d_lfa_attn_pool": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
+    "r3d_lfa_attn_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int,
+                                      c_void_p]),
     "r3d_bn_from_moments": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
                                     c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -174,7 +174,9 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, w, bias):
         x = x.contiguous()
         ctx.save_for_backward(x, w)
-        return ops.pointwise(x.unsqueeze(0), w.contiguous(), None, bias.contiguous(), w_out_in=True).squeeze(0)
+        ctx.has_bias = bias is not None          # the attentive-pooling score Linear has none (modules.py:234-237)
+        return ops.pointwise(x.unsqueeze(0), w.contiguous(), None, bias.contiguous() if ctx.has_bias else None,
+                             w_out_in=True).squeeze(0)
 
     @staticmethod
     def backward(ctx, dy):
@@ -182,12 +184,12 @@ class _LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         if OVERLAP_WEIGHT_GRADS and ctx.needs_input_grad[0]:
             with _fork(dy.device) as f:               # parameter gradients next to the input-gradient GEMM
-                dw, db = ops.rowreduce_gemm(dy, x), dy.sum(dim=0)
+                dw, db = ops.rowreduce_gemm(dy, x), (dy.sum(dim=0) if ctx.has_bias else None)
             dx = ops.pointwise(dy.unsqueeze(0), w.contiguous()).squeeze(0)
             f.join()
             return dx, dw, db
         dx = ops.pointwise(dy.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
-        return dx, ops.rowreduce_gemm(dy, x), dy.sum(dim=0)
+        return dx, ops.rowreduce_gemm(dy, x), (dy.sum(dim=0) if ctx.has_bias else None)
 
 
 def _kernel_layer_ok(x: torch.Tensor, bn) -> bool:
@@ -558,9 +560,73 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tenso
     return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + sc, 0.01)
 
 
-# LFA implementation used by forward_autograd: the fused kernels, or (tests / debugging) the plain
-# tensor-op composition `lfa_block`
-LFA_IMPL = lfa_block_fused
+# ------------------------------------------------- row-form LFA block: any n_neighbors, any layer size
+class _GatherConcatFn(torch.autograd.Function):
+    """X = [r ; feat at the neighbours] over the (B*N*K) rows (ops.lfa_gather_concat) and its scatter-add backward."""
+
+    @staticmethod
+    def forward(ctx, r, feat, idx32):
+        ctx.save_for_backward(idx32)
+        return ops.lfa_gather_concat(r, feat, idx32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx32,) = ctx.saved_tensors
+        dr, dfeat = ops.lfa_gather_concat_bwd(dout, idx32, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dr, dfeat, None
+
+
+class _AttnPoolFn(torch.autograd.Function):
+    """pooled = sum_k softmax_k(S) X over the K rows of every point (ops.lfa_attn_pool / lfa_attn_pool_bwd)."""
+
+    @staticmethod
+    def forward(ctx, S, X, K):
+        ctx.K = K
+        ctx.save_for_backward(S, X)
+        return ops.lfa_attn_pool(S, X, K)
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        S, X = ctx.saved_tensors
+        dS, dX = ops.lfa_attn_pool_bwd(S, X, dpooled, ctx.K)
+        return dS, dX, None
+
+
+def lfa_block_rows(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None, wT=None) -> torch.Tensor:
+    """LocalFeatureAggregation (modules.py:298-325) for settings outside the fused kernels' template lists (any
+    n_neighbors >= 1, any layer size): the neighbourhood rows (B*N*K, C) are materialised, mlp_rpe1/2 and the score
+    Linear run as per-point layers over them (train-mode BatchNorm statistics over all B*N*K rows, modules.py:86-90),
+    gather + concat and softmax-pooling are the row kernels of csrc/lfa_rows.cu.  Differentiable; same result as
+    `lfa_block_fused` to fp32 round-off where both apply (tests/test_lfa_rows_gpu.py)."""
+    K = lfa._n_neighbors
+    B, N, _ = xyz.shape
+    if idx is None:
+        idx = ops.knn(xyz, xyz, K, idx64=False, idx32=True, dist=False)["idx32"]
+    sc = shared_mlp(lfa.shortcut, feat)
+    f = shared_mlp(lfa.mlp1, feat)
+    r1 = shared_mlp(lfa.mlp_rpe1, ops.lfa_rpe_rows(xyz, idx))
+    X1 = _GatherConcatFn.apply(r1, f, idx)
+    S1 = _LinearFn.apply(X1, lfa.pool1.score_fn[0].weight, None)
+    p1 = shared_mlp(lfa.pool1.mlp, _AttnPoolFn.apply(S1, X1, K).view(B, N, -1))
+    r2 = shared_mlp(lfa.mlp_rpe2, r1)                      # fed by r1, not by the raw encoding (modules.py:321)
+    X2 = _GatherConcatFn.apply(r2, p1, idx)
+    S2 = _LinearFn.apply(X2, lfa.pool2.score_fn[0].weight, None)
+    p2 = shared_mlp(lfa.pool2.mlp, _AttnPoolFn.apply(S2, X2, K).view(B, N, -1))
+    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + sc, 0.01)
+
+
+def lfa_block_auto(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None, wT=None) -> torch.Tensor:
+    """The fused kernels where they are instantiated (d in ops.LFA_FUSED_WIDTHS, K in ops.LFA_FUSED_NEIGHBORS), the
+    row form elsewhere."""
+    d = 2 * lfa.mlp_rpe1.conv.weight.shape[0]
+    if ops.lfa_fused_supported(d, lfa._n_neighbors):
+        return lfa_block_fused(lfa, xyz, feat, idx, wT)
+    return lfa_block_rows(lfa, xyz, feat, idx, wT)
+
+
+# LFA implementation used by forward_autograd: the fused kernels (row form for shapes they are not built for), or
+# (tests / debugging) the plain tensor-op composition `lfa_block`
+LFA_IMPL = lfa_block_auto
 
 
 # ------------------------------------------------------------------------------------ full forward
@@ -597,7 +663,7 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     # down-sampled levels and of the decoder's 1-NN up-sampling run on a side stream while level 0 is processed
     # (each is a few-microsecond kernel on a fraction of the SMs; ~75 us of a 3 ms step on the main chain otherwise).
     pre_fork, enc_idx, dec_idx, enc_wT = None, {}, {}, {}
-    if LFA_IMPL is lfa_block_fused and OVERLAP_WEIGHT_GRADS and xyz.is_cuda and L > 1:
+    if LFA_IMPL in (lfa_block_fused, lfa_block_auto) and OVERLAP_WEIGHT_GRADS and xyz.is_cuda and L > 1:
         with torch.no_grad(), _fork(xyz.device, lane=3) as pre_fork:
             if net.training:
                 for lvl in range(1, L):              # weight transposes of the later levels: off the main chain too

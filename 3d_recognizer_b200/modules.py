@@ -169,8 +169,12 @@ class UpSampler(torch.nn.Module):
         return y.unsqueeze(-1)
 
 
-SUPPORTED_LAYER_SIZES = (16, 32, 64, 128, 256)
-SUPPORTED_NEIGHBORS = (16, 32)
+# Widths / neighbour counts the FUSED LocSE + pooling kernels are instantiated for (csrc/lfa*.cu).  Any other setting the
+# reference accepts runs the same operators in row form (csrc/lfa_rows.cu + the per-point layer kernels): slower, same
+# results.  The per-point layer kernels store 4 channels at a time, hence layer sizes in multiples of 8.
+FUSED_LAYER_SIZES = (16, 32, 64, 128, 256)
+FUSED_NEIGHBORS = (16, 32)
+MAX_NEIGHBORS = 64          # R3D_KNN_KMAX
 
 
 class RandLANet(torch.nn.Module):
@@ -185,12 +189,11 @@ class RandLANet(torch.nn.Module):
         self._device = device
         sizes = settings.layer_sizes
         L = len(sizes)
-        # the fused LocSE + pooling kernels are instantiated for these widths / neighbour counts (csrc/lfa*.cu); anything
-        # else fails here, at construction, not at the first forward (there is no tensor-op fallback back-end)
-        bad = [d for d in sizes if d not in SUPPORTED_LAYER_SIZES]
-        if bad or k not in SUPPORTED_NEIGHBORS:
-            raise ValueError(f"3d_recognizer_b200 builds its fused LFA kernels for layer_sizes in {SUPPORTED_LAYER_SIZES} "
-                             f"and n_neighbors in {SUPPORTED_NEIGHBORS}; got layer_sizes={list(sizes)}, n_neighbors={k}")
+        bad = [d for d in sizes if d <= 0 or d % 8]
+        if bad or not 1 <= k <= MAX_NEIGHBORS:
+            raise ValueError(f"3d_recognizer_b200 supports layer_sizes that are positive multiples of 8 (fused kernels for "
+                             f"{FUSED_LAYER_SIZES}, row-form kernels otherwise) and 1 <= n_neighbors <= {MAX_NEIGHBORS} "
+                             f"(fused for {FUSED_NEIGHBORS}); got layer_sizes={list(sizes)}, n_neighbors={k}")
         # (1) K points must survive down to the last encoder level; (2) >= 2 points at the bottleneck
         self._min_n_points = max(k * settings.decimation ** (L - 1), 2 * settings.decimation ** L)
 

@@ -317,6 +317,8 @@ def lfa_pool(stage: int, xyz: torch.Tensor, idx32: torch.Tensor, feat: torch.Ten
     """Fused LocSE + attentive pooling of one LFA half (C ABI ``r3d_lfa_pool``; modules.py:316-323).
     xyz (B,N,3), idx32 (B,N,K) int32, feat (B,N,h) -> pooled (B,N,d), d = 2h."""
     _cabi.require_cuda(xyz, "xyz")
+    if not lfa_fused_supported(2 * feat.shape[2], idx32.shape[2]):
+        return lfa_pool_rows(stage, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT)
     xyz, xs = _cloud_view(xyz)
     feat, fs = _rows_view(feat.detach())
     B, N, K = idx32.shape
@@ -446,6 +448,105 @@ def pc_wgrad(a: torch.Tensor, b: torch.Tensor, absmax_a: Optional[torch.Tensor] 
                                       _cabi.ptr(out), Cb, _cabi.stream_ptr(a.device))
     _cabi.check(rc, "r3d_pc_wgrad")
     return out
+
+
+# ------------------------------------------------------------------------- row-form LFA block (any K, any width)
+# Shapes the fused LocSE + pooling kernels are instantiated for; everything else runs in row form (csrc/lfa_rows.cu).
+LFA_FUSED_WIDTHS, LFA_FUSED_NEIGHBORS = (16, 32, 64, 128, 256), (16, 32)
+
+
+def lfa_fused_supported(d: int, k: int) -> bool:
+    return d in LFA_FUSED_WIDTHS and k in LFA_FUSED_NEIGHBORS
+
+
+def lfa_rpe_rows(xyz: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
+    """(B*N*K, 10) rows [p_i, p_j, p_i - p_j, |p_i - p_j|] (C ABI ``r3d_lfa_rpe_rows``; modules.py:170-186)."""
+    _cabi.require_cuda(xyz, "xyz")
+    xyz, xs = _cloud_view(xyz)
+    idx32 = idx32.contiguous()
+    B, N, K = idx32.shape
+    out = torch.empty((B * N * K, 10), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device), _cabi.kernel_timer("lfa_rpe_rows", flops=8.0 * B * N * K, bytes=68.0 * B * N * K):
+        rc = _cabi.lib().r3d_lfa_rpe_rows(_cabi.raw(xyz), xs, _cabi.ptr(idx32), _cabi.ptr(out), B, N, K,
+                                          _cabi.stream_ptr(xyz.device))
+    _cabi.check(rc, "r3d_lfa_rpe_rows")
+    return out
+
+
+def lfa_gather_concat(r: torch.Tensor, feat: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
+    """r (B*N*K,h) rows, feat (B,N,h), idx32 (B,N,K) -> X (B*N*K,2h) = [r ; feat at the neighbours]
+    (C ABI ``r3d_lfa_gather_concat``; PointFeatureAugmentation, modules.py:200-208)."""
+    _cabi.require_cuda(r, "r")
+    feat, fs = _rows_view(feat.detach())
+    r = r.detach().contiguous()
+    idx32 = idx32.contiguous()
+    B, N, K = idx32.shape
+    h = feat.shape[2]
+    assert r.shape == (B * N * K, h) and r.dtype == torch.float32
+    out = torch.empty((B * N * K, 2 * h), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device), _cabi.kernel_timer("lfa_gather_concat", flops=0.0, bytes=16.0 * B * N * K * h):
+        rc = _cabi.lib().r3d_lfa_gather_concat(_cabi.ptr(r), _cabi.raw(feat), fs, _cabi.ptr(idx32), _cabi.ptr(out), B, N, K,
+                                               h, _cabi.stream_ptr(r.device))
+    _cabi.check(rc, "r3d_lfa_gather_concat")
+    return out
+
+
+def lfa_gather_concat_bwd(dout: torch.Tensor, idx32: torch.Tensor, need_r: bool, need_feat: bool):
+    """Backward of ``lfa_gather_concat``: (dr (B*N*K,h) | None, dfeat (B,N,h) | None)."""
+    dout = dout.contiguous()
+    idx32 = idx32.contiguous()
+    B, N, K = idx32.shape
+    h = dout.shape[1] // 2
+    dev = dout.device
+    dr = torch.empty((B * N * K, h), dtype=torch.float32, device=dev) if need_r else None
+    dfeat = zeros((B, N, h), torch.float32, dev) if need_feat else None
+    with torch.cuda.device(dev), _cabi.kernel_timer("lfa_gather_concat_bwd", flops=float(B * N * K * h),
+                                                    bytes=16.0 * B * N * K * h):
+        rc = _cabi.lib().r3d_lfa_gather_concat_bwd(_cabi.ptr(dout), _cabi.ptr(idx32), _cabi.ptr(dr), _cabi.ptr(dfeat), 0,
+                                                   B, N, K, h, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "r3d_lfa_gather_concat_bwd")
+    return dr, dfeat
+
+
+def lfa_attn_pool(S: torch.Tensor, X: torch.Tensor, K: int) -> torch.Tensor:
+    """S, X (points*K, d) -> pooled (points, d) = sum_k softmax_k(S) X (C ABI ``r3d_lfa_attn_pool``; modules.py:246-252)."""
+    _cabi.require_cuda(S, "S")
+    S, X = S.detach().contiguous(), X.detach().contiguous()
+    rows, d = S.shape
+    assert X.shape == S.shape and rows % K == 0
+    pooled = torch.empty((rows // K, d), dtype=torch.float32, device=S.device)
+    with torch.cuda.device(S.device), _cabi.kernel_timer("lfa_attn_pool", flops=6.0 * rows * d, bytes=8.0 * rows * d):
+        rc = _cabi.lib().r3d_lfa_attn_pool(_cabi.ptr(S), _cabi.ptr(X), _cabi.ptr(pooled), rows // K, K, d,
+                                           _cabi.stream_ptr(S.device))
+    _cabi.check(rc, "r3d_lfa_attn_pool")
+    return pooled
+
+
+def lfa_attn_pool_bwd(S: torch.Tensor, X: torch.Tensor, dpooled: torch.Tensor, K: int):
+    """Backward of ``lfa_attn_pool``: (dS, dX) with dX the direct term g A only (C ABI ``r3d_lfa_attn_pool_bwd``)."""
+    S, X, dpooled = S.contiguous(), X.contiguous(), dpooled.contiguous()
+    rows, d = S.shape
+    dS, dX = torch.empty_like(S), torch.empty_like(X)
+    with torch.cuda.device(S.device), _cabi.kernel_timer("lfa_attn_pool_bwd", flops=12.0 * rows * d, bytes=24.0 * rows * d):
+        rc = _cabi.lib().r3d_lfa_attn_pool_bwd(_cabi.ptr(S), _cabi.ptr(X), _cabi.ptr(dpooled), _cabi.ptr(dS), _cabi.ptr(dX),
+                                               rows // K, K, d, _cabi.stream_ptr(S.device))
+    _cabi.check(rc, "r3d_lfa_attn_pool_bwd")
+    return dS, dX
+
+
+def lfa_pool_rows(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T, a_rpe2, b_rpe2, w_scoreT) -> torch.Tensor:
+    """``lfa_pool`` in row form for shapes outside the fused kernels' template lists (same arguments and result):
+    rpe rows -> mlp_rpe1 [-> mlp_rpe2] as per-point layers over the B*N*K rows -> gather + concat -> score Linear as a
+    per-point layer -> softmax over K and weighted sum.  Inference only (the training path composes the same pieces
+    under autograd, engine.lfa_block_rows)."""
+    B, N, K = idx32.shape
+    rows = lfa_rpe_rows(xyz, idx32)
+    r = pointwise(rows.unsqueeze(0), w_rpe1.contiguous(), a_rpe1, b_rpe1, "relu", w_out_in=True)
+    if stage == 2:
+        r = pointwise(r, w_rpe2T.contiguous(), a_rpe2, b_rpe2, "relu")
+    X = lfa_gather_concat(r.squeeze(0), feat, idx32)
+    S = pointwise(X.unsqueeze(0), w_scoreT.contiguous()).squeeze(0)
+    return lfa_attn_pool(S, X, K).view(B, N, -1)
 
 
 UP_WEIGHTING = {"nni": (0, 1.0), "nna": (1, 1.0), "idw": (1, 1.0), "isdw": (1, 2.0), "mean": (2, 1.0)}

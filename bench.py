@@ -47,6 +47,9 @@ WORKLOADS = {
     # name: (kind, n_points, K, global_batch or None (=> per-GPU batch below), per_gpu_batch)
     "train2500": dict(kind="train", n=2500, k=16, per_gpu_batch=8, scaling="weak"),
     "train40960": dict(kind="train", n=40960, k=16, global_batch=64, scaling="strong"),
+    # one rank's shard of train40960 on 8 / 4 GPUs, run on ONE GPU: the diagnostic for the strong-scaling tail
+    "train40960_b8": dict(kind="train", n=40960, k=16, global_batch=8, scaling="strong"),
+    "train40960_b16": dict(kind="train", n=40960, k=16, global_batch=16, scaling="strong"),
     "infer16k": dict(kind="infer", n=16384, k=16, global_batch=32, scaling="strong"),
     "infer64k": dict(kind="infer", n=65536, k=16, global_batch=32, scaling="strong"),
     "infer256k": dict(kind="infer", n=262144, k=16, global_batch=32, scaling="strong"),

@@ -254,6 +254,27 @@ int r3d_lfa_rpe1_grads(const float* W, int cout, int cin, const double* S, int s
 int r3d_lfa_bn2_coeffs(const double* sums, const float* a2, const float* c2, const double* save, double rows, int h,
                        float* bn2, float* dgamma, float* dbeta, r3d_stream_t stream);
 
+/* ------------------------------------------------------------------ row-form LFA block (any K, any width)
+ * The fused kernels above are built for d in {16,...,256} and K in {16,32}; the reference takes any n_neighbors and any
+ * layer size (modules.py:298-325, 484-500).  Other settings run the same operators in ROW FORM: the (B*N*K, C)
+ * neighbourhood rows are materialised, mlp_rpe1/2 and the score Linear run as per-point layers (r3d_pointwise*) over
+ * them, and these entry points supply what is not a per-point layer (csrc/lfa_rows.cu):
+ *   r3d_lfa_rpe_rows           out (B*N*K,10) = [p_i, p_j, p_i - p_j, |p_i - p_j|]             (modules.py:170-186)
+ *   r3d_lfa_gather_concat      out (B*N*K,2h) = [r (B*N*K,h) ; feat[b, idx, :] (h)]             (modules.py:200-208)
+ *   r3d_lfa_gather_concat_bwd  dr (B*N*K,h, nullable) = dout[:, :h];  dfeat (B,N,h, nullable) += scatter of dout[:, h:]
+ *   r3d_lfa_attn_pool          pooled (points,d) = sum_k softmax_k(S)[k,c] X[k,c]; S, X (points*K,d)  (modules.py:246-252)
+ *   r3d_lfa_attn_pool_bwd      dX = g A (direct term only: the score Linear's own backward adds dS Ws), dS = A g (X - pooled)
+ * idx int32 (B,N,K); feat/dfeat clouds *_bstride floats apart (0 = dense); K >= 1, h, d >= 1. */
+int r3d_lfa_rpe_rows(const float* xyz, long long xyz_bstride, const int32_t* idx, float* out, int B, int N, int K,
+                     r3d_stream_t stream);
+int r3d_lfa_gather_concat(const float* r, const float* feat, long long feat_bstride, const int32_t* idx, float* out,
+                          int B, int N, int K, int h, r3d_stream_t stream);
+int r3d_lfa_gather_concat_bwd(const float* dout, const int32_t* idx, float* dr, float* dfeat, long long dfeat_bstride,
+                              int B, int N, int K, int h, r3d_stream_t stream);
+int r3d_lfa_attn_pool(const float* S, const float* X, float* pooled, long long points, int K, int d, r3d_stream_t stream);
+int r3d_lfa_attn_pool_bwd(const float* S, const float* X, const float* dpooled, float* dS, float* dX, long long points,
+                          int K, int d, r3d_stream_t stream);
+
 /* ------------------------------------------------------------------------- Focal-Tversky / Dice loss
  * randlanet/utils/losses.py:66-86 via trainer.py:245-269: p = softmax over classes, TI_c = (TP_c + eps) /
  * (TP_c + alpha FN_c + (1 - alpha) FP_c + eps), loss = mean over classes >= first_class of (1 - TI_c)^gamma.

@@ -319,13 +319,16 @@ def test_reference_written_checkpoint_matches_the_schema():
         assert tuple(sd[k].shape) == shape and sd[k].dtype == dtype, k
 
 
-def test_unsupported_settings_fail_at_construction():
-    """Widths / neighbour counts the fused kernels are not built for are refused when the network is built, with the
-    supported sets in the message — not at the first forward (advisor finding, round 1)."""
+def test_settings_outside_the_fused_kernels():
+    """Any n_neighbors in 1..64 and any layer size that is a multiple of 8 constructs (the fused kernels cover
+    {16,...,256} x {16,32}; the rest runs in row form, tests/test_lfa_rows_gpu.py); what no kernel serves is refused when
+    the network is built, with the supported sets in the message — not at the first forward (advisor finding, round 1)."""
     modules = importlib.import_module("3d_recognizer_b200.modules")
     dev = torch.device("cpu")
-    for kw in (dict(n_neighbors=24), dict(layer_sizes=[16, 64, 96, 256]), dict(n_neighbors=8)):
-        st = modules.RandLANetSettings(**dict(dict(n_classes=2, n_points=4096, n_features=0), **kw))
-        with pytest.raises(ValueError, match="layer_sizes in"):
-            modules.RandLANet(st, dev)
-    modules.RandLANet(modules.RandLANetSettings(n_classes=2, n_points=4096, n_features=0, n_neighbors=32), dev)
+    base = dict(n_classes=2, n_points=4096, n_features=0)
+    for kw in (dict(n_neighbors=24), dict(layer_sizes=[16, 64, 96, 256]), dict(n_neighbors=8), dict(layer_sizes=[8, 24])):
+        modules.RandLANet(modules.RandLANetSettings(**dict(base, **kw)), dev)
+    for kw in (dict(n_neighbors=65), dict(n_neighbors=0), dict(layer_sizes=[16, 20, 64])):
+        with pytest.raises(ValueError, match="multiples of 8"):
+            modules.RandLANet(modules.RandLANetSettings(**dict(base, **kw)), dev)
+    modules.RandLANet(modules.RandLANetSettings(n_neighbors=32, **base), dev)

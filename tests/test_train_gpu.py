@@ -45,9 +45,9 @@ def test_moments_vs_torch(mods, d, K):
     assert rel_err(s_r1[:, 10], r1.sum(0)) < 1e-5
 
 
-def _lfa_block_case(mods, n_in, d, K, N, train, seed):
-    """Errors of one LocalFeatureAggregation block, fused kernels vs the tensor-op composition, both
-    measured against an fp64 run of the composition (the arbiter).  Returns a list of failures."""
+def _lfa_block_case(mods, n_in, d, K, N, train, seed, impl="lfa_block_fused"):
+    """Errors of one LocalFeatureAggregation block, fused kernels (or the row-form kernels, ``impl``) vs the tensor-op
+    composition, both measured against an fp64 run of the composition (the arbiter).  Returns a list of failures."""
     import copy
     modules, engine, _ = mods
     B = 2
@@ -71,7 +71,7 @@ def _lfa_block_case(mods, n_in, d, K, N, train, seed):
     xa = x.clone().requires_grad_(True)
     xb = x.clone().requires_grad_(True)
     xc = x.double().requires_grad_(True)
-    ya = engine.lfa_block_fused(lfa_a, xyz, xa)
+    ya = getattr(engine, impl)(lfa_a, xyz, xa)
     (ya * gout).sum().backward()
     engine.USE_POINTWISE_KERNELS = False            # plain composition: tensor ops only (KNN excepted)
     try:
@@ -235,7 +235,7 @@ def test_train_step_vs_reference_golden(mods, name):
     atomics make the summation order — hence that branch — vary from run to run, so a step whose deviation is such
     a flip is repeated (at most three attempts, all reported on failure)."""
     _, engine, _ = mods
-    assert engine.LFA_IMPL is engine.lfa_block_fused and engine.USE_POINTWISE_KERNELS
+    assert engine.LFA_IMPL is engine.lfa_block_auto and engine.USE_POINTWISE_KERNELS
     history = []
     for _ in range(3):
         fails = _train_step_case(mods, name)
