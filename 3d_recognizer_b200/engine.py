@@ -192,14 +192,39 @@ class _LinearFn(torch.autograd.Function):
         return dx, ops.rowreduce_gemm(dy, x), (dy.sum(dim=0) if ctx.has_bias else None)
 
 
+class _SharedMLPEvalFn(torch.autograd.Function):
+    """SharedMLP with EVAL-mode BatchNorm (running statistics) under autograd, on the same per-point kernels as the
+    training layer: GEMM, normalise + activation from statistics sums synthesised out of the running mean / variance,
+    and for the backward the BatchNorm reduce pass (dgamma, dbeta) plus the dz pass on zero batch sums (dz = a du)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, bn, act, slope):
+        x = x.contiguous()
+        M = x.shape[0]
+        z = ops.pointwise(x.unsqueeze(0), w.contiguous(), w_out_in=True).squeeze(0)
+        mean = (bn.running_mean - bias).double()              # of z, which carries no conv bias
+        stats = torch.cat((mean * M, (bn.running_var.double() + mean * mean) * M))
+        y, save = ops.bn_apply(z, stats, bn, None, act, slope, track=False)
+        ctx.act, ctx.slope = act, slope
+        ctx.save_for_backward(x, w, z, save, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z, save, beta = ctx.saved_tensors
+        dz, dgamma, dbeta = ops.bn_backward_fixed(dy, z, save, beta, ctx.act, ctx.slope)
+        dx = ops.pointwise(dz.unsqueeze(0), w.contiguous()).squeeze(0) if ctx.needs_input_grad[0] else None
+        return dx, ops.rowreduce_gemm(dz, x), save[0] * dbeta, dgamma, dbeta, None, None, None
+
+
 def _kernel_layer_ok(x: torch.Tensor, bn) -> bool:
-    return x.is_cuda and x.dtype == torch.float32 and (bn is None or (bn.training and bn.weight.shape[0] % 4 == 0))
+    return x.is_cuda and x.dtype == torch.float32 and (bn is None or bn.weight.shape[0] % 4 == 0)
 
 
 def shared_mlp(smlp, x: torch.Tensor) -> torch.Tensor:
-    """SharedMLP on a channel-last tensor (..., C_in) -> (..., C_out).  Train mode on a CUDA device runs the
-    per-point kernels (forward and backward); otherwise (eval with gradients, CPU host-logic tests, fp64
-    arbiters) the same math as differentiable tensor ops."""
+    """SharedMLP on a channel-last tensor (..., C_in) -> (..., C_out).  fp32 tensors on a CUDA device run the per-point
+    kernels, forward and backward, with batch statistics (train mode) or the running ones (eval mode under autograd);
+    the CPU host-logic tests and the fp64 arbiters of the GPU tests take the same math as differentiable tensor ops."""
     bn = smlp.batch_norm
     if USE_POINTWISE_KERNELS and _kernel_layer_ok(x, bn):
         w = conv_weight_2d(smlp)
@@ -208,7 +233,8 @@ def shared_mlp(smlp, x: torch.Tensor) -> torch.Tensor:
             y = _LinearFn.apply(x2, w, smlp.conv.bias)
             return _activation(y, smlp.activation).view(*x.shape[:-1], w.shape[0])
         act, slope = _act_of(smlp)
-        y = _SharedMLPTrainFn.apply(x2, w, smlp.conv.bias, bn.weight, bn.bias, bn, act, slope)
+        fn = _SharedMLPTrainFn if bn.training else _SharedMLPEvalFn
+        y = fn.apply(x2, w, smlp.conv.bias, bn.weight, bn.bias, bn, act, slope)
         return y.view(*x.shape[:-1], w.shape[0])
     y = F.linear(x, conv_weight_2d(smlp), smlp.conv.bias)
     if bn is not None:
@@ -652,8 +678,9 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
     inp = inp.float().index_select(1, perm)
     bn0 = net.bn_start[0]
     if USE_POINTWISE_KERNELS and _kernel_layer_ok(inp, bn0):
-        feat = _SharedMLPTrainFn.apply(inp.reshape(B * N, -1), net.fc_start.weight, net.fc_start.bias, bn0.weight,
-                                       bn0.bias, bn0, "lrelu", float(net.bn_start[1].negative_slope)).view(B, N, -1)
+        fn0 = _SharedMLPTrainFn if bn0.training else _SharedMLPEvalFn
+        feat = fn0.apply(inp.reshape(B * N, -1), net.fc_start.weight, net.fc_start.bias, bn0.weight,
+                         bn0.bias, bn0, "lrelu", float(net.bn_start[1].negative_slope)).view(B, N, -1)
     else:
         feat = F.linear(inp, net.fc_start.weight, net.fc_start.bias)
         feat = F.leaky_relu(batch_norm_lastdim(bn0, feat), net.bn_start[1].negative_slope)
@@ -804,12 +831,32 @@ def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Te
     cur = ops.pointwise(inp, w, sc, sh, "lrelu", 0.2, gidx=perm)
     xyz = inp[..., :3].index_select(1, perm64).contiguous()
 
+    # Every neighbour search depends on the coordinates only: the searches of the down-sampled levels and of the decoder's
+    # 1-NN up-sampling run on a side stream while level 0 is processed (as in forward_autograd; 1.8 of 18 ms at 32 x 65 536
+    # points were searches queued behind kernels they do not depend on).
+    L = len(net.encoder)
+    sizes = [N]
+    for _ in range(L):
+        sizes.append(sizes[-1] // dec)           # points kept after each level (floor, modules.py:583)
+    pre_fork, dec_fork, enc_idx, dec_idx = None, None, {}, {}
+    if OVERLAP_WEIGHT_GRADS and L > 1:
+        with _fork(dev, lane=3) as pre_fork:     # joined before level 1
+            for lvl in range(1, L):
+                enc_idx[lvl] = ops.knn(xyz[:, :sizes[lvl]], xyz[:, :sizes[lvl]], k, idx64=False, idx32=True,
+                                       dist=False)["idx32"]
+        with _fork(dev, lane=4) as dec_fork:     # joined before the decoder
+            for lvl in range(L):                 # decoder stage lvl: sizes[L - lvl] -> sizes[L - lvl - 1] points
+                dec_idx[lvl] = ops.knn(xyz[:, :sizes[L - lvl]], xyz[:, :sizes[L - lvl - 1]], 1, idx64=False, idx32=True,
+                                       dist=False)["idx32"]
+
     skips: List[torch.Tensor] = []
     n_l = N
-    for lfa, e in zip(net.encoder, P["encoder"]):
+    for lvl, (lfa, e) in enumerate(zip(net.encoder, P["encoder"])):
         x = cur[:, :n_l]
         xyz_l = xyz[:, :n_l]
-        idx = ops.knn(xyz_l, xyz_l, k, idx64=False, idx32=True, dist=False)["idx32"]
+        if lvl == 1 and pre_fork is not None:
+            pre_fork.join()
+        idx = enc_idx[lvl] if lvl in enc_idx else ops.knn(xyz_l, xyz_l, k, idx64=False, idx32=True, dist=False)["idx32"]
         w, sc, sh = e["mlp1"]
         f = ops.pointwise(x, w, sc, sh, "lrelu", 0.2)
         w1, a1, b1 = e["rpe1"]
@@ -829,10 +876,13 @@ def forward_kernels(net, inp: torch.Tensor, permutation: np.ndarray) -> torch.Te
         n_l //= dec
     w, sc, sh = P["mlp"]
     cur = ops.pointwise(cur[:, :n_l], w, sc, sh, "relu")
-    for w, sc, sh in P["decoder"]:
+    if dec_fork is not None:
+        dec_fork.join()
+    for lvl, (w, sc, sh) in enumerate(P["decoder"]):
         skip = skips.pop()
         n_up = skip.shape[1]
-        nn1 = ops.knn(xyz[:, :n_l], xyz[:, :n_up], 1, idx64=False, idx32=True, dist=False)["idx32"]
+        nn1 = (dec_idx[lvl] if lvl in dec_idx else
+               ops.knn(xyz[:, :n_l], xyz[:, :n_up], 1, idx64=False, idx32=True, dist=False)["idx32"])
         cur = ops.pointwise(cur, w, sc, sh, "relu", gidx=nn1.view(B, n_up), xb=skip)
         n_l = n_up
     inv = torch.empty_like(perm)

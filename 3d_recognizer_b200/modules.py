@@ -143,7 +143,11 @@ class LocalFeatureAggregation(torch.nn.Module):
         """xyz (B,N,3), input (B,n_in,N,1) -> (B, 2*n_out, N, 1)."""
         if knn_approach not in _KNN_APPROACHES:
             raise ValueError(f"KNN approach {knn_approach} not understood!")
-        y = engine.lfa_block(self, xyz.to(self._device), input.squeeze(-1).transpose(1, 2))
+        xyz, x = xyz.to(self._device), input.squeeze(-1).transpose(1, 2)
+        if x.is_cuda and x.dtype == torch.float32 and self.mlp1.conv.weight.shape[0] % 4 == 0:
+            y = engine.lfa_block_auto(self, xyz.float(), x)       # the sm_100a kernels (fused, or row form)
+        else:
+            y = engine.lfa_block(self, xyz, x)                     # CPU host-logic tests, fp64 arbiters
         return y.transpose(1, 2).unsqueeze(-1)
 
 

@@ -616,14 +616,14 @@ def upsample_bwd(approach: str, dout: torch.Tensor, idx: torch.Tensor, dist: Opt
 
 
 def bn_apply(z: torch.Tensor, stats: torch.Tensor, bn: torch.nn.BatchNorm2d, bias: Optional[torch.Tensor], act,
-             slope: float = 0.0):
+             slope: float = 0.0, track: bool = True):
     """Train-mode BatchNorm + activation of a per-point layer (C ABI ``r3d_bn_apply``): z (M,C) conv output without
     bias, stats (2C) fp64 from ``pointwise(..., stats=)``.  Updates bn's running statistics in place.
     Returns (y (M,C), save (3,C) = a, mean, rstd)."""
     M, C = z.shape
     y = torch.empty_like(z)
     save = torch.empty((3, C), dtype=torch.float32, device=z.device)
-    track = bn.track_running_stats and bn.running_mean is not None
+    track = track and bn.track_running_stats and bn.running_mean is not None
     with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_apply[M={M},C={C}]", flops=4.0 * M * C, bytes=8.0 * M * C):
         rc = _cabi.lib().r3d_bn_apply(_cabi.ptr(z), _cabi.ptr(stats), M, C, _cabi.ptr(bn.weight.detach()),
                                       _cabi.ptr(bn.bias.detach()), _cabi.ptr(bias.detach()) if bias is not None else None,
@@ -691,6 +691,25 @@ def bn_backward(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: tor
                                  _cabi.stream_ptr(z.device))
     _cabi.check(rc, "r3d_bn_bwd")
     return dz, s2[C:], s2[:C]
+
+
+def bn_backward_fixed(dy: torch.Tensor, z: torch.Tensor, save: torch.Tensor, beta: torch.Tensor, act, slope: float = 0.0):
+    """Backward of an EVAL-mode BatchNorm(+activation) (fixed statistics): the reduce pass gives dbeta = sum du and
+    dgamma = sum du zhat, and the dz pass run on zero batch sums is dz = a du (C ABI ``r3d_bn_bwd_reduce`` +
+    ``r3d_bn_bwd_dz``).  Returns (dz (M,C), dgamma (C), dbeta (C))."""
+    M, C = z.shape
+    dy = dy.contiguous()
+    sums = zeros(4 * C, torch.float64, z.device)        # [0:2C] the reduce pass' sums, [2C:4C] stays zero
+    dz = torch.empty_like(z)
+    L = _cabi.lib()
+    with torch.cuda.device(z.device), _cabi.kernel_timer(f"bn_backward[M={M},C={C}]", flops=12.0 * M * C, bytes=20.0 * M * C):
+        rc = L.r3d_bn_bwd_reduce(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act], float(slope),
+                                 _cabi.ptr(sums), _cabi.stream_ptr(z.device))
+        _cabi.check(rc, "r3d_bn_bwd_reduce")
+        rc = L.r3d_bn_bwd_dz(_cabi.ptr(dy), _cabi.ptr(z), M, C, _cabi.ptr(save), _cabi.ptr(beta), _ACT[act], float(slope),
+                             _cabi.ptr(sums[2 * C:]), _cabi.ptr(dz), None, _cabi.stream_ptr(z.device))
+    _cabi.check(rc, "r3d_bn_bwd_dz")
+    return dz, sums[C:2 * C].float(), sums[:C].float()
 
 
 def rowreduce_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

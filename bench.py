@@ -551,6 +551,19 @@ def main():
             def dev_step(i):
                 model.predict_device(x_d[i % pool])
 
+            def eager_step(i):                           # instrumented pass: the network's launches one by one
+                model.use_cuda_graphs = False
+                try:
+                    model.predict_device(x_d[i % pool])
+                finally:
+                    model.use_cuda_graphs = True
+
+            def build_graph():                           # Model.predict captures the network's eval forward itself
+                model.predict_device(x_d[0])
+
+            if args.no_graph:
+                model.use_cuda_graphs, build_graph = False, None
+
             def e2e_step(i):
                 model.predict(frames[i % pool])          # numpy in, numpy out: H2D, forward, up-sampling, D2H
 

@@ -302,3 +302,35 @@ def test_train_step_40960x2_vs_oracle_port(mods):
     assert worst_l2 < 1e-2, (worst_l2, wname)
     assert fracs[3e-3] >= 0.999, fracs
     importlib.import_module("3d_recognizer_b200.ops").check_tc_status(torch.device("cuda"))
+
+
+def test_graphed_predict_matches_eager():
+    """Model.predict replays the network's eval forward from a CUDA graph (model.GraphedEvalForward): same confidences
+    as the eager launches on the same numpy stream, for frames of different sizes (the graph is keyed by the sampled
+    shape, not by the frame), and the graph is rebuilt when a weight changes."""
+    model_mod = importlib.import_module("3d_recognizer_b200.model")
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+    st = dict(n_classes=2, n_points=2500, n_features=0, n_neighbors=32, knn="naive")
+    m = model_mod.Model(modules.RandLANetSettings(**st), weights=onet.synth_state_dict(st, 21))
+    rng = np.random.RandomState(4)
+
+    def both(frame):
+        m.use_cuda_graphs = True
+        np.random.seed(11)
+        a = m.predict(frame)
+        m.use_cuda_graphs = False
+        np.random.seed(11)
+        b = m.predict(frame)
+        m.use_cuda_graphs = True
+        return a, b
+
+    for n in (30, 7000, 50000, 7000):                     # 30: the warm-up call of predict.py:22-24
+        a, b = both(rng.rand(n, 3).astype(np.float32))
+        assert a.shape == (2, n) and np.array_equal(a, b)
+    assert len(m._eval_graphs) == 1
+    first = next(iter(m._eval_graphs.values()))
+    with torch.no_grad():
+        m.module.fc_end[3].conv.bias.add_(0.25)           # a training step would do the same to every parameter
+    a, b = both(rng.rand(9000, 3).astype(np.float32))
+    assert np.array_equal(a, b)
+    assert next(iter(m._eval_graphs.values())) is not first

@@ -187,6 +187,45 @@ def _shared_mlp_train_case(mods, M, cin, cout, act):
             assert int(va) == int(vc) == 1
 
 
+@pytest.mark.parametrize("M,cin,cout,act", [(5000, 8, 8, "lrelu"), (1237, 3, 8, "lrelu"), (2048, 64, 32, "relu"),
+                                            (700, 512, 512, "relu"), (40000, 16, 32, None), (16384, 64, 128, "relu")])
+def test_shared_mlp_eval_kernels_vs_torch(mods, M, cin, cout, act):
+    """EVAL-mode SharedMLP under autograd (running statistics; engine._SharedMLPEvalFn): output, dx, dW, conv-bias, gamma
+    and beta gradients from the per-point kernels vs fp64 tensor ops; the running statistics must not move."""
+    import copy
+    modules, engine, _ = mods
+    dev = torch.device("cuda")
+    torch.manual_seed(M + cin + 1)
+    activation = {"relu": torch.nn.ReLU(), "lrelu": torch.nn.LeakyReLU(0.2), None: None}[act]
+    la = modules.SharedMLP(cin, cout, activation=activation).to(dev)
+    with torch.no_grad():
+        la.batch_norm.weight.uniform_(0.7, 1.3)
+        la.batch_norm.bias.normal_(0, 0.1)
+        la.batch_norm.running_mean.normal_(0, 0.3)
+        la.batch_norm.running_var.uniform_(0.5, 1.5)
+        la.conv.bias.normal_(0, 0.2)
+    lc = copy.deepcopy(la).double()
+    la.eval()
+    lc.eval()
+    before = {k: v.clone() for k, v in la.state_dict().items()}
+    x = torch.randn(2, M // 2, cin, device=dev) * 0.7 + 0.3
+    g = torch.randn(2, M // 2, cout, device=dev)
+    xa = x.clone().requires_grad_(True)
+    xc = x.double().requires_grad_(True)
+    ya = engine.shared_mlp(la, xa)
+    # the kernel path, not the tensor-op one (ya is a view of the function's output)
+    assert "_SharedMLPEvalFn" in type(ya.grad_fn.next_functions[0][0]).__name__
+    yc = engine.shared_mlp(lc, xc)
+    assert rel_err(ya.detach(), yc.detach()) < 1e-5
+    (ya * g).sum().backward()
+    (yc * g.double()).sum().backward()
+    assert rel_err(xa.grad, xc.grad) < TOL
+    for (k, pa), (_, pc) in zip(la.named_parameters(), lc.named_parameters()):
+        assert rel_err(pa.grad.view_as(pc.grad), pc.grad) < TOL, k
+    for k, v in la.state_dict().items():
+        assert torch.equal(v, before[k]), k
+
+
 def _train_step_case(mods, name):
     """One training step against the reference's golden vectors; returns the list of violated bars."""
     modules, engine, _ = mods
