@@ -67,6 +67,10 @@ SIGNATURES = {
     "r3d_lfa_attn_pool": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
     "r3d_lfa_attn_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int,
                                       c_void_p]),
+    "r3d_add_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_float, c_void_p]),
+    "r3d_add_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_float, c_void_p]),
+    "r3d_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_double,
+                              ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p]),
     "r3d_bn_from_moments": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
                                     c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -583,7 +583,55 @@ def lfa_block_fused(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tenso
         sc_fork.join()
     else:
         sc = shared_mlp(lfa.shortcut, feat)
-    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + sc, 0.01)
+    return residual_lrelu(shared_mlp(lfa.mlp2, p2), sc, 0.01)
+
+
+class _SkipAndPrefixFn(torch.autograd.Function):
+    """An encoder level's output is used twice: whole, as the decoder's skip connection, and its first n points per cloud
+    (random down-sampling = a prefix of the permuted cloud, modules.py:583) as the next level's input.  Plain autograd
+    turns that into a zero-filled full-size tensor, a copy of the prefix gradient into it and a full-size sum; here the
+    prefix gradient is added onto the skip gradient's first n rows (a quarter of the tensor, one launch)."""
+
+    @staticmethod
+    def forward(ctx, out, n):
+        ctx.n, ctx.shape = n, out.shape
+        return out.view_as(out), out[:, :n].contiguous()
+
+    @staticmethod
+    def backward(ctx, dskip, dprefix):
+        if dprefix is None:
+            return dskip, None
+        if dskip is None:
+            total = torch.zeros(ctx.shape, dtype=dprefix.dtype, device=dprefix.device)
+        else:
+            # the fresh output of the decoder's up-sampling backward; this node is its only consumer
+            total = dskip if dskip.is_contiguous() else dskip.contiguous()
+        total[:, :ctx.n].add_(dprefix)
+        return total, None
+
+
+class _AddLReluFn(torch.autograd.Function):
+    """LeakyReLU(a + b) — the residual sum that closes an LFA block (modules.py:325) — as one launch each way
+    (ops.add_lrelu / add_lrelu_bwd): the backward's single output is the gradient of both summands."""
+
+    @staticmethod
+    def forward(ctx, a, b, slope):
+        y = ops.add_lrelu(a, b, slope)
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        d = ops.add_lrelu_bwd(dy, y, ctx.slope)
+        return d, d, None
+
+
+def residual_lrelu(a: torch.Tensor, b: torch.Tensor, slope: float = 0.01) -> torch.Tensor:
+    if a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape:
+        return _AddLReluFn.apply(a, b, slope)
+    return F.leaky_relu(a + b, slope)
 
 
 # ------------------------------------------------- row-form LFA block: any n_neighbors, any layer size
@@ -638,7 +686,7 @@ def lfa_block_rows(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor
     X2 = _GatherConcatFn.apply(r2, p1, idx)
     S2 = _LinearFn.apply(X2, lfa.pool2.score_fn[0].weight, None)
     p2 = shared_mlp(lfa.pool2.mlp, _AttnPoolFn.apply(S2, X2, K).view(B, N, -1))
-    return F.leaky_relu(shared_mlp(lfa.mlp2, p2) + sc, 0.01)
+    return residual_lrelu(shared_mlp(lfa.mlp2, p2), sc, 0.01)
 
 
 def lfa_block_auto(lfa, xyz: torch.Tensor, feat: torch.Tensor, idx: torch.Tensor = None, wT=None) -> torch.Tensor:
@@ -714,11 +762,14 @@ def forward_autograd(net, inp: torch.Tensor, permutation) -> torch.Tensor:
             pre_fork.join()
         out = (LFA_IMPL(lfa, xyz[:, :n_l], cur, enc_idx[lvl], enc_wT.get(lvl)) if lvl in enc_idx
                else LFA_IMPL(lfa, xyz[:, :n_l], cur))
-        skips.append(out)
         n_l //= dec
         # random down-sampling = a prefix of the permuted cloud (modules.py:583); one dense copy here instead of one in
         # every consumer of the strided view (mlp1 and shortcut of the next block, forward and backward)
-        cur = out[:, :n_l].contiguous() if out.is_cuda else out[:, :n_l]
+        if out.is_cuda and out.requires_grad:
+            out, cur = _SkipAndPrefixFn.apply(out, n_l)
+        else:
+            cur = out[:, :n_l].contiguous() if out.is_cuda else out[:, :n_l]
+        skips.append(out)
     cur = shared_mlp(net.mlp, cur)
     for lvl, stage in enumerate(net.decoder):
         n_up = skips[-1].shape[1]          # N // dec^(l-1): the encoder level this stage returns to

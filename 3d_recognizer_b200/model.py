@@ -24,7 +24,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import engine, losses
+from . import engine, losses, ops
 from .modules import RandLANet, RandLANetSettings, UpSampler
 from .preprocessing import sample_points
 
@@ -202,7 +202,8 @@ class FlatAdam(torch.optim.Adam):
     gradient buffer with one multi-tensor copy (parameters without a gradient — conv biases in front of a
     train-mode BatchNorm — keep a zero slot, which leaves them untouched exactly as skipping them does: no weight
     decay).  With data parallelism the all-reduced buffer of ``parallel.FlatGradients`` (same parameter order) is
-    used directly (``bind_flat_gradients``).  The arithmetic per element is torch's own fused Adam."""
+    used directly (``bind_flat_gradients``).  The update itself is the library's ``r3d_adam_step`` (torch.optim.Adam's
+    arithmetic per element; weight decay / amsgrad / maximize fall back to torch's fused kernel)."""
 
     def __init__(self, module: torch.nn.Module, lr, capturable: bool):
         self._module_params = [p for p in module.parameters() if p.requires_grad]
@@ -241,7 +242,21 @@ class FlatAdam(torch.optim.Adam):
             if dst:
                 torch._foreach_copy_(dst, src)
             self._flat.grad = self._flat_grad
-        return super().step(closure)
+        group = self.param_groups[0]
+        if not self._flat.is_cuda or group["amsgrad"] or group["weight_decay"] != 0 or group["maximize"]:
+            return super().step(closure)
+        # the library's own update kernel (csrc/elementwise.cu): the state keeps torch.optim.Adam's layout (step as a
+        # device scalar, exp_avg, exp_avg_sq), so state_dict() / load_state_dict() and lr schedulers work unchanged
+        loss = closure() if closure is not None else None
+        st = self.state[self._flat]
+        if len(st) == 0:
+            st["step"] = torch.zeros((), dtype=torch.float32, device=self._flat.device)
+            st["exp_avg"] = torch.zeros_like(self._flat.data)
+            st["exp_avg_sq"] = torch.zeros_like(self._flat.data)
+        beta1, beta2 = group["betas"]
+        ops.adam_step(self._flat.data, self._flat.grad, st["exp_avg"], st["exp_avg_sq"], st["step"], group["lr"], beta1,
+                      beta2, group["eps"])
+        return loss
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self._module_params:

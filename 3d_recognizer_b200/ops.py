@@ -549,6 +549,49 @@ def lfa_pool_rows(stage: int, xyz, idx32, feat, w_rpe1, a_rpe1, b_rpe1, w_rpe2T,
     return lfa_attn_pool(S, X, K).view(B, N, -1)
 
 
+# ------------------------------------------------------------------------- element-wise pieces of the training step
+def add_lrelu(a: torch.Tensor, b: torch.Tensor, slope: float) -> torch.Tensor:
+    """LeakyReLU_slope(a + b) in one launch (C ABI ``r3d_add_lrelu``): the residual sum closing an LFA block."""
+    _cabi.require_cuda(a, "a")
+    a, b = a.detach().contiguous(), b.detach().contiguous()
+    assert a.shape == b.shape and a.dtype == b.dtype == torch.float32
+    y = torch.empty_like(a)
+    n = a.numel()
+    with torch.cuda.device(a.device), _cabi.kernel_timer("add_lrelu", flops=2.0 * n, bytes=12.0 * n):
+        rc = _cabi.lib().r3d_add_lrelu(_cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(y), n, float(slope), _cabi.stream_ptr(a.device))
+    _cabi.check(rc, "r3d_add_lrelu")
+    return y
+
+
+def add_lrelu_bwd(dy: torch.Tensor, y: torch.Tensor, slope: float) -> torch.Tensor:
+    """dy * LeakyReLU'(a + b) from the sign of y (C ABI ``r3d_add_lrelu_bwd``): the gradient of both summands."""
+    dy = dy.contiguous()
+    d = torch.empty_like(y)
+    n = y.numel()
+    with torch.cuda.device(y.device), _cabi.kernel_timer("add_lrelu_bwd", flops=1.0 * n, bytes=12.0 * n):
+        rc = _cabi.lib().r3d_add_lrelu_bwd(_cabi.ptr(dy), _cabi.ptr(y), _cabi.ptr(d), n, float(slope), _cabi.stream_ptr(y.device))
+    _cabi.check(rc, "r3d_add_lrelu_bwd")
+    return d
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: torch.Tensor, lr, beta1: float,
+              beta2: float, eps: float) -> None:
+    """torch.optim.Adam's update over flat fp32 buffers, in place (C ABI ``r3d_adam_step``).  ``step``: device scalar
+    (fp32) advanced by one; ``lr``: a float or a device scalar tensor (a scheduler writes into it)."""
+    _cabi.require_cuda(p, "p")
+    n = p.numel()
+    assert g.numel() == m.numel() == v.numel() == n and all(t.is_contiguous() and t.dtype == torch.float32 for t in (p, g, m, v))
+    assert step.dtype == torch.float32 and step.is_cuda
+    lr_dev = lr if isinstance(lr, torch.Tensor) else None
+    if lr_dev is not None:
+        assert lr_dev.is_cuda and lr_dev.dtype == torch.float32
+    with torch.cuda.device(p.device), _cabi.kernel_timer("adam_step", flops=12.0 * n, bytes=28.0 * n):
+        rc = _cabi.lib().r3d_adam_step(_cabi.raw(p), _cabi.raw(g), _cabi.raw(m), _cabi.raw(v), n, _cabi.raw(lr_dev),
+                                       0.0 if lr_dev is not None else float(lr), float(beta1), float(beta2), float(eps),
+                                       _cabi.raw(step), _cabi.stream_ptr(p.device))
+    _cabi.check(rc, "r3d_adam_step")
+
+
 UP_WEIGHTING = {"nni": (0, 1.0), "nna": (1, 1.0), "idw": (1, 1.0), "isdw": (1, 2.0), "mean": (2, 1.0)}
 
 

@@ -275,6 +275,19 @@ int r3d_lfa_attn_pool(const float* S, const float* X, float* pooled, long long p
 int r3d_lfa_attn_pool_bwd(const float* S, const float* X, const float* dpooled, float* dS, float* dX, long long points,
                           int K, int d, r3d_stream_t stream);
 
+/* ------------------------------------------------------------------ element-wise pieces of the training step
+ * r3d_add_lrelu      y = LeakyReLU_slope(a + b): the residual sum that closes an LFA block (modules.py:325, slope 0.01)
+ * r3d_add_lrelu_bwd  d = dy * LeakyReLU'(a + b), from the sign of y (slope > 0); d is the gradient of BOTH summands
+ * r3d_adam_step      torch.optim.Adam's update (trainer.py:78-81: no weight decay, no amsgrad) over flat fp32 buffers
+ *                    p, g, m, v (n elements).  step: device scalar (fp32), advanced by one inside the call, so that the
+ *                    update can be replayed from a CUDA graph; lr_dev (nullable): device scalar that overrides lr_host
+ *                    (a scheduler updates it in place).
+ * n elements, pointers of the add kernels 16-byte aligned. */
+int r3d_add_lrelu(const float* a, const float* b, float* y, long long n, float slope, r3d_stream_t stream);
+int r3d_add_lrelu_bwd(const float* dy, const float* y, float* d, long long n, float slope, r3d_stream_t stream);
+int r3d_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, double lr_host,
+                  double beta1, double beta2, double eps, float* step, r3d_stream_t stream);
+
 /* ------------------------------------------------------------------------- Focal-Tversky / Dice loss
  * randlanet/utils/losses.py:66-86 via trainer.py:245-269: p = softmax over classes, TI_c = (TP_c + eps) /
  * (TP_c + alpha FN_c + (1 - alpha) FP_c + eps), loss = mean over classes >= first_class of (1 - TI_c)^gamma.
