@@ -28,6 +28,14 @@
 
 namespace r3d {
 
+// unroll factors of the softmax / dS loop over a sub-tile's points (phase C) and of the scatter loop (phase D): the fully
+// unrolled tile loop is ~52 KB of SASS, more than the instruction caches hold with three warp roles in flight
+#ifndef R3D_CL_UNROLL_C
+#define R3D_CL_UNROLL_C 1
+#endif
+#ifndef R3D_CL_UNROLL_D
+#define R3D_CL_UNROLL_D 1
+#endif
 constexpr int kClFlush = 8;       // tiles of a group between two folds of its first-level accumulator
 
 struct LfaClBwdArgs {
@@ -473,7 +481,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
 #pragma unroll
                 for (int k0 = 0; k0 < K; k0 += 16) tmem_ld16_nowait(tacc + (uint32_t)k0, *reinterpret_cast<uint32_t(*)[16]>(un + k0));
                 tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
                 for (int p = 0; p < C::PTS; ++p) {
                     float s[K], x[K];
 #pragma unroll
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     uint32_t un[16];
                     tmem_ld16_nowait(tacc, un);
                     tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
                     for (int c0 = 0; c0 < R; c0 += 16) {
                         uint32_t u[16];
 #pragma unroll
