@@ -250,6 +250,7 @@ __device__ __forceinline__ int cl_unit_off(int l, int ng) {
 // D[tmem] (+)= A B^T over `ksteps` K steps of 16, three split products per step.
 //   a_*: hi/lo plane addresses of the A operand, a_lbo / a_sbo its core-matrix strides along K / along M
 //   b_*: likewise for B.   The per-step advance along K is two core matrices: 2 * lbo.
+template <int UNROLL = 2>
 __device__ __forceinline__ void cl_mma_3x(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo,
                                           uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
                                           int ksteps, bool accumulate) {
@@ -257,11 +258,11 @@ __device__ __forceinline__ void cl_mma_3x(uint32_t tmem_d, uint32_t a_hi, uint32
     // waiting for the tensor core) and, fully unrolled with all five call sites of the backward, it is ~30 KB of SASS
     // competing with the worker groups for the instruction cache.  So: descriptors are built once and advanced by adding
     // the K-step increment to their 14-bit address field (shared-memory addresses stay below 2^18, no carry into the
-    // stride fields), and the loop is unrolled by two only.
+    // stride fields), and the loop is unrolled by two only (UNROLL: kernels with a single call site take four).
     uint64_t ah = umma_desc_b(a_hi, a_lbo, a_sbo), al = umma_desc_b(a_lo, a_lbo, a_sbo);
     uint64_t bh = umma_desc_b(b_hi, b_lbo, b_sbo), bl = umma_desc_b(b_lo, b_lbo, b_sbo);
     const uint64_t ia = (uint64_t)((2 * a_lbo) >> 4), ib = (uint64_t)((2 * b_lbo) >> 4);
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int ks = 0; ks < ksteps; ++ks) {
         umma_f16(tmem_d, ah, bh, idesc, (accumulate || ks > 0) ? 1u : 0u);
         umma_f16(tmem_d, ah, bl, idesc, 1u);

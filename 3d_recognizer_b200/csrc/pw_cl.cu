@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NSETS * kPcLoaders + 32, NSETS == 1 ? 2 : 1) p
                 mbar_wait(&full[s], ph);
                 tc_fence_after_sync();
                 const uint32_t xhi = smem_u32(smem + L.off_st + s * L.stage);
-                cl_mma_3x(tmem + s * kPcRows, smem_u32(Whi), smem_u32(Wlo), kPcWIS, 128, xhi, xhi + L.x_bytes, kPcCS, 128,
+                cl_mma_3x<4>(tmem + s * kPcRows, smem_u32(Whi), smem_u32(Wlo), kPcWIS, 128, xhi, xhi + L.x_bytes, kPcCS, 128,
                           idesc, ksteps, false);
                 umma_commit(&empty[s]);
                 umma_commit(&accfull[s]);
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_wgrad_kernel(PcWgradArgs a) 
                 tc_fence_after_sync();
                 const uint32_t base = smem_u32(smem + s * S::STAGE);
                 // contraction over the stage's 64 rows: K-step = 2 row groups (256 B), LBO = row-group stride, SBO = channel-group stride
-                cl_mma_3x(tmem + buf * 128, base, base + S::PLANE, 128, kPcCS, base + 2 * S::PLANE, base + 3 * S::PLANE, 128, kPcCS,
+                cl_mma_3x<4>(tmem + buf * 128, base, base + S::PLANE, 128, kPcCS, base + 2 * S::PLANE, base + 3 * S::PLANE, 128, kPcCS,
                           idesc, kPcRows / 16, it % kPcFold != 0);
                 umma_commit(&empty[s]);
                 if (it % kPcFold == kPcFold - 1 || it == nst - 1) umma_commit(&accfull[buf]);
