@@ -280,6 +280,7 @@ def roofline_of(tab, peaks, fp32_peak):
         return dict(kernel=name, launches=f["launches"], ms_avg=f["ms"] / n, traffic=None, shapes=sorted(f["shapes"]),
                     algorithmic_flops_per_launch=f["flops"] / n, algorithmic_bytes_per_launch=f["bytes"] / n,
                     bound="tensor", achieved=ach, peak=tpeak, unit="TFLOP/s", frac=ach / tpeak,
+                    vs_fp32_pipe=ach / fp32_peak["ffma"],       # > 1: more than the FP32 pipe could deliver at its peak
                     peak_source=peaks["source"] + ": dense bf16/fp16 tensor peak, sustained; fp32-accurate split-fp16 "
                                 "issues 3 MMAs per algorithmic product (attainable <= 1/3 of this peak)")
     common = dict(kernel=name, launches=f["launches"], ms_avg=f["ms"] / n, traffic=None, shapes=sorted(f["shapes"]),
@@ -422,6 +423,8 @@ def compose_line(*, metric, value, unit, world, args, ms_per_step, wl, name, n, 
     if roof:
         roof_short = {a: _r(roof[a]) for a in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic")}
         roof_short["launches"] = roof["launches"]
+        if "vs_fp32_pipe" in roof:
+            roof_short["vs_fp32_pipe"] = _r(roof["vs_fp32_pipe"])
     cpu_short = None
     if cpu_base:
         cpu_short = dict(value=_r(cpu_base["value"]), unit=cpu_base["unit"], cores=cpu_base["cores"],
