@@ -50,6 +50,7 @@ WORKLOADS = {
     # one rank's shard of train40960 on 8 / 4 GPUs, run on ONE GPU: the diagnostic for the strong-scaling tail
     "train40960_b8": dict(kind="train", n=40960, k=16, global_batch=8, scaling="strong"),
     "train40960_b16": dict(kind="train", n=40960, k=16, global_batch=16, scaling="strong"),
+    "infer64k_b4": dict(kind="infer", n=65536, k=16, global_batch=4, scaling="strong"),
     "infer16k": dict(kind="infer", n=16384, k=16, global_batch=32, scaling="strong"),
     "infer64k": dict(kind="infer", n=65536, k=16, global_batch=32, scaling="strong"),
     "infer256k": dict(kind="infer", n=262144, k=16, global_batch=32, scaling="strong"),
@@ -604,15 +605,23 @@ def main():
             model.module.eval()
             res_h = torch.empty((batch, 2, n), dtype=torch.float32).pin_memory()
 
-            def dev_step(i):
+            def eager_step(i):                           # instrumented pass: the launches one by one
                 with torch.no_grad():
                     model.module(x_d[i % pool])
 
+            def dev_step(i):                             # Model.infer: CUDA-graph replay per input shape
+                model.infer(x_d[i % pool])
+
+            def build_graph():
+                model.infer(x_d[0])
+
             def e2e_step(i):
-                with torch.no_grad():
-                    logits = model.module(x_h[i % pool].to(dev, non_blocking=True))
-                    res_h.copy_(logits, non_blocking=True)
+                logits = model.infer(x_h[i % pool].to(dev, non_blocking=True))
+                res_h.copy_(logits, non_blocking=True)
                 torch.cuda.synchronize()
+
+            if args.no_graph:
+                model.use_cuda_graphs, build_graph = False, None
 
             h2d, d2h = batch * n * 12, batch * n * 2 * 4
 

@@ -334,3 +334,20 @@ def test_graphed_predict_matches_eager():
     a, b = both(rng.rand(9000, 3).astype(np.float32))
     assert np.array_equal(a, b)
     assert next(iter(m._eval_graphs.values())) is not first
+
+
+def test_model_infer_matches_module_forward():
+    """Model.infer (eval forward replayed from a CUDA graph per input shape) == module(x) on the same numpy stream."""
+    model_mod = importlib.import_module("3d_recognizer_b200.model")
+    modules = importlib.import_module("3d_recognizer_b200.modules")
+    st = dict(n_classes=2, n_points=4096, n_features=0, n_neighbors=16, knn="naive")
+    m = model_mod.Model(modules.RandLANetSettings(**st), weights=onet.synth_state_dict(st, 7))
+    for B, N in ((2, 4096), (3, 2048), (2, 4096)):
+        x = torch.from_numpy(make_input(B, N, 0, B + N)).cuda()
+        np.random.seed(5)
+        a = m.infer(x)
+        np.random.seed(5)
+        with torch.no_grad():
+            b = m.module(x)
+        assert a.shape == (B, 2, N) and torch.equal(a, b)
+    assert len(m._eval_graphs) == 2
