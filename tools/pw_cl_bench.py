@@ -31,7 +31,26 @@ WGRAD = [(40960, 256, 1024), (163840, 256, 128), (40960, 512, 256), (163840, 128
          (655360, 128, 64), (655360, 128, 32), (40960, 128, 256), (10240, 512, 512), (163840, 128, 128),
          (655360, 64, 64), (2621440, 32, 64), (2621440, 8, 64), (2621440, 16, 16)]
 
+# one rank's shard of train40960 on 8 GPUs (8 clouds): the layers whose dispatch decides the strong-scaling tail
+SHARD_GEMM = [(5120, 256, 512), (5120, 256, 1024), (5120, 1024, 256), (20480, 256, 128), (5120, 512, 256), (20480, 512, 128),
+              (1280, 512, 512), (5120, 256, 256), (5120, 128, 256), (5120, 256, 128), (20480, 128, 128), (20480, 64, 128)]
+SHARD_WGRAD = [(5120, 512, 256), (5120, 256, 1024), (5120, 128, 256), (1280, 512, 512), (5120, 256, 256), (20480, 256, 128),
+               (327680, 64, 8), (327680, 32, 16)]
+
 if __name__ == "__main__":
+    if "--shard" in sys.argv:
+        GEMM, WGRAD = SHARD_GEMM, SHARD_WGRAD
+        L = importlib.import_module("3d_recognizer_b200._cabi").lib()
+        print("fwd GEMM, forced round-1 3xTF32 kernel (r3d_pointwise_set_tensor_cores(2)) vs default dispatch")
+        for M, cin, cout in GEMM:
+            x = torch.randn(M, cin, device="cuda")
+            wT = (torch.randn(cout, cin, device="cuda") * 0.1).t().contiguous()
+            stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+            t0 = timeit(lambda: ops.pointwise(x.unsqueeze(0), wT, stats=stats))
+            prev = L.r3d_pointwise_set_tensor_cores(2)
+            t1 = timeit(lambda: ops.pointwise(x.unsqueeze(0), wT, stats=stats))
+            L.r3d_pointwise_set_tensor_cores(prev)
+            print(f"M={M:8d} {cin:4d}->{cout:4d}   default {t0:8.3f}   pw_tc {t1:8.3f}")
     print("fwd / dgrad GEMM              fp32 ms   tc ms   tc TFLOP/s   tc GB/s")
     for M, cin, cout in GEMM:
         x = torch.randn(M, cin, device="cuda")
