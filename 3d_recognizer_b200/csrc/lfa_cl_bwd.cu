@@ -514,7 +514,13 @@ __global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) lfa_cl_bwd_kernel(LfaClB
                     }
                     const float inv = 1.0f / (den0 + den1);
                     const float pooled = (num0 + num1) * inv;             // scaled by sx like x
-                    const float gi = gpre[p] * sg * inv;
+                    // the point loop is rolled (code size): select this point's gradient with static indices so that
+                    // gpre stays in registers and its loads stay in flight across the accumulator wait (as a local-memory
+                    // array the loads had to land before the wait: 11 % of the warp samples of the d = 64 pass 1)
+                    float gsel = gpre[0];
+#pragma unroll
+                    for (int q = 1; q < C::PTS; ++q) gsel = (p == q) ? gpre[q] : gsel;
+                    const float gi = gsel * sg * inv;
 #pragma unroll
                     for (int k0 = 0; k0 < K; k0 += 16) {
                         uint32_t u[16];
