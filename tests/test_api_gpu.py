@@ -160,12 +160,14 @@ def test_train_step_16k_vs_oracle_port(mods):
     raise AssertionError(("no seed met the strict gradient bar", history))
 
 
-def test_graphed_train_step_matches_eager(mods):
+@pytest.mark.parametrize("extra", [{}, dict(n_neighbors=8, layer_sizes=[16, 24, 64])], ids=["fused", "row_form"])
+def test_graphed_train_step_matches_eager(mods, extra):
     """GraphedTrainStep (CUDA-graph replay) follows the same loss trajectory as eager Model.train_step from the
-    same weights, data and numpy seed (Dropout off so that both paths are deterministic functions of those)."""
+    same weights, data and numpy seed (Dropout off so that both paths are deterministic functions of those).
+    ``row_form``: settings outside the fused kernels' template lists (csrc/lfa_rows.cu) capture and replay too."""
     modules, _, model_mod = mods
     syn = importlib.import_module("3d_recognizer_b200.synthetic")
-    st = modules.RandLANetSettings(n_classes=2, n_points=1024, n_features=0, n_neighbors=16, knn="naive")
+    st = modules.RandLANetSettings(**dict(dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=16, knn="naive"), **extra))
     torch.manual_seed(3)
     a = model_mod.Model(st)
     b = model_mod.Model(st, weights=copy.deepcopy(a.module.state_dict()))
