@@ -481,19 +481,22 @@ __global__ void __launch_bounds__(NT, (D <= 16 ? 4 : (D <= 64 ? 3 : (FINE ? 2 : 
 // Moments of the position encoding (r3d_lfa_moments mode 0) as an HBM-streaming kernel: they depend on the coordinates
 // and the neighbour lists only, any width.  A thread walks rows with the grid stride, accumulates the 66 distinct
 // products of e = [rpe(10), 1] over at most 16 rows in fp32, then the warp reduces them in fp64 and adds them to the
-// CTA's fp64 shared-memory matrix; one global fp64 atomic per entry and CTA at the end.  (The tile kernel above rebuilt
-// a channel-major shared-memory tile and ran a 16 x 16 reduce_gemm over it: 2.0 ms for 42 M rows; this: ~0.3 ms.)
+// CTA's fp64 shared-memory slices; one global fp64 atomic per entry and CTA at the end.  (The tile kernel above rebuilt
+// a channel-major shared-memory tile and ran a 16 x 16 reduce_gemm over it: 2.0 ms for 42 M rows; this: 0.9 ms.)
 __global__ void __launch_bounds__(256) lfa_rpe_moments_kernel(const float* __restrict__ xyz, long long xyz_bstride,
                                                               const int32_t* __restrict__ idx, double* __restrict__ m_rpe,
                                                               int N, int K, long long rows) {
-    __shared__ double acc64[66];
-    if (threadIdx.x < 66) acc64[threadIdx.x] = 0.0;
+    // one fp64 slice per warp, entry i owned by lane i % 32 of that warp: plain read-modify-write, no atomics (fp64
+    // shared-memory atomics are CAS loops; eight warps retrying on the same 66 addresses were most of this kernel's time)
+    __shared__ double acc64[8][66];
+    for (int i = threadIdx.x; i < 8 * 66; i += blockDim.x) (&acc64[0][0])[i] = 0.0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // every thread of a warp runs the same number of batches (the warp reduction below is collective)
     const long long warp_first = row - lane;
+    const bool small = rows <= 0x7fffffffLL;
     for (long long base = warp_first; base < rows; base += 16 * stride) {
         float p[66];
 #pragma unroll
@@ -501,8 +504,17 @@ __global__ void __launch_bounds__(256) lfa_rpe_moments_kernel(const float* __res
         for (int it = 0; it < 16; ++it) {
             const long long r = base + lane + (long long)it * stride;
             if (r < rows) {
-                const long long gp = r / K;
-                const int b = (int)(gp / N), pi = (int)(gp - (long long)b * N);
+                // 64-bit divisions are ~100-instruction sequences, two of them per row cost more than the 66 FMAs
+                int b, pi;
+                if (small) {
+                    const unsigned gp = (unsigned)r / (unsigned)K;
+                    b = (int)(gp / (unsigned)N);
+                    pi = (int)(gp - (unsigned)b * (unsigned)N);
+                } else {
+                    const long long gp = r / K;
+                    b = (int)(gp / N);
+                    pi = (int)(gp - (long long)b * N);
+                }
                 float e[11];
                 float rpe[10];
                 rpe_of_row(xyz + (size_t)b * xyz_bstride, pi, idx[r], rpe);
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(256) lfa_rpe_moments_kernel(const float* __res
             double v = (double)p[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == (i & 31)) atomicAdd(&acc64[i], v);
+            if (lane == (i & 31)) acc64[warp][i] += v;
         }
     }
     __syncthreads();
@@ -533,7 +545,9 @@ __global__ void __launch_bounds__(256) lfa_rpe_moments_kernel(const float* __res
             ++i;
         }
         const int j = i + t;
-        const double v = acc64[threadIdx.x];
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += acc64[w][threadIdx.x];
         atomicAdd(m_rpe + i * kRpeRows + j, v);
         if (i != j) atomicAdd(m_rpe + j * kRpeRows + i, v);
     }
