@@ -13,7 +13,9 @@ clouds.  Workloads (BASELINE.json `configs`):
               clouds of 40 960 points, K=16, 4 encoder levels [16,64,128,256], global batch 64 split over the
               GPUs (strong scaling; NCCL gradient all-reduce at N>1)
   train2500   (configs[1]) the same step on 8 clouds x 2 500 points (train.py:50-56 cloud size) per GPU (weak)
-  infer16k | infer64k | infer256k   (configs[2]) eval forward, global batch 32 split over the GPUs
+  infer16k | infer64k | infer256k   (configs[2]) eval forward, global batch 32 split over the GPUs (Model.infer: CUDA-graph
+                                    replay per input shape; the instrumented pass launches eagerly)
+  train40960_b8 | train40960_b16 | infer64k_b4   one rank's shard of the 8- / 4-GPU runs on ONE GPU (diagnostics)
   knn1m_k16 | knn1m_k32             (configs[4]) 1 M x 1 M exact KNN micro-benchmark (1 GPU)
   predict160k                       (configs[0]'s call, on the GPU) Model.predict of one 160 998-point LiDAR-shaped frame
                                     with the repo-default model: the UI's 250 ms budget (main.py:49)
