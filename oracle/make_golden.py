@@ -109,9 +109,21 @@ def make_input(B, N, F, seed):
     return x
 
 
-def gen_e2e(rmod):
+# settings outside the template lists of the fused kernels (any n_neighbors / layer size: modules.py:298-325, 484-500):
+# served by the row-form kernels (csrc/lfa_rows.cu); the oracle port is pinned to the reference on them as well
+E2E_ROWS = [
+    ("k8_sizes_8_24_40_n1024", dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=8, layer_sizes=[8, 24, 40],
+                                    knn="naive"), 2, 1024, 131),
+    ("k20_n1600", dict(n_classes=2, n_points=1600, n_features=0, n_neighbors=20, knn="naive"), 2, 1600, 32),
+    ("k16_sizes_16_48_96_256_n2048", dict(n_classes=2, n_points=2048, n_features=0, n_neighbors=16,
+                                          layer_sizes=[16, 48, 96, 256], knn="naive"), 1, 2048, 34),
+]
+
+
+def gen_e2e(rmod, cases=None, filename="e2e_golden.npz"):
     out = {}
-    for name, st, B, N, seed in E2E:
+    upsampler_too = cases is None
+    for name, st, B, N, seed in (E2E if cases is None else cases):
         settings = rmod.RandLANetSettings(**st)
         net = rmod.RandLANet(settings, torch.device("cpu"))
         schema = onet.state_dict_schema(st)
@@ -169,6 +181,9 @@ def gen_e2e(rmod):
                 out[f"{name}/after/{k_}"] = v.numpy()
         out[f"{name}/perm"] = perm.astype(np.int32)
 
+    if not upsampler_too:
+        np.savez_compressed(os.path.join(GOLD, filename), **out)
+        return
     # ---- UpSampler variants (modules.py:416-456) on reference module
     rng = np.random.RandomState(5)
     feat = torch.from_numpy(rng.rand(2, 5, 200, 1).astype(np.float32))
@@ -182,7 +197,7 @@ def gen_e2e(rmod):
         out[f"upsample/{ap}"] = r.numpy()
     out["upsample/feat"], out["upsample/xyz"], out["upsample/xyz_up"] = feat.numpy(), xyz.numpy(), xyz_up.numpy()
     print("upsampler variants: oracle == reference")
-    np.savez_compressed(os.path.join(GOLD, "e2e_golden.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, filename), **out)
 
 
 def gen_predict(rmod):
@@ -297,9 +312,13 @@ def main():
     build(ref=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-rows" in sys.argv:          # add the row-form fixtures without rewriting the others
+        gen_e2e(import_reference(), E2E_ROWS, "e2e_rows_golden.npz")
+        return
     gen_knn()
     rmod = import_reference()
     gen_e2e(rmod)
+    gen_e2e(rmod, E2E_ROWS, "e2e_rows_golden.npz")
     gen_predict(rmod)
     gen_loss()
     gen_feed()

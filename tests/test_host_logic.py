@@ -332,3 +332,32 @@ def test_settings_outside_the_fused_kernels():
         with pytest.raises(ValueError, match="multiples of 8"):
             modules.RandLANet(modules.RandLANetSettings(**dict(base, **kw)), dev)
     modules.RandLANet(modules.RandLANetSettings(n_neighbors=32, **base), dev)
+
+
+ROWS = {
+    "k8_sizes_8_24_40_n1024": (dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=8, layer_sizes=[8, 24, 40],
+                                    knn="naive"), 2, 1024, 131),
+    "k20_n1600": (dict(n_classes=2, n_points=1600, n_features=0, n_neighbors=20, knn="naive"), 2, 1600, 32),
+    "k16_sizes_16_48_96_256_n2048": (dict(n_classes=2, n_points=2048, n_features=0, n_neighbors=16,
+                                          layer_sizes=[16, 48, 96, 256], knn="naive"), 1, 2048, 34),
+}
+
+
+@pytest.mark.parametrize("name", list(ROWS))
+def test_oracle_vs_reference_golden_outside_fused_shapes(name):
+    """The oracle port against vectors written by the reference's own modules for settings outside the fused kernels'
+    template lists (oracle/make_golden.py E2E_ROWS): eval logits, train logits and loss — the checker of
+    tests/test_lfa_rows_gpu.py is pinned on these shapes too."""
+    g = np.load(os.path.join(GOLDEN, "e2e_rows_golden.npz"))
+    st, B, N, seed = ROWS[name]
+    sd = onet.synth_state_dict(st, seed)
+    x = torch.from_numpy(make_input(B, N, 0, seed))
+    labels = torch.from_numpy(np.random.RandomState(seed).randint(0, 2, (B, N)))
+    perm = g[f"{name}/perm"].astype(np.int64)
+    with torch.no_grad():
+        ev = onet.forward({k: v.clone() for k, v in sd.items()}, st, x, perm)
+        tr = onet.forward({k: v.clone() for k, v in sd.items()}, st, x, perm, training=True, dropout_p=0.0)
+    for got, key in ((ev, "eval_logits"), (tr, "train_logits")):
+        ref = torch.from_numpy(g[f"{name}/{key}"])
+        assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5, key
+    assert abs(float(onet.dice_loss(tr, labels)) - float(g[f"{name}/train_loss"])) < 1e-5

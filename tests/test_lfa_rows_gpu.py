@@ -3,6 +3,7 @@ route for n_neighbors / layer sizes outside the fused kernels' template lists (t
 randlanet/utils/modules.py:298-325, 484-500).  Checked against fp64 tensor ops, against the fused kernels where both
 apply, and — whole network, eval logits and one training step — against the oracle port."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -10,7 +11,8 @@ import torch
 
 from oracle import network as onet
 from test_forward_gpu import make_input, rel_err
-from test_train_gpu import _lfa_block_case
+from conftest import GOLDEN
+from test_train_gpu import _lfa_block_case, _train_step_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -154,4 +156,38 @@ def test_network_outside_fused_shapes_vs_oracle(mods, name):
         if worst < TOL:
             return
         history.append((worst, wname))
+    raise AssertionError(history)
+
+
+# the same three kinds of settings, with fixtures written by the REFERENCE's own modules (oracle/make_golden.py E2E_ROWS)
+GOLDEN_ROWS = {
+    "k8_sizes_8_24_40_n1024": (dict(n_classes=2, n_points=1024, n_features=0, n_neighbors=8, layer_sizes=[8, 24, 40],
+                                    knn="naive"), 2, 1024, 131),
+    "k20_n1600": (dict(n_classes=2, n_points=1600, n_features=0, n_neighbors=20, knn="naive"), 2, 1600, 32),
+    "k16_sizes_16_48_96_256_n2048": (dict(n_classes=2, n_points=2048, n_features=0, n_neighbors=16,
+                                          layer_sizes=[16, 48, 96, 256], knn="naive"), 1, 2048, 34),
+}
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_ROWS))
+def test_row_form_network_vs_reference_golden(mods, name):
+    """Eval logits, train-mode logits, Dice loss, every parameter gradient and the BatchNorm running statistics after one
+    step against vectors written by the reference's modules for settings outside the fused kernels' template lists.
+    A ReLU-kink flip is repeated up to three times, as in test_train_step_vs_reference_golden."""
+    modules, _, _ = mods
+    g = np.load(os.path.join(GOLDEN, "e2e_rows_golden.npz"))
+    st, B, N, seed = GOLDEN_ROWS[name]
+    net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
+    net.load_state_dict(onet.synth_state_dict(st, seed))
+    net.eval()
+    np.random.seed(seed)
+    with torch.no_grad():
+        logits = net(torch.from_numpy(make_input(B, N, 0, seed)).cuda())
+    assert rel_err(logits, torch.from_numpy(g[f"{name}/eval_logits"]).cuda()) < TOL
+    history = []
+    for _ in range(3):
+        fails = _train_step_case(mods, name, GOLDEN_ROWS, "e2e_rows_golden.npz")
+        if not fails:
+            return
+        history.append(fails)
     raise AssertionError(history)

@@ -226,11 +226,11 @@ def test_shared_mlp_eval_kernels_vs_torch(mods, M, cin, cout, act):
         assert torch.equal(v, before[k]), k
 
 
-def _train_step_case(mods, name):
+def _train_step_case(mods, name, cases=None, filename="e2e_golden.npz"):
     """One training step against the reference's golden vectors; returns the list of violated bars."""
     modules, engine, _ = mods
-    g = np.load(os.path.join(GOLDEN, "e2e_golden.npz"))
-    st, B, N, seed = E2E[name]
+    g = np.load(os.path.join(GOLDEN, filename))
+    st, B, N, seed = (E2E if cases is None else cases)[name]
     net = modules.RandLANet(modules.RandLANetSettings(**st), torch.device("cuda"))
     net.load_state_dict(onet.synth_state_dict(st, seed))
     x = torch.from_numpy(make_input(B, N, st["n_features"], seed)).cuda()
