@@ -604,8 +604,10 @@ class _SkipAndPrefixFn(torch.autograd.Function):
         if dskip is None:
             total = torch.zeros(ctx.shape, dtype=dprefix.dtype, device=dprefix.device)
         else:
-            # the fresh output of the decoder's up-sampling backward; this node is its only consumer
-            total = dskip if dskip.is_contiguous() else dskip.contiguous()
+            # In this network dskip is the fresh tensor the decoder's up-sampling backward allocated (ops.upsample_bwd) and
+            # this node is its only consumer, so the prefix gradient is accumulated into it in place; anything that is a
+            # view of other storage, or not dense, is copied first.
+            total = dskip if (dskip.is_contiguous() and dskip._base is None) else dskip.clone(memory_format=torch.contiguous_format)
         total[:, :ctx.n].add_(dprefix)
         return total, None
 
